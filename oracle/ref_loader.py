@@ -1,0 +1,80 @@
+"""Load the UNMODIFIED reference model files from /root/reference by path.
+
+TEST INFRASTRUCTURE ONLY (container-side): used by tests/golden/make_golden.py to
+generate golden vectors and by the CPU test that pins the oracle restatement
+against the real reference.  /root/reference does not exist on the GPU box, so
+nothing on the GPU path may import this module.
+
+The shims below are version-compat only (transformers 5.5 / torch 2.11 vs the
+reference's pinned transformers 4.17 / torch 1.8.1); none changes arithmetic.
+See SURVEY.md section 8(c).
+"""
+import dataclasses
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF_ROOT = os.environ.get("FROZENBILM_REFERENCE", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "model", "deberta.py"))
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_cache = {}
+
+
+def load_reference_deberta():
+    """Returns the reference's model.deberta module (with compat shims applied)."""
+    if "deberta" in _cache:
+        return _cache["deberta"]
+    if not hasattr(np, "int"):
+        np.int = int  # deberta.py:588 uses the removed alias
+    pkg = types.ModuleType("model")
+    pkg.__path__ = [os.path.join(REF_ROOT, "model")]
+    saved = sys.modules.get("model")
+    sys.modules["model"] = pkg
+    try:
+        _load("model.adapter", os.path.join(REF_ROOT, "model", "adapter.py"))
+        deb = _load("model.deberta", os.path.join(REF_ROOT, "model", "deberta.py"))
+    finally:
+        # keep our synthetic package registered under a private alias only
+        sys.modules["_ref_model_pkg"] = pkg
+        if saved is not None:
+            sys.modules["model"] = saved
+        else:
+            sys.modules.pop("model", None)
+    # shim 1: transformers>=5 init_weights needs post_init bookkeeping
+    deb.DebertaV2PreTrainedModel.init_weights = lambda self: self.apply(self._init_weights)
+    # shim 3: torch>=1.11 _softmax_backward_data takes a dtype, not a tensor
+    orig = deb._softmax_backward_data
+    deb._softmax_backward_data = lambda g, o, dim, t: orig(g, o, dim, t.dtype)
+    # shim 4: ModelOutput subclasses must be dataclasses in transformers 5
+    if not dataclasses.is_dataclass(deb.BaseModelOutput):
+        deb.BaseModelOutput = dataclasses.dataclass(deb.BaseModelOutput)
+    _cache["deberta"] = deb
+    return deb
+
+
+def build_reference_deberta(hf_config, *, max_feats, features_dim=768, ds_factor_attn=8,
+                            ds_factor_ff=8, dropout=0.0, n_ans=0, freeze_lm=True,
+                            freeze_mlm=True, ft_ln=True, freeze_last=True):
+    deb = load_reference_deberta()
+    model = deb.DebertaV2ForMaskedLM(
+        config=hf_config, max_feats=max_feats, features_dim=features_dim,
+        freeze_lm=freeze_lm, freeze_mlm=freeze_mlm, ds_factor_attn=ds_factor_attn,
+        ds_factor_ff=ds_factor_ff, ft_ln=ft_ln, dropout=dropout, n_ans=n_ans,
+        freeze_last=freeze_last)
+    return model
