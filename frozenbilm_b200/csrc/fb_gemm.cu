@@ -1,0 +1,496 @@
+// fb_gemm: persistent, warp-specialised bf16 GEMM for sm_100a.
+//
+//   D[b] = epilogue(alpha * A[b] (M x K) * B[b]^T (N x K)),  fp32 accumulation in TMEM.
+//
+// Roles inside one 256-thread CTA (one CTA per SM, persistent over output tiles):
+//   warp 0      TMA producer: cp.async.bulk.tensor (128B-swizzled boxes) -> smem ring
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma 128 x BN x 16, commits to mbarriers
+//   warp 2      TMEM allocator (2 accumulator stages so the epilogue of tile i overlaps tile i+1)
+//   warps 4-7   epilogue: tcgen05.ld (lane = output row) -> bias/activation/aux/residual -> global
+//
+// Both operands may be K-major (nn.Linear layout) or MN-major (the transposed view), selected in
+// the UMMA instruction/smem descriptors, so dX = dY.W and dW = dY^T.X need no explicit transposes.
+// Replaces the nn.Linear/bmm call sites listed in include/frozenbilm_b200.h.
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/frozenbilm_b200.h"
+#include "fb_common.cuh"
+
+namespace fb {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+static constexpr int A_STAGE_BYTES = BM * BK * 2;
+static constexpr int NUM_THREADS = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192) ? 5 : (BN == 128) ? 6 : 8;
+  static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  int M, N, K, batch;
+  int mblocks, nblocks, kblocks, split_k, kblocks_per_split, total_tiles;
+  void* D; long long ldd, stride_d; int d_f32;
+  float alpha;
+  const float* bias;
+  __nv_bfloat16* D_pre; long long ld_pre;
+  int act;
+  const __nv_bfloat16* aux; long long ld_aux; int aux_op;
+  const float* resid; long long ld_resid;
+  int accumulate;
+};
+
+__device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int& split, int& b,
+                                            int& mb, int& nb) {
+  nb = tile % p.nblocks;
+  int t = tile / p.nblocks;
+  mb = t % p.mblocks;
+  t /= p.mblocks;
+  b = t % p.batch;
+  split = t / p.batch;
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int row, int col0,
+                                               const uint32_t (&acc)[32], bool first_split) {
+  if (row >= p.M || col0 >= p.N) return;
+  const bool full = (col0 + 32 <= p.N);
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * p.alpha;
+  if (first_split) {
+    if (p.bias) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (full || col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+    }
+    if (p.D_pre) {
+      __nv_bfloat16* dst = p.D_pre + (long long)row * p.ld_pre + col0;
+      if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 q = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                               pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+          reinterpret_cast<uint4*>(dst)[i] = q;
+        }
+      } else {
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < p.N) dst[i] = __float2bfloat16_rn(v[i]);
+      }
+    }
+    if (p.act == FB_ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    } else if (p.act == FB_ACT_RELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+    }
+    if (p.aux_op != FB_AUX_NONE) {
+      const __nv_bfloat16* src = p.aux + (long long)row * p.ld_aux + col0;
+      float a[32];
+      if (full && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 q = __ldg(reinterpret_cast<const uint4*>(src) + i);
+          float2 f0 = unpack_bf16(q.x), f1 = unpack_bf16(q.y), f2 = unpack_bf16(q.z), f3 = unpack_bf16(q.w);
+          a[8 * i] = f0.x; a[8 * i + 1] = f0.y; a[8 * i + 2] = f1.x; a[8 * i + 3] = f1.y;
+          a[8 * i + 4] = f2.x; a[8 * i + 5] = f2.y; a[8 * i + 6] = f3.x; a[8 * i + 7] = f3.y;
+        }
+      } else {
+        for (int i = 0; i < 32; ++i) a[i] = (col0 + i < p.N) ? __bfloat162float(src[i]) : 0.0f;
+      }
+      if (p.aux_op == FB_AUX_MUL_GELU_GRAD) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= gelu_erf_grad(a[i]);
+      } else if (p.aux_op == FB_AUX_MUL_RELU_MASK) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = (a[i] > 0.0f) ? v[i] : 0.0f;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += a[i];
+      }
+    }
+    if (p.resid) {
+      const float* src = p.resid + (long long)row * p.ld_resid + col0;
+      if (full && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 q = __ldg(reinterpret_cast<const float4*>(src) + i);
+          v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+        }
+      } else {
+        for (int i = 0; i < 32; ++i)
+          if (col0 + i < p.N) v[i] += src[i];
+      }
+    }
+  }
+  if (p.d_f32) {
+    float* dst = reinterpret_cast<float*>(p.D) + (long long)b * p.stride_d + (long long)row * p.ldd + col0;
+    if (p.split_k > 1) {
+      for (int i = 0; i < 32; ++i)
+        if (full || col0 + i < p.N) atomicAdd(dst + i, v[i]);
+    } else if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 q = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        if (p.accumulate) {
+          float4 o = reinterpret_cast<float4*>(dst)[i];
+          q.x += o.x; q.y += o.y; q.z += o.z; q.w += o.w;
+        }
+        reinterpret_cast<float4*>(dst)[i] = q;
+      }
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) dst[i] = p.accumulate ? dst[i] + v[i] : v[i];
+    }
+  } else {
+    __nv_bfloat16* dst =
+        reinterpret_cast<__nv_bfloat16*>(p.D) + (long long)b * p.stride_d + (long long)row * p.ldd + col0;
+    if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 q = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                             pack_bf16(v[8 * i + 4], v[8 * i + 5]), pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+        reinterpret_cast<uint4*>(dst)[i] = q;
+      }
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) dst[i] = __float2bfloat16_rn(v[i]);
+    }
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+            const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one_sync()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int split, b, mb, nb;
+        decode_tile(p, tile, split, b, mb, nb);
+        const int m0 = mb * BM, n0 = nb * BN;
+        const int k_begin = split * p.kblocks_per_split;
+        const int k_end = min(k_begin + p.kblocks_per_split, p.kblocks);
+        for (int kb = k_begin; kb < k_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+          uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
+          if constexpr (!A_MN) {
+            tma_load_3d(sa, &map_a, &full_bar[stage], kb * BK, m0, b);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c)
+              tma_load_3d(sa + c * (64 * BK * 2), &map_a, &full_bar[stage], m0 + c * 64, kb * BK, b);
+          }
+          if constexpr (!B_MN) {
+            tma_load_3d(sb, &map_b, &full_bar[stage], kb * BK, n0, b);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_3d(sb + c * (64 * BK * 2), &map_b, &full_bar[stage], n0 + c * 64, kb * BK, b);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      // K-major: rows of 128 B, 8-row groups 1024 B apart (SBO); one UMMA_K = 32 B inside the row.
+      // MN-major: [64 mn x 64 k] chunks of 8192 B (LBO between chunks), 8-k groups 1024 B apart
+      // (SBO); one UMMA_K = 16 k-rows = 2048 B.
+      constexpr uint32_t A_LBO = A_MN ? 64 * BK * 2 : 16, B_LBO = B_MN ? 64 * BK * 2 : 16;
+      constexpr uint32_t A_KSTEP = A_MN ? 2048 : 32, B_KSTEP = B_MN ? 2048 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        int split, b, mb, nb;
+        decode_tile(p, tile, split, b, mb, nb);
+        const int k_begin = split * p.kblocks_per_split;
+        const int k_end = min(k_begin + p.kblocks_per_split, p.kblocks);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+        for (int kb = k_begin; kb < k_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(sa + k * A_KSTEP, A_LBO, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(sb + k * B_KSTEP, B_LBO, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > k_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int wq = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      int split, b, mb, nb;
+      decode_tile(p, tile, split, b, mb, nb);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int row = mb * BM + wq * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * Cfg::ACC_STRIDE;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t acc[32];
+        tmem_ld_32x32(taddr + c * 32, acc);
+        tmem_ld_wait();
+        epilogue_chunk<BN>(p, b, row, nb * BN + c * 32, acc, split == 0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int n = -1;
+  if (n < 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+    n = prop.multiProcessorCount;
+  }
+  return n;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+  });
+  return fn;
+}
+
+// 3-D bf16 tensor map {inner, rows, batch} with a {64, box_rows, 1} box and 128B swizzle.
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch,
+                   uint64_t ld_elems, uint64_t batch_stride_elems, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  FB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  FB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand must be 16-byte aligned");
+  FB_REQUIRE((ld_elems * 2) % 16 == 0, "TMA operand leading dimension must be a multiple of 8 elements (got %llu)",
+             (unsigned long long)ld_elems);
+  if (batch <= 1) { batch = 1; batch_stride_elems = ld_elems * rows; }
+  FB_REQUIRE((batch_stride_elems * 2) % 16 == 0, "TMA batch stride must be a multiple of 8 elements");
+  cuuint64_t dims[3] = {inner, rows, batch};
+  cuuint64_t strides[2] = {ld_elems * 2, batch_stride_elems * 2};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu rows=%llu ld=%llu)",
+             (int)r, (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)ld_elems);
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  auto kern = gemm_kernel<BN, A_MN, B_MN>;
+  if (!configured) {
+    FB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  int grid = std::min(p.total_tiles, num_sms());
+  FB_REQUIRE(grid > 0, "no CUDA device / empty GEMM");
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+  count_launch();
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p,
+                          cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(ma, mb, p, st);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(ma, mb, p, st);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(ma, mb, p, st);
+  return launch_gemm<BN, true, true>(ma, mb, p, st);
+}
+
+static int pick_block_n(int M, int N, int batch, int split_k) {
+  const int nsm = std::max(1, num_sms());
+  const int mblocks = (M + BM - 1) / BM;
+  int best = 64;
+  double best_cost = 1e30;
+  const int cands[4] = {256, 192, 128, 64};
+  for (int bn : cands) {
+    const long long tiles = (long long)mblocks * ((N + bn - 1) / bn) * batch * split_k;
+    const long long waves = (tiles + nsm - 1) / nsm;
+    const double cost = (double)waves * (bn + 24);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+int gemm(const fb_gemm_args* a, cudaStream_t st) {
+  FB_REQUIRE(a != nullptr, "fb_gemm: null args");
+  FB_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->batch >= 1, "fb_gemm: bad shape M=%d N=%d K=%d batch=%d", a->M,
+             a->N, a->K, a->batch);
+  FB_REQUIRE(a->A && a->B && a->D, "fb_gemm: null operand");
+  const int split_k = a->split_k > 1 ? a->split_k : 1;
+  if (split_k > 1) FB_REQUIRE(a->d_dtype == FB_DT_F32, "fb_gemm: split_k needs an fp32 output");
+  if (a->accumulate) FB_REQUIRE(a->d_dtype == FB_DT_F32, "fb_gemm: accumulate needs an fp32 output");
+  if (a->batch > 1)
+    FB_REQUIRE(!a->D_pre && !a->aux && !a->resid, "fb_gemm: batched mode supports bias/act only");
+  int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N, a->batch, split_k);
+  FB_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, "fb_gemm: block_n must be 64/128/192/256");
+
+  CUtensorMap ma, mb;
+  int rc;
+  if (!a->a_mn_major)
+    rc = make_tmap_bf16(&ma, a->A, a->K, a->M, a->batch, a->lda, a->stride_a, BM);
+  else
+    rc = make_tmap_bf16(&ma, a->A, a->M, a->K, a->batch, a->lda, a->stride_a, BK);
+  if (rc) return rc;
+  if (!a->b_mn_major)
+    rc = make_tmap_bf16(&mb, a->B, a->K, a->N, a->batch, a->ldb, a->stride_b, bn);
+  else
+    rc = make_tmap_bf16(&mb, a->B, a->N, a->K, a->batch, a->ldb, a->stride_b, BK);
+  if (rc) return rc;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->M; p.N = a->N; p.K = a->K; p.batch = a->batch;
+  p.mblocks = (a->M + BM - 1) / BM;
+  p.nblocks = (a->N + bn - 1) / bn;
+  p.kblocks = (a->K + BK - 1) / BK;
+  p.split_k = std::min(split_k, p.kblocks);
+  p.kblocks_per_split = (p.kblocks + p.split_k - 1) / p.split_k;
+  p.split_k = (p.kblocks + p.kblocks_per_split - 1) / p.kblocks_per_split;  // no empty splits
+  p.total_tiles = p.mblocks * p.nblocks * p.batch * p.split_k;
+  p.D = a->D; p.ldd = a->ldd; p.stride_d = a->stride_d; p.d_f32 = (a->d_dtype == FB_DT_F32);
+  p.alpha = a->alpha;
+  p.bias = a->bias;
+  p.D_pre = reinterpret_cast<__nv_bfloat16*>(a->D_pre); p.ld_pre = a->ld_pre;
+  p.act = a->act;
+  p.aux = reinterpret_cast<const __nv_bfloat16*>(a->aux); p.ld_aux = a->ld_aux;
+  p.aux_op = a->aux ? a->aux_op : FB_AUX_NONE;
+  p.resid = a->resid; p.ld_resid = a->ld_resid;
+  p.accumulate = (a->accumulate || split_k > 1) ? 1 : 0;
+
+  switch (bn) {
+    case 64: return dispatch_major<64>(a->a_mn_major, a->b_mn_major, ma, mb, p, st);
+    case 128: return dispatch_major<128>(a->a_mn_major, a->b_mn_major, ma, mb, p, st);
+    case 192: return dispatch_major<192>(a->a_mn_major, a->b_mn_major, ma, mb, p, st);
+    default: return dispatch_major<256>(a->a_mn_major, a->b_mn_major, ma, mb, p, st);
+  }
+}
+
+}  // namespace fb
+
+extern "C" {
+const char* fb_last_error(void) { return fb::last_error(); }
+int fb_abi_version(void) { return FB_ABI_VERSION; }
+long long fb_launch_count(void) { return fb::g_launches.load(); }
+int fb_gemm(const fb_gemm_args* args, void* stream) { return fb::gemm(args, reinterpret_cast<cudaStream_t>(stream)); }
+}
