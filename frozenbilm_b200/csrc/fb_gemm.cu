@@ -391,6 +391,28 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t r
   return 0;
 }
 
+int make_tmap_bf16_nd(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
+                      const uint64_t* strides_elems, const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  FB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  FB_REQUIRE(rank >= 2 && rank <= 4, "tensor map rank must be 2..4");
+  FB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand must be 16-byte aligned");
+  cuuint64_t d[4];
+  cuuint64_t st[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i < rank - 1; ++i) {
+    st[i] = strides_elems[i] * 2;
+    FB_REQUIRE(st[i] % 16 == 0, "TMA stride %d (%llu bytes) must be a multiple of 16 bytes", i,
+               (unsigned long long)st[i]);
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), d, st, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(rank %d) failed with CUresult %d", rank, (int)r);
+  return 0;
+}
+
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;

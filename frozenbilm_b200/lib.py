@@ -39,6 +39,21 @@ class GemmArgs(C.Structure):
     ]
 
 
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("L", C.c_int), ("h", C.c_int),
+        ("Q", C.c_void_p), ("ldq", C.c_longlong),
+        ("K", C.c_void_p), ("ldk", C.c_longlong),
+        ("V", C.c_void_p), ("ldv", C.c_longlong),
+        ("PKrel", C.c_void_p), ("PQrel", C.c_void_p), ("rel_rows", C.c_int), ("rel_off", C.c_int),
+        ("mask", C.c_void_p),
+        ("ctx", C.c_void_p), ("ldc", C.c_longlong),
+        ("lse", C.c_void_p),
+        ("scale", C.c_float),
+        ("dropout_p", C.c_float), ("seed", C.c_ulonglong), ("offset", C.c_ulonglong),
+    ]
+
+
 _lib = None
 
 
@@ -64,7 +79,7 @@ def load() -> C.CDLL:
 
 # every symbol include/frozenbilm_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "fb_last_error", "fb_abi_version", "fb_launch_count", "fb_gemm",
+    "fb_last_error", "fb_abi_version", "fb_launch_count", "fb_gemm", "fb_attn_fwd", "fb_build_rel_tables",
 ]
 
 
@@ -135,3 +150,42 @@ def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, a_mn_major=False,
     args.block_n = int(block_n)
     check(load().fb_gemm(C.byref(args), stream_ptr()), "fb_gemm")
     return D
+
+
+def rel_table_geometry(L: int):
+    """(rel_rows, rel_off) of the per-relative-position tables for sequence length L."""
+    lpad = (L + 127) // 128 * 128
+    return 2 * lpad + 8, lpad
+
+
+def build_rel_tables(pqk: torch.Tensor, bucket_of_rel: torch.Tensor, L: int, h: int, out_pq=None, out_pk=None):
+    """pqk: bf16 [2S, 2H] (PQ | PK).  Returns (PQrel, PKrel) bf16 [h, rel_rows, 64]."""
+    H = pqk.shape[1] // 2
+    rel_rows, rel_off = rel_table_geometry(L)
+    if out_pq is None:
+        out_pq = torch.empty(h, rel_rows, 64, device=pqk.device, dtype=torch.bfloat16)
+    if out_pk is None:
+        out_pk = torch.empty(h, rel_rows, 64, device=pqk.device, dtype=torch.bfloat16)
+    assert bucket_of_rel.dtype == torch.int32 and bucket_of_rel.numel() == 1023
+    check(load().fb_build_rel_tables(_ptr(pqk), C.c_longlong(pqk.stride(0)), H, h, _ptr(bucket_of_rel), rel_rows,
+                                     rel_off, L, _ptr(out_pq), _ptr(out_pk), stream_ptr()), "fb_build_rel_tables")
+    return out_pq, out_pk
+
+
+def attn_fwd(Q, K, V, PKrel, PQrel, mask_u8, ctx, lse, *, B, L, h, scale, dropout_p=0.0, seed=0, offset=0):
+    """Q/K/V: bf16 2-D views [B*L, >= h*64] (row pitch = stride(0)); ctx: bf16 [B*L, H]; lse: fp32 [B, h, L]."""
+    rel_rows, rel_off = rel_table_geometry(L)
+    assert PKrel.shape[1] == rel_rows and mask_u8.dtype == torch.uint8 and lse.dtype == torch.float32
+    a = AttnArgs()
+    a.B, a.L, a.h = B, L, h
+    a.Q, a.ldq = _ptr(Q), Q.stride(0)
+    a.K, a.ldk = _ptr(K), K.stride(0)
+    a.V, a.ldv = _ptr(V), V.stride(0)
+    a.PKrel, a.PQrel, a.rel_rows, a.rel_off = _ptr(PKrel), _ptr(PQrel), rel_rows, rel_off
+    a.mask = _ptr(mask_u8)
+    a.ctx, a.ldc = _ptr(ctx), ctx.stride(0)
+    a.lse = _ptr(lse)
+    a.scale = float(scale)
+    a.dropout_p, a.seed, a.offset = float(dropout_p), int(seed), int(offset)
+    check(load().fb_attn_fwd(C.byref(a), stream_ptr()), "fb_attn_fwd")
+    return ctx, lse

@@ -63,6 +63,39 @@ typedef struct fb_gemm_args {
 
 int fb_gemm(const fb_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * fb_attn_fwd: fused disentangled self-attention forward for one layer pass (head_dim = 64).
+ * Replaces DisentangledSelfAttention.forward (deberta.py:717-818) + disentangled_attention_bias
+ * (:820-947) + XSoftmax (:100-138) + attention-prob dropout (:796):
+ *   s[b,h,i,j] = (Q_i.K_j + Q_i.PKrel[h, i-j] + K_j.PQrel[h, i-j]) * scale ; masked softmax ; P.V
+ * Q/K/V: bf16, token row (b*L + i) with pitch ld*, head hh at columns [hh*64, hh*64+64).
+ * PKrel/PQrel: bf16 [h, rel_rows, 64] tables indexed by relative position, row = (i - j) + rel_off
+ * (fb_build_rel_tables); mask: uint8 [B, L] (cat(video_mask, attention_mask)); M[b,i,j] = m_i*m_j.
+ * ctx: bf16 [B*L, ldc]; lse: fp32 [B, h, L] = log2-domain log-sum-exp of the scaled scores
+ * (+inf for fully masked rows) for the backward.  Dropout masks come from Philox(seed, offset).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct fb_attn_args {
+  int B, L, h;
+  const void* Q; long long ldq;
+  const void* K; long long ldk;
+  const void* V; long long ldv;
+  const void* PKrel; const void* PQrel; int rel_rows; int rel_off;
+  const unsigned char* mask;
+  void* ctx; long long ldc;
+  float* lse;
+  float scale;
+  float dropout_p; unsigned long long seed; unsigned long long offset;
+} fb_attn_args;
+
+int fb_attn_fwd(const fb_attn_args* args, void* stream);
+
+/* Expands pqk = Linear_{q|k}(rel_emb) ([2S, 2H] bf16: PQ in cols [0,H), PK in [H,2H); deberta.py:847-853)
+ * into the per-relative-position tables used above: out[hh][row] = pqk[bucket_of_rel[row - rel_off + 511]].
+ * bucket_of_rel: int32 [1023] = clamp(bucket(rel) + S, 0, 2S-1) for rel in [-511, 511]
+ * (make_log_bucket_position, deberta.py:578-589).  Rows with |rel| >= L are zero. */
+int fb_build_rel_tables(const void* pqk, long long ld, int H, int h, const int* bucket_of_rel, int rel_rows,
+                        int rel_off, int L, void* out_pq, void* out_pk, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
