@@ -37,23 +37,11 @@ struct AttnParams {
   const uint8_t* mask;
   __nv_bfloat16* ctx; long long ldc;
   float* lse;
+  float* s_out; int lp;   // optional [B, h, L, lp] fp32 copy of the masked, scaled scores (log2 domain)
   float scale_log2;
   float inv_keep; uint32_t drop_thresh16;  // keep iff rnd16 >= thresh
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
 };
-
-// 8 Bernoulli(keep) decisions for columns [8*jgroup, 8*jgroup+8) of score row `rowid`.
-__device__ __forceinline__ uint32_t dropout_keep8(uint32_t rowid, uint32_t jgroup, uint32_t thresh16,
-                                                  uint32_t seed_lo, uint32_t seed_hi, uint32_t off_lo,
-                                                  uint32_t off_hi) {
-  const uint4 r = philox4x32(rowid, jgroup, off_lo, off_hi, seed_lo, seed_hi);
-  uint32_t m = 0;
-  m |= ((r.x & 0xFFFF) >= thresh16) << 0; m |= ((r.x >> 16) >= thresh16) << 1;
-  m |= ((r.y & 0xFFFF) >= thresh16) << 2; m |= ((r.y >> 16) >= thresh16) << 3;
-  m |= ((r.z & 0xFFFF) >= thresh16) << 4; m |= ((r.z >> 16) >= thresh16) << 5;
-  m |= ((r.w & 0xFFFF) >= thresh16) << 6; m |= ((r.w >> 16) >= thresh16) << 7;
-  return m;
-}
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -241,6 +229,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           }
         }
         tmem_st_32x32(lane_base + TM_S + 32 * q, v);
+        if (p.s_out != nullptr && i < p.L) {
+          float4* dst = reinterpret_cast<float4*>(p.s_out + (((long long)b * p.h + hh) * p.L + i) * p.lp + j0 + 32 * q);
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            dst[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                 __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+        }
       }
       tmem_st_wait();
       const float m_new = fmaxf(m_run, mblk);
@@ -337,6 +332,108 @@ __global__ void build_rel_tables_kernel(const __nv_bfloat16* __restrict__ pqk, l
   *reinterpret_cast<uint32_t*>(out + threadIdx.x * 2) = val;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Attention backward, stage 1 (one CTA per score row): from the saved scores s2 (log2 domain), the
+// row log-sum-exp and dP = dO.V^T, rebuild P and form
+//   dS = P * (dropout_bwd(dP) - D) * scale,  D = rowsum(dO * O)         (softmax + XDropout backward,
+//   deberta.py:134-138, 188-194), written as bf16 in three layouts: dS[b,h,i,j], the dropped
+//   probabilities Pd[b,h,i,j] (for dV), and Z1[h, b*L+i, (i-j)+rel_off] = dS (the c2p term regrouped by
+//   relative position, so that dQ += Z1 . PKrel and dPKrel = Z1^T . Q are plain GEMMs).
+// ---------------------------------------------------------------------------------------------
+struct AttnBwdParams {
+  int B, L, h, lp, rel_rows, rel_off;
+  const float* s2; const float* lse; const __nv_bfloat16* dp; const __nv_bfloat16* ctx; const __nv_bfloat16* dctx;
+  long long ldc;
+  __nv_bfloat16* ds; __nv_bfloat16* pd; __nv_bfloat16* z1;
+  float scale; DropSpec drop;
+};
+
+__global__ void __launch_bounds__(128) attn_bwd_ds_kernel(const AttnBwdParams p) {
+  __shared__ float sds[512];
+  __shared__ float sD;
+  const int i = blockIdx.x, hh = blockIdx.y, b = blockIdx.z;
+  const long long row = ((long long)b * p.h + hh) * p.L + i;
+  const int tid = threadIdx.x;
+  if (tid < 32) {
+    const __nv_bfloat16* o = p.ctx + ((long long)b * p.L + i) * p.ldc + hh * 64;
+    const __nv_bfloat16* g = p.dctx + ((long long)b * p.L + i) * p.ldc + hh * 64;
+    const float2 o2 = unpack_bf16(*reinterpret_cast<const uint32_t*>(o + 2 * tid));
+    const float2 g2 = unpack_bf16(*reinterpret_cast<const uint32_t*>(g + 2 * tid));
+    float d = o2.x * g2.x + o2.y * g2.y;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+    if (tid == 0) sD = d;
+  }
+  __syncthreads();
+  const float D = sD, lse = p.lse[row];
+  const uint32_t rowid = (uint32_t)row;
+  for (int j = tid; j < p.lp; j += 128) {
+    float ds = 0.0f, pd = 0.0f;
+    if (j < p.L) {
+      const float s = p.s2[row * p.lp + j];
+      const float pr = exp2f(s - lse);   // s = -inf (masked) or lse = +inf (dead row) -> 0
+      float dpv = __bfloat162float(p.dp[row * p.lp + j]);
+      pd = pr;
+      if (p.drop.thresh16) {
+        const uint32_t keep = drop_keep8(p.drop, rowid, (uint32_t)j >> 3);
+        const float f = ((keep >> (j & 7)) & 1) ? p.drop.inv_keep : 0.0f;
+        dpv *= f;
+        pd *= f;
+      }
+      ds = (pr > 0.0f) ? pr * (dpv - D) * p.scale : 0.0f;
+    }
+    sds[j] = ds;
+    p.ds[row * p.lp + j] = __float2bfloat16_rn(ds);
+    p.pd[row * p.lp + j] = __float2bfloat16_rn(pd);
+  }
+  __syncthreads();
+  __nv_bfloat16* z = p.z1 + ((long long)hh * p.B * p.L + (long long)b * p.L + i) * p.rel_rows;
+  for (int r = tid; r < p.rel_rows; r += 128) {
+    const int j = i - (r - p.rel_off);
+    z[r] = __float2bfloat16_rn((j >= 0 && j < p.L) ? sds[j] : 0.0f);
+  }
+}
+
+// Stage 2: Z2[h, b*L+j, (i-j)+rel_off] = dS[b,h,i,j]  (the p2c term regrouped by relative position:
+// dK += Z2 . PQrel, dPQrel = Z2^T . K).  One CTA per (b, h, 32-key stripe); the stripe is transposed
+// through shared memory so that both the dS reads and the Z2 writes are contiguous.
+__global__ void __launch_bounds__(256) attn_bwd_z2_kernel(const __nv_bfloat16* __restrict__ ds, int B, int L, int h,
+                                                          int lp, int rel_rows, int rel_off,
+                                                          __nv_bfloat16* __restrict__ z2) {
+  extern __shared__ __nv_bfloat16 tile[];   // [L][34]
+  const int j0 = blockIdx.x * 32, hh = blockIdx.y, b = blockIdx.z;
+  const long long base = ((long long)b * h + hh) * L;
+  for (int idx = threadIdx.x; idx < L * 32; idx += 256) {
+    const int i = idx >> 5, jj = idx & 31;
+    tile[i * 34 + jj] = (j0 + jj < L) ? ds[(base + i) * lp + j0 + jj] : __float2bfloat16_rn(0.0f);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int jj = warp; jj < 32; jj += 8) {
+    const int j = j0 + jj;
+    if (j >= L) break;
+    __nv_bfloat16* z = z2 + ((long long)hh * B * L + (long long)b * L + j) * rel_rows;
+    for (int r = lane; r < rel_rows; r += 32) {
+      const int i = j + (r - rel_off);
+      z[r] = (i >= 0 && i < L) ? tile[i * 34 + jj] : __float2bfloat16_rn(0.0f);
+    }
+  }
+}
+
+// Stage 3: fold the per-relative-position gradients back onto the 2S bucket rows:
+//   out[bucket_of_rel[rel], t*H + hh*64 + k] += g_t[hh, rel + rel_off, k]   (t = 0: dPQ, t = 1: dPK)
+__global__ void rel_to_bucket_kernel(const float* __restrict__ gpq, const float* __restrict__ gpk, int H, int h,
+                                     const int* __restrict__ bucket_of_rel, int rel_rows, int rel_off, int L,
+                                     float* __restrict__ out, long long ldo) {
+  const int row = blockIdx.x, hh = blockIdx.y, t = blockIdx.z;
+  const int rel = row - rel_off;
+  if (rel <= -L || rel >= L) return;
+  const int bucket = bucket_of_rel[rel + 511];
+  const float* g = (t == 0 ? gpq : gpk) + ((long long)hh * rel_rows + row) * 64;
+  atomicAdd(out + (long long)bucket * ldo + t * H + hh * 64 + threadIdx.x, g[threadIdx.x]);
+}
+
 static int make_qkv_map(CUtensorMap* m, const void* ptr, long long ld, int B, int L, int h) {
   const uint64_t dims[4] = {64, (uint64_t)h, (uint64_t)L, (uint64_t)B};
   const uint64_t strides[3] = {64, (uint64_t)ld, (uint64_t)ld * L};
@@ -369,6 +466,7 @@ int attn_fwd(const fb_attn_args* a, cudaStream_t st) {
   p.mask = a->mask;
   p.ctx = reinterpret_cast<__nv_bfloat16*>(a->ctx); p.ldc = a->ldc;
   p.lse = a->lse;
+  p.s_out = a->s_out; p.lp = lpad;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   if (a->dropout_p > 0.0f) {
     FB_REQUIRE(a->dropout_p < 1.0f, "fb_attn_fwd: dropout_p must be < 1");
@@ -404,9 +502,48 @@ int build_rel_tables(const void* pqk, long long ld, int H, int h, const int* buc
   return 0;
 }
 
+int attn_bwd_prep(const fb_attn_bwd_prep_args* a, cudaStream_t st) {
+  FB_REQUIRE(a && a->s2 && a->lse && a->dp && a->ctx && a->dctx && a->ds && a->pd && a->z1 && a->z2,
+             "fb_attn_bwd_prep: null arg");
+  FB_REQUIRE(a->L > 0 && a->L <= 512 && a->lp >= a->L && a->lp <= 512, "fb_attn_bwd_prep: bad L/lp");
+  AttnBwdParams p;
+  p.B = a->B; p.L = a->L; p.h = a->h; p.lp = a->lp; p.rel_rows = a->rel_rows; p.rel_off = a->rel_off;
+  p.s2 = a->s2; p.lse = a->lse; p.dp = (const __nv_bfloat16*)a->dp; p.ctx = (const __nv_bfloat16*)a->ctx;
+  p.dctx = (const __nv_bfloat16*)a->dctx; p.ldc = a->ldc;
+  p.ds = (__nv_bfloat16*)a->ds; p.pd = (__nv_bfloat16*)a->pd; p.z1 = (__nv_bfloat16*)a->z1;
+  p.scale = a->scale; p.drop = make_drop(a->dropout_p, a->seed, a->offset);
+  attn_bwd_ds_kernel<<<dim3(a->L, a->h, a->B), 128, 0, st>>>(p);
+  count_launch();
+  FB_CHECK_CUDA(cudaGetLastError());
+  const int smem = a->L * 34 * 2;
+  attn_bwd_z2_kernel<<<dim3((a->L + 31) / 32, a->h, a->B), 256, smem, st>>>(
+      (const __nv_bfloat16*)a->ds, a->B, a->L, a->h, a->lp, a->rel_rows, a->rel_off, (__nv_bfloat16*)a->z2);
+  count_launch();
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int rel_to_bucket(const float* gpq, const float* gpk, int H, int h, const int* bucket_of_rel, int rel_rows,
+                  int rel_off, int L, float* out, long long ldo, cudaStream_t st) {
+  FB_REQUIRE(gpq && gpk && bucket_of_rel && out && H == h * 64, "fb_rel_to_bucket: bad args");
+  rel_to_bucket_kernel<<<dim3(rel_rows, h, 2), 64, 0, st>>>(gpq, gpk, H, h, bucket_of_rel, rel_rows, rel_off, L, out,
+                                                          ldo);
+  count_launch();
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace fb
 
 extern "C" {
+int fb_attn_bwd_prep(const fb_attn_bwd_prep_args* args, void* stream) {
+  return fb::attn_bwd_prep(args, reinterpret_cast<cudaStream_t>(stream));
+}
+int fb_rel_to_bucket(const float* gpq, const float* gpk, int H, int h, const int* bucket_of_rel, int rel_rows,
+                     int rel_off, int L, float* out, long long ldo, void* stream) {
+  return fb::rel_to_bucket(gpq, gpk, H, h, bucket_of_rel, rel_rows, rel_off, L, out, ldo,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
 int fb_attn_fwd(const fb_attn_args* args, void* stream) { return fb::attn_fwd(args, reinterpret_cast<cudaStream_t>(stream)); }
 int fb_build_rel_tables(const void* pqk, long long ld, int H, int h, const int* bucket_of_rel, int rel_rows,
                         int rel_off, int L, void* out_pq, void* out_pk, void* stream) {

@@ -289,4 +289,36 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c
   return make_uint4(c0, c1, c2, c3);
 }
 
+// 8 Bernoulli(keep) decisions (bit e = keep element 8*group+e of row `rowid`), 16-bit resolution:
+// keep iff rnd16 >= thresh16 with thresh16 = round(p * 65536).
+__device__ __forceinline__ uint32_t dropout_keep8(uint32_t rowid, uint32_t group, uint32_t thresh16,
+                                                  uint32_t seed_lo, uint32_t seed_hi, uint32_t off_lo,
+                                                  uint32_t off_hi) {
+  const uint4 r = philox4x32(rowid, group, off_lo, off_hi, seed_lo, seed_hi);
+  uint32_t m = 0;
+  m |= ((r.x & 0xFFFF) >= thresh16) << 0; m |= ((r.x >> 16) >= thresh16) << 1;
+  m |= ((r.y & 0xFFFF) >= thresh16) << 2; m |= ((r.y >> 16) >= thresh16) << 3;
+  m |= ((r.z & 0xFFFF) >= thresh16) << 4; m |= ((r.z >> 16) >= thresh16) << 5;
+  m |= ((r.w & 0xFFFF) >= thresh16) << 6; m |= ((r.w >> 16) >= thresh16) << 7;
+  return m;
+}
+
+// Host-side description of one dropout site (plain data, passed by value into kernels).
+struct DropSpec {
+  uint32_t thresh16;  // 0 = disabled
+  float inv_keep;
+  uint32_t seed_lo, seed_hi, off_lo, off_hi;
+};
+inline DropSpec make_drop(float p, unsigned long long seed, unsigned long long offset) {
+  DropSpec d;
+  d.thresh16 = (p > 0.0f) ? (uint32_t)(p * 65536.0f + 0.5f) : 0u;
+  d.inv_keep = (p > 0.0f) ? 1.0f / (1.0f - p) : 1.0f;
+  d.seed_lo = (uint32_t)seed; d.seed_hi = (uint32_t)(seed >> 32);
+  d.off_lo = (uint32_t)offset; d.off_hi = (uint32_t)(offset >> 32);
+  return d;
+}
+__device__ __forceinline__ uint32_t drop_keep8(const DropSpec& d, uint32_t rowid, uint32_t group) {
+  return dropout_keep8(rowid, group, d.thresh16, d.seed_lo, d.seed_hi, d.off_lo, d.off_hi);
+}
+
 }  // namespace fb

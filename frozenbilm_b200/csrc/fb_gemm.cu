@@ -41,7 +41,11 @@ struct GemmCfg {
 };
 
 struct GemmParams {
-  int M, N, K, batch;
+  int M, N, K, batch, batch_inner;
+  int a_bi_mul, a_bo_mul, b_bi_mul, b_bo_mul;  // 0 = operand broadcast over that batch level
+  long long stride_d_in;
+  const uint8_t* rowmask;
+  DropSpec drop; int drop_pos;
   int mblocks, nblocks, kblocks, split_k, kblocks_per_split, total_tiles;
   void* D; long long ldd, stride_d; int d_f32;
   float alpha;
@@ -59,8 +63,17 @@ __device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int& 
   int t = tile / p.nblocks;
   mb = t % p.mblocks;
   t /= p.mblocks;
-  b = t % p.batch;
+  b = t % p.batch;   // combined batch index: outer * batch_inner + inner
   split = t / p.batch;
+}
+
+__device__ __forceinline__ void apply_dropout32(const DropSpec& d, int row, int col0, float (&v)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint32_t keep = drop_keep8(d, (uint32_t)row, (uint32_t)(col0 + 8 * g) >> 3);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[8 * g + e] = ((keep >> e) & 1) ? v[8 * g + e] * d.inv_keep : 0.0f;
+  }
 }
 
 template <int BN>
@@ -77,6 +90,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
       for (int i = 0; i < 32; ++i)
         if (full || col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
     }
+    if (p.rowmask && p.rowmask[row] == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+    }
+    if (p.drop_pos == 1) apply_dropout32(p.drop, row, col0, v);
     if (p.D_pre) {
       __nv_bfloat16* dst = p.D_pre + (long long)row * p.ld_pre + col0;
       if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -123,6 +141,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
         for (int i = 0; i < 32; ++i) v[i] += a[i];
       }
     }
+    if (p.drop_pos == 2) apply_dropout32(p.drop, row, col0, v);
     if (p.resid) {
       const float* src = p.resid + (long long)row * p.ld_resid + col0;
       if (full && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
@@ -138,7 +157,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
     }
   }
   if (p.d_f32) {
-    float* dst = reinterpret_cast<float*>(p.D) + (long long)b * p.stride_d + (long long)row * p.ldd + col0;
+    float* dst = reinterpret_cast<float*>(p.D) + (long long)(b / p.batch_inner) * p.stride_d +
+                 (long long)(b % p.batch_inner) * p.stride_d_in + (long long)row * p.ldd + col0;
     if (p.split_k > 1) {
       for (int i = 0; i < 32; ++i)
         if (full || col0 + i < p.N) atomicAdd(dst + i, v[i]);
@@ -157,8 +177,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
         if (col0 + i < p.N) dst[i] = p.accumulate ? dst[i] + v[i] : v[i];
     }
   } else {
-    __nv_bfloat16* dst =
-        reinterpret_cast<__nv_bfloat16*>(p.D) + (long long)b * p.stride_d + (long long)row * p.ldd + col0;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.D) + (long long)(b / p.batch_inner) * p.stride_d +
+                         (long long)(b % p.batch_inner) * p.stride_d_in + (long long)row * p.ldd + col0;
     if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -232,19 +252,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
+          const int bi = b % p.batch_inner, bo = b / p.batch_inner;
+          const int abi = bi * p.a_bi_mul, abo = bo * p.a_bo_mul, bbi = bi * p.b_bi_mul, bbo = bo * p.b_bo_mul;
           if constexpr (!A_MN) {
-            tma_load_3d(sa, &map_a, &full_bar[stage], kb * BK, m0, b);
+            tma_load_4d(sa, &map_a, &full_bar[stage], kb * BK, m0, abi, abo);
           } else {
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c)
-              tma_load_3d(sa + c * (64 * BK * 2), &map_a, &full_bar[stage], m0 + c * 64, kb * BK, b);
+              tma_load_4d(sa + c * (64 * BK * 2), &map_a, &full_bar[stage], m0 + c * 64, kb * BK, abi, abo);
           }
           if constexpr (!B_MN) {
-            tma_load_3d(sb, &map_b, &full_bar[stage], kb * BK, n0, b);
+            tma_load_4d(sb, &map_b, &full_bar[stage], kb * BK, n0, bbi, bbo);
           } else {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)
-              tma_load_3d(sb + c * (64 * BK * 2), &map_b, &full_bar[stage], n0 + c * 64, kb * BK, b);
+              tma_load_4d(sb + c * (64 * BK * 2), &map_b, &full_bar[stage], n0 + c * 64, kb * BK, bbi, bbo);
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -369,28 +391,6 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// 3-D bf16 tensor map {inner, rows, batch} with a {64, box_rows, 1} box and 128B swizzle.
-int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch,
-                   uint64_t ld_elems, uint64_t batch_stride_elems, uint32_t box_rows) {
-  PFN_encodeTiled enc = get_encode();
-  FB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
-  FB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand must be 16-byte aligned");
-  FB_REQUIRE((ld_elems * 2) % 16 == 0, "TMA operand leading dimension must be a multiple of 8 elements (got %llu)",
-             (unsigned long long)ld_elems);
-  if (batch <= 1) { batch = 1; batch_stride_elems = ld_elems * rows; }
-  FB_REQUIRE((batch_stride_elems * 2) % 16 == 0, "TMA batch stride must be a multiple of 8 elements");
-  cuuint64_t dims[3] = {inner, rows, batch};
-  cuuint64_t strides[2] = {ld_elems * 2, batch_stride_elems * 2};
-  cuuint32_t box[3] = {64, box_rows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  FB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu rows=%llu ld=%llu)",
-             (int)r, (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)ld_elems);
-  return 0;
-}
-
 int make_tmap_bf16_nd(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
                       const uint64_t* strides_elems, const uint32_t* box) {
   PFN_encodeTiled enc = get_encode();
@@ -411,6 +411,24 @@ int make_tmap_bf16_nd(CUtensorMap* out, const void* ptr, int rank, const uint64_
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(rank %d) failed with CUresult %d", rank, (int)r);
   return 0;
+}
+
+// 4-D operand map {inner, rows, batch_inner, batch_outer} with a {64, box_rows, 1, 1} box.
+static int make_tmap_operand(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t rows, uint64_t ld,
+                             int batch_in, long long stride_in, int batch_out, long long stride_out,
+                             uint32_t box_rows) {
+  FB_REQUIRE(ld % 8 == 0, "fb_gemm: operand leading dimension must be a multiple of 8 elements (got %llu)",
+             (unsigned long long)ld);
+  // a zero batch stride means "broadcast": that level is collapsed to size 1 and the kernel always
+  // addresses coordinate 0 (GemmParams::*_mul)
+  if (stride_in == 0) batch_in = 1;
+  if (stride_out == 0) batch_out = 1;
+  uint64_t dims[4] = {inner, rows, (uint64_t)std::max(batch_in, 1), (uint64_t)std::max(batch_out, 1)};
+  uint64_t strides[3] = {ld, batch_in > 1 ? (uint64_t)stride_in : ld * rows,
+                         batch_out > 1 ? (uint64_t)stride_out : ld * rows * dims[2]};
+  // dummy strides of size-1 dims still have to be 16-byte multiples: ld is, so ld*rows is
+  uint32_t box[4] = {64, box_rows, 1, 1};
+  return make_tmap_bf16_nd(out, ptr, 4, dims, strides, box);
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -462,27 +480,38 @@ int gemm(const fb_gemm_args* a, cudaStream_t st) {
   const int split_k = a->split_k > 1 ? a->split_k : 1;
   if (split_k > 1) FB_REQUIRE(a->d_dtype == FB_DT_F32, "fb_gemm: split_k needs an fp32 output");
   if (a->accumulate) FB_REQUIRE(a->d_dtype == FB_DT_F32, "fb_gemm: accumulate needs an fp32 output");
-  if (a->batch > 1)
-    FB_REQUIRE(!a->D_pre && !a->aux && !a->resid, "fb_gemm: batched mode supports bias/act only");
-  int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N, a->batch, split_k);
+  const int b_out = a->batch, b_in = a->batch_inner > 1 ? a->batch_inner : 1;
+  const int batch_total = b_out * b_in;
+  if (batch_total > 1)
+    FB_REQUIRE(!a->D_pre && !a->aux && !a->resid && !a->rowmask && !a->drop_pos,
+               "fb_gemm: batched mode supports bias/act only");
+  int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N, batch_total, split_k);
   FB_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, "fb_gemm: block_n must be 64/128/192/256");
 
   CUtensorMap ma, mb;
   int rc;
   if (!a->a_mn_major)
-    rc = make_tmap_bf16(&ma, a->A, a->K, a->M, a->batch, a->lda, a->stride_a, BM);
+    rc = make_tmap_operand(&ma, a->A, a->K, a->M, a->lda, b_in, a->stride_a_in, b_out, a->stride_a, BM);
   else
-    rc = make_tmap_bf16(&ma, a->A, a->M, a->K, a->batch, a->lda, a->stride_a, BK);
+    rc = make_tmap_operand(&ma, a->A, a->M, a->K, a->lda, b_in, a->stride_a_in, b_out, a->stride_a, BK);
   if (rc) return rc;
   if (!a->b_mn_major)
-    rc = make_tmap_bf16(&mb, a->B, a->K, a->N, a->batch, a->ldb, a->stride_b, bn);
+    rc = make_tmap_operand(&mb, a->B, a->K, a->N, a->ldb, b_in, a->stride_b_in, b_out, a->stride_b, bn);
   else
-    rc = make_tmap_bf16(&mb, a->B, a->N, a->K, a->batch, a->ldb, a->stride_b, BK);
+    rc = make_tmap_operand(&mb, a->B, a->N, a->K, a->ldb, b_in, a->stride_b_in, b_out, a->stride_b, BK);
   if (rc) return rc;
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.M = a->M; p.N = a->N; p.K = a->K; p.batch = a->batch;
+  p.M = a->M; p.N = a->N; p.K = a->K; p.batch = batch_total; p.batch_inner = b_in;
+  p.stride_d_in = a->stride_d_in;
+  p.a_bi_mul = (b_in > 1 && a->stride_a_in != 0) ? 1 : 0;
+  p.a_bo_mul = (b_out > 1 && a->stride_a != 0) ? 1 : 0;
+  p.b_bi_mul = (b_in > 1 && a->stride_b_in != 0) ? 1 : 0;
+  p.b_bo_mul = (b_out > 1 && a->stride_b != 0) ? 1 : 0;
+  p.rowmask = a->rowmask;
+  p.drop = make_drop(a->drop.p, a->drop.seed, a->drop.offset);
+  p.drop_pos = (a->drop.p > 0.0f) ? a->drop_pos : 0;
   p.mblocks = (a->M + BM - 1) / BM;
   p.nblocks = (a->N + bn - 1) / bn;
   p.kblocks = (a->K + BK - 1) / BK;

@@ -1,0 +1,589 @@
+"""Kernel schedule of the FrozenBiLM masked-LM hot path (DeBERTa-V2 + adapters + visual prefix).
+
+This module only SEQUENCES the C-ABI kernels of libfrozenbilm_sm100.so (tcgen05 GEMMs, fused
+disentangled attention, LayerNorm/row kernels): PyTorch provides device memory, streams and the
+tiny index/mask preparation.  There is no eager/CPU fallback.
+
+Forward  = reference model/deberta.py:997-1058 (embeddings + visual prefix), :507-575 (encoder, the
+           discarded last ordinary pass skipped), :395-419 (conv after layer 0),
+           :1382-1412 (two enhanced-mask-decoder passes), :1544-1558 + :1481-1488 (head + CE).
+Backward = hand-scheduled selective backward: dX through the frozen linears, dW only for adapters,
+           LayerNorms and linear_video (freezing rules deberta.py:1152-1158, 1334-1339).  GEMM outputs
+           needed by the backward are kept (180 GB of HBM makes a full recompute a net loss); cheap
+           things are recomputed: dropout masks (Philox), GELU/ReLU derivatives, softmax probabilities.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import lib
+from .config import FBConfig
+from .relpos import bucket_of_rel
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+# dropout site ids inside one layer pass (offset = pass_id * 8 + site)
+SITE_POS, SITE_PROBS, SITE_AD1, SITE_HID1, SITE_AD2, SITE_HID2 = 0, 1, 2, 3, 4, 5
+OFF_EMB, OFF_CONV = 100000, 100001
+
+
+def _ceil8(n):
+    return (n + 7) // 8 * 8
+
+
+class Workspace:
+    """Named, shape-keyed scratch tensors reused across steps (no per-step cudaMalloc)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, name, shape, dtype, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, device=self.device, dtype=dtype)
+            self.bufs[key] = t
+        if zero:
+            t.zero_()
+        return t
+
+    def rows(self, name, nrows, ncols, dtype):
+        """[nrows, ncols] view of a growable buffer (row counts that vary per step, e.g. labelled positions)."""
+        key = (name, ncols, dtype)
+        t = self.bufs.get(key)
+        if t is None or t.shape[0] < nrows:
+            cap = max(256, int(nrows * 1.25) + 8)
+            t = torch.empty((cap, ncols), device=self.device, dtype=dtype)
+            self.bufs[key] = t
+        return t[:nrows]
+
+
+class DebertaEngine:
+    def __init__(self, cfg: FBConfig, params: dict, device):
+        """params: name -> fp32 CUDA tensor (the module's parameters; reference names)."""
+        lib.load()
+        if device.type != "cuda":
+            raise lib.FbError("frozenbilm_b200 has no CPU path: move the model to a CUDA device")
+        self.cfg = cfg
+        self.P = params
+        self.device = device
+        self.ws = Workspace(device)
+        self.saved = None
+        self.step_seed = 0x5EED0000
+        if cfg.head_dim != 64:
+            raise NotImplementedError("the fused attention kernel is specialised for head_dim = 64")
+        if cfg.hidden_size % 128 != 0:
+            raise NotImplementedError("hidden_size must be a multiple of 128")
+        self.bucket_of_rel = torch.from_numpy(bucket_of_rel(cfg.position_buckets, cfg.max_position_embeddings)).to(device)
+        self._frozen_versions = None
+        self.W = {}
+        self.prepare_frozen()
+
+    # ------------------------------------------------------------------ weight preparation
+    def _frozen_sig(self):
+        return tuple((k, v._version, v.data_ptr()) for k, v in self.P.items())
+
+    def prepare_frozen(self):
+        """bf16 operand copies of the LM matrices (one-time, or after load_state_dict)."""
+        cfg, P, W = self.cfg, self.P, self.W
+        H = cfg.hidden_size
+        with torch.no_grad():
+            for i in range(cfg.num_hidden_layers):
+                p = f"deberta.encoder.layer.{i}."
+                a = p + "attention.self."
+                W[f"qkv.w.{i}"] = torch.cat([P[a + "query_proj.weight"], P[a + "key_proj.weight"],
+                                             P[a + "value_proj.weight"]], 0).to(BF16).contiguous()
+                W[f"qkv.b.{i}"] = torch.cat([P[a + "query_proj.bias"], P[a + "key_proj.bias"],
+                                             P[a + "value_proj.bias"]], 0).float().contiguous()
+                W[f"o.w.{i}"] = P[p + "attention.output.dense.weight"].to(BF16).contiguous()
+                W[f"ffn1.w.{i}"] = P[p + "intermediate.dense.weight"].to(BF16).contiguous()
+                W[f"ffn2.w.{i}"] = P[p + "output.dense.weight"].to(BF16).contiguous()
+            c = "deberta.encoder."
+            # Conv1d weight [out, in, 3] -> [out, 3*in] with column = k * H + in (matches fb_conv_im2col)
+            W["conv.w"] = P[c + "conv.conv.weight"].permute(0, 2, 1).reshape(H, 3 * H).to(BF16).contiguous()
+            W["head.w"] = P["lm_predictions.lm_head.dense.weight"].to(BF16).contiguous()
+            W["emb16"] = P["deberta.embeddings.word_embeddings.weight"].to(BF16).contiguous()
+            if cfg.n_ans:
+                self.refresh_answer_embeddings()
+        self._frozen_versions = self._frozen_sig()
+
+    def refresh_answer_embeddings(self):
+        E = self.P["answer_embeddings.weight"]
+        n = E.shape[0]
+        Ep = torch.zeros(_ceil8(n), self.cfg.hidden_size, device=self.device, dtype=BF16)
+        Ep[:n] = E.to(BF16)
+        self.W["ans16"] = Ep
+        self.W["ans_n"] = n
+
+    def refresh_trainable(self, flat32, flat16, slices):
+        """flat16 = bf16 copy of the flat trainable bucket (one cast kernel); slices: name -> (a, b, shape)."""
+        lib.cast_bf16(flat32, flat16)
+        self.T16 = {k: flat16[a:b].view(shape) for k, (a, b, shape) in slices.items()}
+
+    def t16(self, name):
+        return self.T16[name]
+
+    # ------------------------------------------------------------------ helpers
+    def drop(self, p, offset):
+        return lib.drop(p if self.training else 0.0, self.step_seed, offset)
+
+    # ------------------------------------------------------------------ forward
+    def forward_encoder(self, video, video_mask, input_ids, attention_mask, training):
+        cfg, P, W, ws = self.cfg, self.P, self.W, self.ws
+        if self._frozen_versions != self._frozen_sig():
+            self.prepare_frozen()
+        self.training = bool(training)
+        self.step_seed += 1
+        dev = self.device
+        H, NL, h = cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads
+        B, Lt = input_ids.shape
+        use_video = bool(cfg.features_dim) and video is not None
+        F = video.shape[1] if use_video else 0
+        L = F + Lt
+        T = B * L
+        if L > cfg.max_position_embeddings or L > 512:
+            raise ValueError(f"sequence length {L} exceeds max_position_embeddings / kernel limit 512")
+        self.dims = (B, L, F, Lt, T)
+        hid_p, att_p, ad_p = cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob, cfg.adapter_dropout
+        e = "deberta.embeddings."
+        sv = {"passes": []} if training else None
+
+        # ---- masks (tiny index math stays in torch)
+        if attention_mask is None:
+            attention_mask = torch.ones(B, Lt, device=dev, dtype=torch.long)
+        if use_video:
+            if video_mask is None:
+                video_mask = torch.ones(B, F, device=dev, dtype=torch.long)
+            m = torch.cat([video_mask.to(dev), attention_mask.to(dev)], 1)
+        else:
+            m = attention_mask.to(dev)
+        mask_u8 = (m != 0).to(torch.uint8).contiguous()
+        self.mask_u8 = mask_u8
+
+        # ---- embeddings: [linear_video(video) ; word_emb[ids]] -> LN -> * mask -> dropout
+        e32 = ws.get("e32", (T, H), F32)
+        if use_video:
+            Dv = cfg.features_dim
+            v16 = ws.get("video16", (B * F, _ceil8(Dv)), BF16)
+            vin = video.to(dev, F32).reshape(B * F, Dv).contiguous()
+            if _ceil8(Dv) != Dv:
+                v16.zero_()
+                v16[:, :Dv] = vin.to(BF16)
+            else:
+                lib.cast_bf16(vin, v16)
+            wv = self.t16(e + "linear_video.weight")
+            lib.gemm(v16, wv, e32, bias=P[e + "linear_video.bias"], M=F, N=H, K=Dv,
+                     batch={"outer": (B, F * v16.stride(0), 0, L * H)})
+            idx_out = (torch.arange(B, device=dev)[:, None] * L + F + torch.arange(Lt, device=dev)[None, :]).reshape(-1)
+        else:
+            idx_out = None
+        ids = input_ids.to(dev).reshape(-1).contiguous()
+        lib.move_rows(P[e + "word_embeddings.weight"], e32, idx_in=ids,
+                      idx_out=idx_out.contiguous() if idx_out is not None else None)
+        x32 = ws.get("x32.0", (T, H), F32)
+        x16 = ws.get("x16.0", (T, H), BF16)
+        emb_mean, emb_rstd = ws.get("emb.mean", (T,), F32), ws.get("emb.rstd", (T,), F32)
+        lib.layernorm_fwd(e32, P[e + "LayerNorm.weight"], P[e + "LayerNorm.bias"], cfg.layer_norm_eps,
+                          rowmask=mask_u8, out_drop=self.drop(hid_p, OFF_EMB), y32=x32, y16=x16,
+                          mean=emb_mean, rstd=emb_rstd)
+        x0_16 = x16
+
+        # ---- relative embeddings: R = LN(rel_embeddings.weight) (trainable LN), once per forward
+        c = "deberta.encoder."
+        S2 = 2 * cfg.position_buckets
+        R32 = ws.get("R32", (S2, H), F32)
+        rel_mean, rel_rstd = ws.get("rel.mean", (S2,), F32), ws.get("rel.rstd", (S2,), F32)
+        lib.layernorm_fwd(P[c + "rel_embeddings.weight"], P[c + "LayerNorm.weight"], P[c + "LayerNorm.bias"],
+                          cfg.layer_norm_eps, y32=R32, mean=rel_mean, rstd=rel_rstd)
+        self._R32 = R32
+        self._rel_tables_cache = {}
+
+        # ---- encoder: NL-1 ordinary passes (the NL-th only feeds hidden_states[-1], which nothing reads)
+        pass_id = 0
+        for i in range(NL - 1):
+            qkv = ws.get(f"qkv.{pass_id}" if training else "qkv", (T, 3 * H), BF16)
+            lib.gemm(x16, W[f"qkv.w.{i}"], qkv, bias=W[f"qkv.b.{i}"])
+            y32, y16, rec = self._layer_pass(i, pass_id, x32, qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], training)
+            if training:
+                rec["qkv"] = qkv
+            if i == 0:
+                # ConvLayer on the EMBEDDING output; LN(layer0_out + gelu(dropout(conv))) * mask
+                col16 = ws.get("col16", (T, 3 * H), BF16)
+                lib.conv_im2col(x0_16, B, L, H, col16)
+                sc32 = ws.get("conv.s", (T, H), F32)
+                cg16 = ws.get("conv.pre", (T, H), BF16)
+                lib.gemm(col16, W["conv.w"], sc32, bias=P[c + "conv.conv.bias"], rowmask=mask_u8,
+                         dropout=self.drop(hid_p, OFF_CONV), drop_pos=1, D_pre=cg16, act=lib.FB_ACT_GELU, resid=y32)
+                cm, cr = ws.get("conv.mean", (T,), F32), ws.get("conv.rstd", (T,), F32)
+                y32b, y16b = ws.get("x32.c", (T, H), F32), ws.get("x16.c", (T, H), BF16)
+                lib.layernorm_fwd(sc32, P[c + "conv.LayerNorm.weight"], P[c + "conv.LayerNorm.bias"],
+                                  cfg.layer_norm_eps, rowmask=mask_u8, y32=y32b, y16=y16b, mean=cm, rstd=cr)
+                y32, y16 = y32b, y16b
+                if training:
+                    sv.update(conv_s=sc32, conv_pre=cg16, conv_mean=cm, conv_rstd=cr)
+            if training:
+                sv["passes"].append(rec)
+            x32, x16 = y32, y16
+            pass_id += 1
+
+        # ---- enhanced mask decoder: 2 passes of the last layer, Q from z / o1, K/V from h[-2] (computed once)
+        last = NL - 1
+        kv32, kv16 = x32, x16
+        z32, z16 = ws.get("emd.z32", (T, H), F32), ws.get("emd.z16", (T, H), BF16)
+        lib.add_rowbcast(kv32, P[e + "position_embeddings.weight"][:L].contiguous(), B, L, H, z32, z16)
+        kvp = ws.get("emd.kv", (T, 2 * H), BF16)
+        lib.gemm(kv16, W[f"qkv.w.{last}"][H:], kvp, bias=W[f"qkv.b.{last}"][H:].contiguous())
+        q32, q16 = z32, z16
+        for j in range(2):
+            qp = ws.get(f"emd.q.{j}", (T, H), BF16)
+            lib.gemm(q16, W[f"qkv.w.{last}"][:H], qp, bias=W[f"qkv.b.{last}"][:H].contiguous())
+            y32, y16, rec = self._layer_pass(last, pass_id, q32, qp, kvp[:, :H], kvp[:, H:], training, tag=f"e{j}")
+            if training:
+                rec["q"] = qp
+                rec["kv"] = kvp
+                sv["passes"].append(rec)
+            q32, q16 = y32, y16
+            pass_id += 1
+        if training:
+            sv.update(e32=e32, emb_mean=emb_mean, emb_rstd=emb_rstd, rel_mean=rel_mean, rel_rstd=rel_rstd,
+                      video16=v16 if use_video else None, use_video=use_video)
+            self.saved = sv
+        self.o2_32, self.o2_16 = q32, q16
+        return q32, q16
+
+    def _rel_tables(self, layer, pass_id, L):
+        """PQrel / PKrel for one layer pass: Linear_{q|k}(dropout(R)) expanded to relative positions."""
+        cfg, W, ws = self.cfg, self.W, self.ws
+        H, h = cfg.hidden_size, cfg.num_attention_heads
+        p = cfg.hidden_dropout_prob if self.training else 0.0
+        key = layer if p == 0.0 else None
+        if key is not None and key in self._rel_tables_cache:
+            return self._rel_tables_cache[key]
+        S2 = 2 * cfg.position_buckets
+        tagk = f".{pass_id}" if self.training else ""
+        Rd16 = ws.get("Rd16", (S2, H), BF16)
+        lib.dropout_apply(self._R32, self.drop(cfg.hidden_dropout_prob, pass_id * 8 + SITE_POS), out16=Rd16)
+        pqk = ws.get("pqk16", (S2, 2 * H), BF16)
+        lib.gemm(Rd16, W[f"qkv.w.{layer}"][:2 * H], pqk, bias=W[f"qkv.b.{layer}"][:2 * H].contiguous())
+        rel_rows, _ = lib.rel_table_geometry(L)
+        pq = ws.get("PQrel" + tagk, (h, rel_rows, 64), BF16)
+        pk = ws.get("PKrel" + tagk, (h, rel_rows, 64), BF16)
+        lib.build_rel_tables(pqk, self.bucket_of_rel, L, h, out_pq=pq, out_pk=pk)
+        if key is not None:
+            self._rel_tables_cache[key] = (pq, pk)
+        return pq, pk
+
+    def _sublayer_out(self, name, i, pass_id, u_in16, W_dense, b_dense, ad_prefix, ln_prefix, resid32, site_ad,
+                      site_hid, training, tag):
+        """dense -> adapter -> dropout -> + residual -> LayerNorm  (deberta.py:254-260 / 328-334)."""
+        cfg, P, ws = self.cfg, self.P, self.ws
+        T = u_in16.shape[0]
+        H = cfg.hidden_size
+        sfx = f".{tag}" if training else ""
+        hid = self.drop(cfg.hidden_dropout_prob, pass_id * 8 + site_hid)
+        s32 = ws.get(f"{name}.s{sfx}", (T, H), F32)
+        rec = {}
+        r = cfg.r_attn if name == "att" else cfg.r_ff
+        if r:
+            u16 = ws.get(f"{name}.u{sfx}", (T, H), BF16)
+            lib.gemm(u_in16, W_dense, u16, bias=b_dense)
+            z16 = ws.get(f"{name}.z{sfx}", (T, r), BF16)
+            lib.gemm(u16, self.t16(ad_prefix + "down.weight"), z16, bias=P[ad_prefix + "down.bias"],
+                     act=lib.FB_ACT_RELU, dropout=self.drop(cfg.adapter_dropout, pass_id * 8 + site_ad), drop_pos=2)
+            lib.gemm(z16, self.t16(ad_prefix + "up.weight"), s32, bias=P[ad_prefix + "up.bias"], aux=u16,
+                     aux_op=lib.FB_AUX_ADD, dropout=hid, drop_pos=2, resid=resid32)
+            rec.update(u=u16, z=z16)
+        else:
+            lib.gemm(u_in16, W_dense, s32, bias=b_dense, dropout=hid, drop_pos=2, resid=resid32)
+        y32 = ws.get(f"{name}.y32.{pass_id % 2}", (T, H), F32)
+        y16 = ws.get(f"{name}.y16.{pass_id % 2}", (T, H), BF16)
+        mean = ws.get(f"{name}.mean{sfx}", (T,), F32)
+        rstd = ws.get(f"{name}.rstd{sfx}", (T,), F32)
+        lib.layernorm_fwd(s32, P[ln_prefix + "weight"], P[ln_prefix + "bias"], cfg.layer_norm_eps, y32=y32, y16=y16,
+                          mean=mean, rstd=rstd)
+        rec.update(s=s32, mean=mean, rstd=rstd)
+        return y32, y16, rec
+
+    def _layer_pass(self, i, pass_id, xq32, Q, K, V, training, tag=None):
+        """One DebertaV2Layer pass (deberta.py:351-375) given the projected Q/K/V views."""
+        cfg, P, W, ws = self.cfg, self.P, self.W, self.ws
+        B, L, F, Lt, T = self.dims
+        H, h, I = cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size
+        tag = tag if tag is not None else str(pass_id)
+        sfx = f".{tag}" if training else ""
+        p = f"deberta.encoder.layer.{i}."
+        pq, pk = self._rel_tables(i, pass_id, L)
+        ctx16 = ws.get("ctx" + sfx, (T, H), BF16)
+        lse = ws.get("lse" + sfx, (B, h, L), F32)
+        att_drop = self.drop(cfg.attention_probs_dropout_prob, pass_id * 8 + SITE_PROBS)
+        s2 = ws.get("s2" + sfx, (B, h, L, (L + 127) // 128 * 128), F32) if training else None
+        lib.attn_fwd(Q, K, V, pk, pq, self.mask_u8, ctx16, lse, B=B, L=L, h=h, scale=1.0 / math.sqrt(3 * 64),
+                     dropout_p=att_drop.p, seed=att_drop.seed, offset=att_drop.offset, s_out=s2)
+        a32, a16, rec1 = self._sublayer_out("att", i, pass_id, ctx16, W[f"o.w.{i}"], P[p + "attention.output.dense.bias"],
+                                            p + "attention.output.adapter.", p + "attention.output.LayerNorm.",
+                                            xq32, SITE_AD1, SITE_HID1, training, tag)
+        f16 = ws.get("ffn.f", (T, I), BF16)
+        h1 = ws.get("ffn.h1" + sfx, (T, I), BF16) if training else None
+        lib.gemm(a16, W[f"ffn1.w.{i}"], f16, bias=P[p + "intermediate.dense.bias"], act=lib.FB_ACT_GELU, D_pre=h1)
+        y32, y16, rec2 = self._sublayer_out("ffn", i, pass_id, f16, W[f"ffn2.w.{i}"], P[p + "output.dense.bias"],
+                                            p + "output.adapter.", p + "output.LayerNorm.", a32, SITE_AD2, SITE_HID2,
+                                            training, tag)
+        rec = None
+        if training:
+            rec = dict(layer=i, pass_id=pass_id, Q=Q, K=K, V=V, pq=pq, pk=pk, ctx=ctx16, lse=lse, att=rec1, ffn=rec2,
+                       h1=h1, s2=s2)
+        return y32, y16, rec
+
+    # ------------------------------------------------------------------ head
+    def head_logits(self, rows16, n_rows, mlm, out=None, scratch=False):
+        """logits = LN(gelu(dense(x))) . E^T + bias for the given rows (deberta.py:1544-1558).
+        ``scratch`` uses separate buffers and leaves the state saved for the backward untouched."""
+        cfg, P, W, ws = self.cfg, self.P, self.W, self.ws
+        H = cfg.hidden_size
+        hp = "lm_predictions.lm_head."
+        pfx = "headx." if scratch else "head."
+        hd32 = ws.rows(pfx + "hd32", n_rows, H, F32)
+        pre16 = ws.rows(pfx + "pre16", n_rows, H, BF16)
+        lib.gemm(rows16, W["head.w"], hd32, bias=P[hp + "dense.bias"], act=lib.FB_ACT_GELU, D_pre=pre16)
+        t16 = ws.rows(pfx + "t16", n_rows, H, BF16)
+        mean, rstd = ws.rows(pfx + "mean", n_rows, 1, F32), ws.rows(pfx + "rstd", n_rows, 1, F32)
+        lib.layernorm_fwd(hd32, P[hp + "LayerNorm.weight"], P[hp + "LayerNorm.bias"], cfg.layer_norm_eps, y16=t16,
+                          mean=mean, rstd=rstd)
+        if cfg.n_ans and not mlm:
+            E, bias, V = W["ans16"], P["answer_bias"], W["ans_n"]
+        else:
+            E, bias, V = W["emb16"], P[hp + "bias"], cfg.vocab_size
+        if out is None:
+            out = ws.rows(pfx + "logits", n_rows, _ceil8(V), F32)
+        lib.gemm(t16, E, out, bias=bias, N=V)
+        if scratch:
+            return out, V
+        self.head_saved = dict(hd32=hd32, pre16=pre16, t16=t16, mean=mean, rstd=rstd, E=E, V=V, n_rows=n_rows)
+        return out, V
+
+    def head_mlm_loss(self, sel, labels_sel, n_sel, want_grad):
+        """MLM loss over the labelled positions only (CrossEntropyLoss ignores -100, deberta.py:1481-1488): the
+        head runs on n_sel rows instead of all B*L and the [B, L, V] logits are never materialised."""
+        cfg, ws = self.cfg, self.ws
+        H = cfg.hidden_size
+        rows16 = ws.rows("head.rows16", n_sel, H, BF16)
+        lib.move_rows(self.o2_16, rows16, idx_in=sel)
+        logits, V = self.head_logits(rows16, n_sel, mlm=True)
+        loss_sum = ws.get("head.loss", (1,), F32, zero=True)
+        dlog16 = ws.rows("head.dlog16", n_sel, _ceil8(V), BF16) if want_grad else None
+        lib.cross_entropy(logits, V, labels_sel, loss_sum, 1.0 / n_sel, dlog16, 1.0 / n_sel)
+        self.head_saved.update(sel=sel, dlog16=dlog16, mode="mlm")
+        return loss_sum[0]
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, gviews, scale=None, dlogits=None):
+        """Selective backward: accumulates into ``gviews`` (name -> fp32 view of the flat gradient bucket)."""
+        cfg, P, W, ws, sv, hs = self.cfg, self.P, self.W, self.ws, self.saved, self.head_saved
+        if sv is None:
+            raise lib.FbError("backward() without a training-mode forward")
+        B, L, F, Lt, T = self.dims
+        H = cfg.hidden_size
+        hp = "lm_predictions.lm_head."
+        self.g = gviews
+        n = hs["n_rows"]
+        # ---- head: logits -> t -> LN -> gelu -> dense
+        dt32 = ws.rows("bw.dt32", n, H, F32)
+        if dlogits is None:
+            lib.gemm(hs["dlog16"], hs["E"], dt32, b_mn_major=True, K=hs["V"], N=H)
+            if scale is not None and scale != 1.0:
+                dt32.mul_(scale)
+        else:
+            nans = hs["V"]
+            d16 = ws.get("bw.dlog_ans", (n, _ceil8(nans)), BF16, zero=True)
+            d16[:, :nans] = dlogits.reshape(n, nans).to(BF16)
+            lib.gemm(d16, hs["E"], dt32, b_mn_major=True, N=H)
+        dhd32 = ws.rows("bw.dhd32", n, H, F32)
+        lib.layernorm_bwd(dt32, hs["hd32"], hs["mean"], hs["rstd"], P[hp + "LayerNorm.weight"], dx32=dhd32,
+                          dgamma=self._g(hp + "LayerNorm.weight"), dbeta=self._g(hp + "LayerNorm.bias"))
+        dpre16 = ws.rows("bw.dpre16", n, H, BF16)
+        lib.gelu_bwd(dhd32, hs["pre16"], dpre16)
+        dy32 = ws.get("bw.dy32.a", (T, H), F32)
+        if dlogits is None:
+            drows32 = ws.rows("bw.drows32", n, H, F32)
+            lib.gemm(dpre16, W["head.w"], drows32, b_mn_major=True)
+            dy32.zero_()
+            lib.move_rows(drows32, dy32, idx_out=hs["sel"])
+        else:
+            lib.gemm(dpre16, W["head.w"], dy32, b_mn_major=True)
+        self._dR32 = ws.get("bw.dR32", (2 * cfg.position_buckets, H), F32, zero=True)
+        passes = sv["passes"]
+        NL = cfg.num_hidden_layers
+        last = NL - 1
+        # ---- enhanced mask decoder passes (reverse): shared K/V projection of h[-2]
+        dq32, dkv_b = self._bwd_pass(passes[-1], dy32, emd=True, slot=0)
+        dz32, dkv_a = self._bwd_pass(passes[-2], dq32, emd=True, slot=1)
+        dx32 = ws.get("bw.dx32.e", (T, H), F32)
+        wkv = W[f"qkv.w.{last}"][H:]
+        lib.gemm(dkv_b, wkv, dx32, b_mn_major=True, resid=dz32)
+        lib.gemm(dkv_a, wkv, dx32, b_mn_major=True, accumulate=True)
+        # ---- ordinary passes, last to first
+        c = "deberta.encoder."
+        dcol16 = None
+        for rec in reversed(passes[:-2]):
+            if rec["layer"] == 0:
+                # y0' = LN_conv(y0 + gelu(dropout(conv(x0) * m))) * m
+                ds_c = ws.get("bw.ds_c", (T, H), F32)
+                lib.layernorm_bwd(dx32, sv["conv_s"], sv["conv_mean"], sv["conv_rstd"], P[c + "conv.LayerNorm.weight"],
+                                  rowmask=self.mask_u8, dx32=ds_c, dgamma=self._g(c + "conv.LayerNorm.weight"),
+                                  dbeta=self._g(c + "conv.LayerNorm.bias"))
+                dconv16 = ws.get("bw.dconv16", (T, H), BF16)
+                lib.gelu_bwd(ds_c, sv["conv_pre"], dconv16, rowmask=self.mask_u8,
+                             dropout=self.drop(cfg.hidden_dropout_prob, OFF_CONV))
+                dcol16 = ws.get("bw.dcol16", (T, 3 * H), BF16)
+                lib.gemm(dconv16, W["conv.w"], dcol16, b_mn_major=True)
+                dx32 = ds_c
+            dx32 = self._bwd_pass(rec, dx32, emd=False, slot=rec["pass_id"] % 2)
+        if dcol16 is not None:
+            lib.conv_col2im(dcol16, B, L, H, dx32, accumulate=True)
+        # ---- embeddings: dropout -> * mask -> LayerNorm -> [linear_video ; word_emb (frozen)]
+        e = "deberta.embeddings."
+        de16 = ws.get("bw.de16", (T, H), BF16)
+        lib.layernorm_bwd(dx32, sv["e32"], sv["emb_mean"], sv["emb_rstd"], P[e + "LayerNorm.weight"],
+                          rowmask=self.mask_u8, out_drop=self.drop(cfg.hidden_dropout_prob, OFF_EMB), dx16=de16,
+                          dgamma=self._g(e + "LayerNorm.weight"), dbeta=self._g(e + "LayerNorm.bias"))
+        if sv["use_video"]:
+            dv16 = ws.get("bw.dv16", (B * F, H), BF16)
+            idx = (torch.arange(B, device=self.device)[:, None] * L + torch.arange(F, device=self.device)[None, :])
+            lib.move_rows(de16, dv16, idx_in=idx.reshape(-1).contiguous())
+            v16 = sv["video16"]
+            lib.gemm(dv16, v16, self._g(e + "linear_video.weight"), a_mn_major=True, b_mn_major=True,
+                     N=cfg.features_dim, accumulate=True)
+            lib.colsum_bf16(dv16, self._g(e + "linear_video.bias"))
+        # ---- relative-embedding LayerNorm (trainable under ft_ln): gamma/beta only, the table is frozen
+        lib.layernorm_bwd(self._dR32, P[c + "rel_embeddings.weight"], sv["rel_mean"], sv["rel_rstd"],
+                          P[c + "LayerNorm.weight"], dgamma=self._g(c + "LayerNorm.weight"),
+                          dbeta=self._g(c + "LayerNorm.bias"))
+        self.saved = None
+
+    def _g(self, name):
+        """fp32 gradient view of a trainable tensor, or None when it is frozen (kernels skip null outputs)."""
+        return self.g.get(name)
+
+    def _bwd_sublayer(self, name, rec, dy32, ad_prefix, ln_prefix, W_dense, pass_id, site_ad, site_hid, slot):
+        """Backward of LN(dropout(adapter(dense(x))) + resid): returns (ds32 = grad of the residual branch,
+        dxin16 = grad of the dense input)."""
+        cfg, P, ws = self.cfg, self.P, self.ws
+        T, H = dy32.shape
+        r = cfg.r_attn if name == "att" else cfg.r_ff
+        ds32 = ws.get(f"bw.{name}.ds32.{slot}", (T, H), F32)
+        gw16 = ws.get(f"bw.{name}.gw16", (T, H), BF16)
+        lib.layernorm_bwd(dy32, rec["s"], rec["mean"], rec["rstd"], P[ln_prefix + "weight"],
+                          in_drop=self.drop(cfg.hidden_dropout_prob, pass_id * 8 + site_hid), dx32=ds32, dx16=gw16,
+                          dgamma=self._g(ln_prefix + "weight"), dbeta=self._g(ln_prefix + "bias"))
+        if r:
+            u16, z16 = rec["u"], rec["z"]
+            wu, wd = self.t16(ad_prefix + "up.weight"), self.t16(ad_prefix + "down.weight")
+            ad = self.drop(cfg.adapter_dropout, pass_id * 8 + site_ad)
+            inv_keep = 1.0 / (1.0 - ad.p) if ad.p > 0 else 1.0
+            dz16 = ws.get(f"bw.{name}.dz16", (T, r), BF16)
+            # d(zd) = gw . Wu ; through dropout and ReLU: zd > 0 <=> kept and pre-activation > 0
+            lib.gemm(gw16, wu, dz16, b_mn_major=True, alpha=inv_keep, aux=z16, aux_op=lib.FB_AUX_MUL_RELU_MASK)
+            sk = max(1, min(32, T // 512))
+            lib.gemm(gw16, z16, self._g(ad_prefix + "up.weight"), a_mn_major=True, b_mn_major=True, split_k=sk,
+                     accumulate=True)
+            lib.colsum_bf16(gw16, self._g(ad_prefix + "up.bias"))
+            lib.gemm(dz16, u16, self._g(ad_prefix + "down.weight"), a_mn_major=True, b_mn_major=True, split_k=sk,
+                     accumulate=True)
+            lib.colsum_bf16(dz16, self._g(ad_prefix + "down.bias"))
+            du16 = ws.get(f"bw.{name}.du16", (T, H), BF16)
+            lib.gemm(dz16, wd, du16, b_mn_major=True, aux=gw16, aux_op=lib.FB_AUX_ADD)
+        else:
+            du16 = gw16
+        return ds32, du16
+
+    def _bwd_pass(self, rec, dy32, emd, slot):
+        cfg, P, W, ws = self.cfg, self.P, self.W, self.ws
+        B, L, F, Lt, T = self.dims
+        H, h, I = cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size
+        i, pass_id = rec["layer"], rec["pass_id"]
+        p = f"deberta.encoder.layer.{i}."
+        # ---- FFN sub-layer
+        ds2, du2 = self._bwd_sublayer("ffn", rec["ffn"], dy32, p + "output.adapter.", p + "output.LayerNorm.",
+                                      W[f"ffn2.w.{i}"], pass_id, SITE_AD2, SITE_HID2, slot)
+        dh1 = ws.get("bw.dh1", (T, I), BF16)
+        lib.gemm(du2, W[f"ffn2.w.{i}"], dh1, b_mn_major=True, aux=rec["h1"], aux_op=lib.FB_AUX_MUL_GELU_GRAD)
+        da32 = ws.get("bw.da32", (T, H), F32)
+        lib.gemm(dh1, W[f"ffn1.w.{i}"], da32, b_mn_major=True, resid=ds2)
+        # ---- attention sub-layer
+        ds1, du1 = self._bwd_sublayer("att", rec["att"], da32, p + "attention.output.adapter.",
+                                      p + "attention.output.LayerNorm.", W[f"o.w.{i}"], pass_id, SITE_AD1,
+                                      SITE_HID1, slot)
+        dctx16 = ws.get("bw.dctx16", (T, H), BF16)
+        lib.gemm(du1, W[f"o.w.{i}"], dctx16, b_mn_major=True)
+        dqkv32 = self._attn_bwd(rec, dctx16)
+        dqkv16 = ws.get(f"bw.dqkv16.{slot if emd else 0}", (T, 3 * H), BF16)
+        lib.cast_bf16(dqkv32, dqkv16)
+        dxq = ws.get(f"bw.dxq.{slot}", (T, H), F32)
+        if not emd:
+            lib.gemm(dqkv16, W[f"qkv.w.{i}"], dxq, b_mn_major=True, resid=ds1)
+            return dxq
+        lib.gemm(dqkv16[:, :H], W[f"qkv.w.{i}"][:H], dxq, b_mn_major=True, resid=ds1)
+        return dxq, dqkv16[:, H:]
+
+    def _attn_bwd(self, rec, dctx16):
+        """Attention backward from GEMMs + the staging kernels of fb_attention.cu (see fb_attn_bwd_prep)."""
+        cfg, W, ws = self.cfg, self.W, self.ws
+        B, L, F, Lt, T = self.dims
+        H, h = cfg.hidden_size, cfg.num_attention_heads
+        i, pass_id = rec["layer"], rec["pass_id"]
+        Q, K, V = rec["Q"], rec["K"], rec["V"]
+        lp = (L + 127) // 128 * 128
+        rel_rows, rel_off = lib.rel_table_geometry(L)
+        scale = 1.0 / math.sqrt(3 * 64)
+        bh = {"outer": None, "inner": None}
+        # dP = dO . V^T
+        dp = ws.get("bw.dp", (B, h, L, lp), BF16)
+        lib.gemm(dctx16, V, dp.view(-1, lp), M=L, N=L, K=64,
+                 batch={"outer": (B, L * H, L * V.stride(0), h * L * lp), "inner": (h, 64, 64, L * lp)})
+        ds = ws.get("bw.ds", (B, h, L, lp), BF16)
+        pd = ws.get("bw.pd", (B, h, L, lp), BF16)
+        z1 = ws.get("bw.z1", (h, B * L, rel_rows), BF16)
+        z2 = ws.get("bw.z2", (h, B * L, rel_rows), BF16)
+        ad = self.drop(cfg.attention_probs_dropout_prob, pass_id * 8 + SITE_PROBS)
+        lib.attn_bwd_prep(rec["s2"], rec["lse"], dp, rec["ctx"], dctx16, ds, pd, z1, z2, B=B, L=L, h=h, scale=scale,
+                          dropout_p=ad.p, seed=ad.seed, offset=ad.offset)
+        dqkv32 = ws.get("bw.dqkv32", (T, 3 * H), F32)
+        ds2d, pd2d = ds.view(-1, lp), pd.view(-1, lp)
+        z1_2d, z2_2d = z1.view(-1, rel_rows), z2.view(-1, rel_rows)
+        pk2d, pq2d = rec["pk"].view(-1, 64), rec["pq"].view(-1, 64)
+        dq32, dk32, dv32 = dqkv32[:, :H], dqkv32[:, H:2 * H], dqkv32[:, 2 * H:]
+        sq, sk_, svv = Q.stride(0), K.stride(0), V.stride(0)
+        o3 = 3 * H
+        # dV = Pd^T . dO
+        lib.gemm(pd2d, dctx16, dv32, a_mn_major=True, b_mn_major=True, M=L, N=64, K=L,
+                 batch={"outer": (B, h * L * lp, L * H, L * o3), "inner": (h, L * lp, 64, 64)})
+        # dQ = dS . K + Z1 . PKrel
+        lib.gemm(ds2d, K, dq32, b_mn_major=True, M=L, N=64, K=L,
+                 batch={"outer": (B, h * L * lp, L * sk_, L * o3), "inner": (h, L * lp, 64, 64)})
+        lib.gemm(z1_2d, pk2d, dq32, b_mn_major=True, M=L, N=64, K=rel_rows, accumulate=True,
+                 batch={"outer": (B, L * rel_rows, 0, L * o3), "inner": (h, B * L * rel_rows, rel_rows * 64, 64)})
+        # dK = dS^T . Q + Z2 . PQrel
+        lib.gemm(ds2d, Q, dk32, a_mn_major=True, b_mn_major=True, M=L, N=64, K=L,
+                 batch={"outer": (B, h * L * lp, L * sq, L * o3), "inner": (h, L * lp, 64, 64)})
+        lib.gemm(z2_2d, pq2d, dk32, b_mn_major=True, M=L, N=64, K=rel_rows, accumulate=True,
+                 batch={"outer": (B, L * rel_rows, 0, L * o3), "inner": (h, B * L * rel_rows, rel_rows * 64, 64)})
+        # positional projections: dPKrel = Z1^T . Q, dPQrel = Z2^T . K (sum over batch inside the K dimension)
+        gpk = ws.get("bw.gpk", (h, rel_rows, 64), F32)
+        gpq = ws.get("bw.gpq", (h, rel_rows, 64), F32)
+        lib.gemm(z1_2d, Q, gpk.view(-1, 64), a_mn_major=True, b_mn_major=True, M=rel_rows, N=64, K=B * L,
+                 batch={"outer": (h, B * L * rel_rows, 64, rel_rows * 64)})
+        lib.gemm(z2_2d, K, gpq.view(-1, 64), a_mn_major=True, b_mn_major=True, M=rel_rows, N=64, K=B * L,
+                 batch={"outer": (h, B * L * rel_rows, 64, rel_rows * 64)})
+        S2 = 2 * cfg.position_buckets
+        dpqk32 = ws.get("bw.dpqk32", (S2, 2 * H), F32, zero=True)
+        lib.rel_to_bucket(gpq, gpk, self.bucket_of_rel, L, h, dpqk32)
+        dpqk16 = ws.get("bw.dpqk16", (S2, 2 * H), BF16)
+        lib.cast_bf16(dpqk32, dpqk16)
+        dRd32 = ws.get("bw.dRd32", (S2, H), F32)
+        lib.gemm(dpqk16, W[f"qkv.w.{i}"][:2 * H], dRd32, b_mn_major=True)
+        lib.dropout_apply(dRd32, self.drop(cfg.hidden_dropout_prob, pass_id * 8 + SITE_POS), out32=self._dR32,
+                          accumulate=True)
+        return dqkv32

@@ -21,6 +21,15 @@ class FbError(RuntimeError):
     pass
 
 
+class Dropout(C.Structure):
+    _fields_ = [("p", C.c_float), ("seed", C.c_ulonglong), ("offset", C.c_ulonglong)]
+
+
+def drop(p=0.0, seed=0, offset=0):
+    """fb_dropout value (None / p == 0 -> disabled)."""
+    return Dropout(float(p), int(seed), int(offset))
+
+
 class GemmArgs(C.Structure):
     _fields_ = [
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("batch", C.c_int),
@@ -36,6 +45,10 @@ class GemmArgs(C.Structure):
         ("accumulate", C.c_int),
         ("split_k", C.c_int),
         ("block_n", C.c_int),
+        ("batch_inner", C.c_int), ("stride_a_in", C.c_longlong), ("stride_b_in", C.c_longlong),
+        ("stride_d_in", C.c_longlong),
+        ("rowmask", C.c_void_p),
+        ("drop", Dropout), ("drop_pos", C.c_int),
     ]
 
 
@@ -49,6 +62,19 @@ class AttnArgs(C.Structure):
         ("mask", C.c_void_p),
         ("ctx", C.c_void_p), ("ldc", C.c_longlong),
         ("lse", C.c_void_p),
+        ("scale", C.c_float),
+        ("dropout_p", C.c_float), ("seed", C.c_ulonglong), ("offset", C.c_ulonglong),
+        ("s_out", C.c_void_p),
+    ]
+
+
+class AttnBwdPrepArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("L", C.c_int), ("h", C.c_int), ("lp", C.c_int), ("rel_rows", C.c_int), ("rel_off", C.c_int),
+        ("s2", C.c_void_p), ("lse", C.c_void_p),
+        ("dp", C.c_void_p),
+        ("ctx", C.c_void_p), ("dctx", C.c_void_p), ("ldc", C.c_longlong),
+        ("ds", C.c_void_p), ("pd", C.c_void_p), ("z1", C.c_void_p), ("z2", C.c_void_p),
         ("scale", C.c_float),
         ("dropout_p", C.c_float), ("seed", C.c_ulonglong), ("offset", C.c_ulonglong),
     ]
@@ -73,6 +99,23 @@ def load() -> C.CDLL:
         if name in ("fb_last_error", "fb_abi_version", "fb_launch_count"):
             continue
         getattr(lib, name).restype = C.c_int
+    vp, ll, i, f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+    dp = C.POINTER(Dropout)
+    lib.fb_layernorm_fwd.argtypes = [vp, i, i, vp, vp, f, vp, dp, vp, vp, vp, vp, vp]
+    lib.fb_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, vp, dp, dp, vp, vp, vp, vp, vp]
+    lib.fb_move_rows.argtypes = [vp, ll, i, vp, vp, i, i, vp, ll, i, vp]
+    lib.fb_gelu_bwd.argtypes = [vp, vp, i, i, vp, dp, vp, vp]
+    lib.fb_add_rowbcast.argtypes = [vp, vp, i, i, i, vp, vp, vp]
+    lib.fb_conv_im2col.argtypes = [vp, i, i, i, vp, vp]
+    lib.fb_conv_col2im.argtypes = [vp, i, i, i, vp, i, vp]
+    lib.fb_colsum_bf16.argtypes = [vp, ll, i, i, vp, vp]
+    lib.fb_cross_entropy.argtypes = [vp, ll, i, i, vp, vp, f, vp, ll, f, vp]
+    lib.fb_dropout_apply.argtypes = [vp, i, i, dp, vp, i, vp, vp]
+    lib.fb_sumsq.argtypes = [vp, ll, vp, vp]
+    lib.fb_adam_step.argtypes = [vp, vp, vp, vp, ll, f, f, f, f, i, vp, f, f, vp, vp]
+    lib.fb_cast_f32_bf16.argtypes = [vp, ll, vp, vp]
+    lib.fb_build_rel_tables.argtypes = [vp, ll, i, i, vp, i, i, i, vp, vp, vp]
+    lib.fb_rel_to_bucket.argtypes = [vp, vp, i, i, vp, i, i, i, vp, ll, vp]
     _lib = lib
     return lib
 
@@ -80,6 +123,9 @@ def load() -> C.CDLL:
 # every symbol include/frozenbilm_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "fb_last_error", "fb_abi_version", "fb_launch_count", "fb_gemm", "fb_attn_fwd", "fb_build_rel_tables",
+    "fb_layernorm_fwd", "fb_layernorm_bwd", "fb_move_rows", "fb_gelu_bwd", "fb_add_rowbcast", "fb_conv_im2col",
+    "fb_conv_col2im", "fb_colsum_bf16", "fb_cross_entropy", "fb_dropout_apply", "fb_sumsq", "fb_adam_step",
+    "fb_cast_f32_bf16", "fb_attn_bwd_prep", "fb_rel_to_bucket",
 ]
 
 
@@ -92,6 +138,10 @@ def stream_ptr() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _dp(d):
+    return C.byref(d) if d is not None else None
+
+
 def launch_count() -> int:
     return int(load().fb_launch_count())
 
@@ -102,7 +152,8 @@ def _ptr(t):
 
 def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, a_mn_major=False, b_mn_major=False,
          bias=None, act=FB_ACT_NONE, D_pre=None, aux=None, aux_op=FB_AUX_NONE, resid=None, alpha=1.0,
-         accumulate=False, split_k=1, block_n=0, M=None, N=None, K=None):
+         accumulate=False, split_k=1, block_n=0, M=None, N=None, K=None, rowmask=None, dropout=None,
+         drop_pos=0, batch=None):
     """D = epilogue(alpha * A @ B^T) on the tcgen05 GEMM.
 
     A: bf16 [M, K] (or [K, M] when a_mn_major);  B: bf16 [N, K] (or [K, N] when b_mn_major);
@@ -110,10 +161,16 @@ def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, a_mn_major=False,
     """
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     assert A.stride(-1) == 1 and B.stride(-1) == 1 and D.stride(-1) == 1
-    batch = 1
+    nbatch = 1
     sa = sb = sd = 0
-    if A.dim() == 3:
-        batch = A.shape[0]
+    bin_, sai, sbi, sdi = 1, 0, 0, 0
+    if batch is not None:
+        # explicit batching over 2-D base views: batch = dict(outer=(n, sa, sb, sd), inner=(n, sa, sb, sd))
+        A2, B2, D2 = A, B, D
+        nbatch, sa, sb, sd = batch.get("outer", (1, 0, 0, 0))
+        bin_, sai, sbi, sdi = batch.get("inner", (1, 0, 0, 0))
+    elif A.dim() == 3:
+        nbatch = A.shape[0]
         sa, sb, sd = A.stride(0), B.stride(0), D.stride(0)
         A2, B2, D2 = A[0], B[0], D[0]
     else:
@@ -125,7 +182,13 @@ def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, a_mn_major=False,
     if N is None:
         N = B2.shape[1] if b_mn_major else B2.shape[0]
     args = GemmArgs()
-    args.M, args.N, args.K, args.batch = M, N, K, batch
+    args.M, args.N, args.K, args.batch = M, N, K, nbatch
+    args.batch_inner, args.stride_a_in, args.stride_b_in, args.stride_d_in = bin_, sai, sbi, sdi
+    if rowmask is not None:
+        assert rowmask.dtype == torch.uint8
+        args.rowmask = _ptr(rowmask)
+    if dropout is not None and dropout.p > 0:
+        args.drop, args.drop_pos = dropout, int(drop_pos)
     args.A, args.lda, args.stride_a, args.a_mn_major = _ptr(A), A2.stride(0), sa, int(a_mn_major)
     args.B, args.ldb, args.stride_b, args.b_mn_major = _ptr(B), B2.stride(0), sb, int(b_mn_major)
     args.D, args.ldd, args.stride_d = _ptr(D), D2.stride(0), sd
@@ -172,7 +235,8 @@ def build_rel_tables(pqk: torch.Tensor, bucket_of_rel: torch.Tensor, L: int, h: 
     return out_pq, out_pk
 
 
-def attn_fwd(Q, K, V, PKrel, PQrel, mask_u8, ctx, lse, *, B, L, h, scale, dropout_p=0.0, seed=0, offset=0):
+def attn_fwd(Q, K, V, PKrel, PQrel, mask_u8, ctx, lse, *, B, L, h, scale, dropout_p=0.0, seed=0, offset=0,
+             s_out=None):
     """Q/K/V: bf16 2-D views [B*L, >= h*64] (row pitch = stride(0)); ctx: bf16 [B*L, H]; lse: fp32 [B, h, L]."""
     rel_rows, rel_off = rel_table_geometry(L)
     assert PKrel.shape[1] == rel_rows and mask_u8.dtype == torch.uint8 and lse.dtype == torch.float32
@@ -187,5 +251,112 @@ def attn_fwd(Q, K, V, PKrel, PQrel, mask_u8, ctx, lse, *, B, L, h, scale, dropou
     a.lse = _ptr(lse)
     a.scale = float(scale)
     a.dropout_p, a.seed, a.offset = float(dropout_p), int(seed), int(offset)
+    if s_out is not None:
+        assert s_out.dtype == torch.float32 and s_out.shape[-1] == (L + 127) // 128 * 128
+        a.s_out = _ptr(s_out)
     check(load().fb_attn_fwd(C.byref(a), stream_ptr()), "fb_attn_fwd")
     return ctx, lse
+
+
+def layernorm_fwd(x, gamma, beta, eps, *, rowmask=None, out_drop=None, y32=None, y16=None, mean=None, rstd=None):
+    M, H = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    check(load().fb_layernorm_fwd(_ptr(x), M, H, _ptr(gamma), _ptr(beta), float(eps), _ptr(rowmask), _dp(out_drop),
+                                  _ptr(y32), _ptr(y16), _ptr(mean), _ptr(rstd), stream_ptr()), "fb_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, *, rowmask=None, out_drop=None, in_drop=None, dx32=None, dx16=None,
+                  dgamma=None, dbeta=None):
+    M, H = x.shape
+    assert dy.dtype == torch.float32 and dy.is_contiguous() and x.is_contiguous()
+    check(load().fb_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), M, H, _ptr(rowmask),
+                                  _dp(out_drop), _dp(in_drop), _ptr(dx32), _ptr(dx16), _ptr(dgamma), _ptr(dbeta),
+                                  stream_ptr()), "fb_layernorm_bwd")
+
+
+def move_rows(src, dst, *, idx_in=None, idx_out=None, R=None, ncols=None):
+    """dst[idx_out[r]] = src[idx_in[r]] (int64 index tensors; None = identity)."""
+    if R is None:
+        R = (idx_in if idx_in is not None else idx_out).numel() if (idx_in is not None or idx_out is not None) \
+            else src.shape[0]
+    if R == 0:
+        return
+    ncols = ncols or src.shape[1]
+    for t in (idx_in, idx_out):
+        assert t is None or (t.dtype == torch.int64 and t.is_contiguous())
+    check(load().fb_move_rows(_ptr(src), src.stride(0), int(src.dtype == torch.bfloat16), _ptr(idx_in), _ptr(idx_out),
+                              R, ncols, _ptr(dst), dst.stride(0), int(dst.dtype == torch.bfloat16), stream_ptr()),
+          "fb_move_rows")
+
+
+def gelu_bwd(dy, pre16, out16, *, rowmask=None, dropout=None):
+    M, N = dy.shape
+    check(load().fb_gelu_bwd(_ptr(dy), _ptr(pre16), M, N, _ptr(rowmask), _dp(dropout), _ptr(out16), stream_ptr()),
+          "fb_gelu_bwd")
+
+
+def add_rowbcast(a, b, B, L, H, out32, out16=None):
+    check(load().fb_add_rowbcast(_ptr(a), _ptr(b), B, L, H, _ptr(out32), _ptr(out16), stream_ptr()), "fb_add_rowbcast")
+
+
+def conv_im2col(x16, B, L, H, out16):
+    check(load().fb_conv_im2col(_ptr(x16), B, L, H, _ptr(out16), stream_ptr()), "fb_conv_im2col")
+
+
+def conv_col2im(dcol16, B, L, H, dx32, accumulate=False):
+    check(load().fb_conv_col2im(_ptr(dcol16), B, L, H, _ptr(dx32), int(accumulate), stream_ptr()), "fb_conv_col2im")
+
+
+def colsum_bf16(x16, out32):
+    M, N = x16.shape
+    check(load().fb_colsum_bf16(_ptr(x16), x16.stride(0), M, N, _ptr(out32), stream_ptr()), "fb_colsum_bf16")
+
+
+def cross_entropy(logits32, V, labels, loss_sum, loss_scale, dlogits16=None, grad_scale=0.0):
+    P = logits32.shape[0]
+    assert labels.dtype == torch.int64 and labels.is_contiguous()
+    check(load().fb_cross_entropy(_ptr(logits32), logits32.stride(0), P, V, _ptr(labels), _ptr(loss_sum),
+                                  float(loss_scale), _ptr(dlogits16),
+                                  dlogits16.stride(0) if dlogits16 is not None else 0, float(grad_scale),
+                                  stream_ptr()), "fb_cross_entropy")
+
+
+def dropout_apply(x32, dropout, *, out32=None, accumulate=False, out16=None):
+    M, N = x32.shape
+    check(load().fb_dropout_apply(_ptr(x32), M, N, _dp(dropout), _ptr(out32), int(accumulate), _ptr(out16),
+                                  stream_ptr()), "fb_dropout_apply")
+
+
+def sumsq(g, out):
+    check(load().fb_sumsq(_ptr(g), g.numel(), _ptr(out), stream_ptr()), "fb_sumsq")
+
+
+def adam_step(p, g, m, v, *, lr, beta1, beta2, eps, step, gnorm_sq=None, max_norm=0.0, grad_scale=1.0, p16=None):
+    check(load().fb_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1), float(beta2),
+                              float(eps), int(step), _ptr(gnorm_sq), float(max_norm), float(grad_scale), _ptr(p16),
+                              stream_ptr()), "fb_adam_step")
+
+
+def cast_bf16(x32, out16):
+    check(load().fb_cast_f32_bf16(_ptr(x32), x32.numel(), _ptr(out16), stream_ptr()), "fb_cast_f32_bf16")
+
+
+def attn_bwd_prep(s2, lse, dp, ctx, dctx, ds, pd, z1, z2, *, B, L, h, scale, dropout_p=0.0, seed=0, offset=0):
+    rel_rows, rel_off = rel_table_geometry(L)
+    a = AttnBwdPrepArgs()
+    a.B, a.L, a.h, a.lp, a.rel_rows, a.rel_off = B, L, h, s2.shape[-1], rel_rows, rel_off
+    a.s2, a.lse, a.dp = _ptr(s2), _ptr(lse), _ptr(dp)
+    a.ctx, a.dctx, a.ldc = _ptr(ctx), _ptr(dctx), ctx.stride(0)
+    assert dctx.stride(0) == ctx.stride(0)
+    a.ds, a.pd, a.z1, a.z2 = _ptr(ds), _ptr(pd), _ptr(z1), _ptr(z2)
+    a.scale = float(scale)
+    a.dropout_p, a.seed, a.offset = float(dropout_p), int(seed), int(offset)
+    check(load().fb_attn_bwd_prep(C.byref(a), stream_ptr()), "fb_attn_bwd_prep")
+
+
+def rel_to_bucket(gpq, gpk, bucket_of_rel, L, h, out):
+    """gpq/gpk: fp32 [h, rel_rows, 64]; out: fp32 [2S, 2H], ACCUMULATES (PQ | PK column blocks)."""
+    rel_rows, rel_off = rel_table_geometry(L)
+    H = h * 64
+    check(load().fb_rel_to_bucket(_ptr(gpq), _ptr(gpk), H, h, _ptr(bucket_of_rel), rel_rows, rel_off, L, _ptr(out),
+                                  out.stride(0), stream_ptr()), "fb_rel_to_bucket")

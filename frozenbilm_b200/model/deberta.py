@@ -1,0 +1,373 @@
+"""DebertaV2ForMaskedLM drop-in (reference model/deberta.py:1288-1501).
+
+Same constructor arguments, parameter names / shapes / requires_grad pattern, ``forward`` signature,
+``set_answer_embeddings`` and outputs as the reference class; the arithmetic is executed by
+frozenbilm_b200.engine.DebertaEngine on the sm_100a kernels.  The torch sub-modules below are
+PARAMETER HOLDERS ONLY (so that ``state_dict()`` keys equal the reference's); they are never called.
+"""
+from __future__ import annotations
+
+import os
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+from ..config import FBConfig
+from ..engine import DebertaEngine
+from .. import lib
+
+
+class _Holder(nn.Module):
+    pass
+
+
+def _adapter(ds_factor, H):
+    m = _Holder()
+    m.down = nn.Linear(H, H // ds_factor)
+    m.up = nn.Linear(H // ds_factor, H)
+    return m
+
+
+class FBMaskedLMOutput(dict):
+    """Supports out["loss"], out["logits"], out.loss, out.logits like transformers' MaskedLMOutput
+    (reference deberta.py:1496-1501).  In the MLM-loss path ``logits`` ([B, F+Lt, V], 5.8 GB at the
+    WebVid shape) is materialised lazily on first access."""
+
+    def __init__(self, loss=None, logits=None, logits_fn=None):
+        super().__init__()
+        self._logits_fn = logits_fn
+        if loss is not None:
+            dict.__setitem__(self, "loss", loss)
+        if logits is not None:
+            dict.__setitem__(self, "logits", logits)
+
+    def __getitem__(self, k):
+        if isinstance(k, int):
+            return self.to_tuple()[k]
+        if k == "logits" and not dict.__contains__(self, "logits") and self._logits_fn is not None:
+            dict.__setitem__(self, "logits", self._logits_fn())
+        return dict.__getitem__(self, k)
+
+    def __contains__(self, k):
+        return dict.__contains__(self, k) or (k == "logits" and self._logits_fn is not None)
+
+    @property
+    def loss(self):
+        return self.get("loss")
+
+    @property
+    def logits(self):
+        return self["logits"] if "logits" in self else None
+
+    def to_tuple(self):
+        return tuple(self[k] for k in ("loss", "logits") if k in self)
+
+
+class _MLMLossFn(torch.autograd.Function):
+    """Bridges loss.backward() (main.py:81) to the hand-scheduled selective backward."""
+
+    @staticmethod
+    def forward(ctx, anchor, module, loss):
+        ctx.module = module
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, dloss):
+        ctx.module._run_backward(scale=float(dloss))
+        return None, None, None
+
+
+class _LogitsFn(torch.autograd.Function):
+    """Downstream mode (mc.py / videoqa.py): gradients arrive through the answer-head logits."""
+
+    @staticmethod
+    def forward(ctx, anchor, module, logits):
+        ctx.module = module
+        return logits.clone()
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        ctx.module._run_backward(dlogits=dlogits)
+        return None, None, None
+
+
+class DebertaV2ForMaskedLM(nn.Module):
+    def __init__(self, config, max_feats=10, features_dim=768, freeze_lm=True, freeze_mlm=True, ds_factor_attn=8,
+                 ds_factor_ff=8, ft_ln=True, dropout=0.1, n_ans=0, freeze_last=True):
+        super().__init__()
+        self.config = config
+        self.fb = FBConfig.from_hf(config, features_dim=features_dim, max_feats=max_feats,
+                                   ds_factor_attn=ds_factor_attn, ds_factor_ff=ds_factor_ff,
+                                   adapter_dropout=dropout, n_ans=n_ans, freeze_lm=freeze_lm, freeze_mlm=freeze_mlm,
+                                   ft_ln=ft_ln, freeze_last=freeze_last)
+        fb = self.fb
+        H, I, V = fb.hidden_size, fb.intermediate_size, fb.vocab_size
+        eps = fb.layer_norm_eps
+        # ---- parameter holders with the reference's module tree (deberta.py:950-995, 420-472, 1523-1570)
+        deb = _Holder()
+        emb = _Holder()
+        emb.word_embeddings = nn.Embedding(V, H, padding_idx=fb.pad_token_id)
+        emb.position_embeddings = nn.Embedding(fb.max_position_embeddings, H)
+        emb.LayerNorm = nn.LayerNorm(H, eps)
+        emb.register_buffer("position_ids", torch.arange(fb.max_position_embeddings).expand((1, -1)))
+        if features_dim:
+            emb.linear_video = nn.Linear(features_dim, H)
+        deb.embeddings = emb
+        enc = _Holder()
+        layers = []
+        for _ in range(fb.num_hidden_layers):
+            lay = _Holder()
+            att = _Holder()
+            sa = _Holder()
+            sa.query_proj, sa.key_proj, sa.value_proj = nn.Linear(H, H), nn.Linear(H, H), nn.Linear(H, H)
+            att.self = sa
+            ao = _Holder()
+            ao.dense = nn.Linear(H, H)
+            ao.LayerNorm = nn.LayerNorm(H, eps)
+            if ds_factor_attn:
+                ao.adapter = _adapter(ds_factor_attn, H)
+            att.output = ao
+            lay.attention = att
+            inter = _Holder()
+            inter.dense = nn.Linear(H, I)
+            lay.intermediate = inter
+            out = _Holder()
+            out.dense = nn.Linear(I, H)
+            out.LayerNorm = nn.LayerNorm(H, eps)
+            if ds_factor_ff:
+                out.adapter = _adapter(ds_factor_ff, H)
+            lay.output = out
+            layers.append(lay)
+        enc.layer = nn.ModuleList(layers)
+        enc.rel_embeddings = nn.Embedding(2 * fb.position_buckets, H)
+        enc.LayerNorm = nn.LayerNorm(H, eps, elementwise_affine=True)
+        conv = _Holder()
+        conv.conv = nn.Conv1d(H, H, 3, padding=1)
+        conv.LayerNorm = nn.LayerNorm(H, eps)
+        enc.conv = conv
+        deb.encoder = enc
+        self.deberta = deb
+        head = _Holder()
+        lm = _Holder()
+        lm.dense = nn.Linear(H, H)
+        lm.LayerNorm = nn.LayerNorm(H, eps=eps)
+        lm.decoder = nn.Linear(H, V, bias=False)   # allocated but unused by forward, like the reference (:1535-1542)
+        lm.bias = nn.Parameter(torch.zeros(V))
+        lm.decoder.bias = lm.bias
+        head.lm_head = lm
+        self.lm_predictions = head
+        self.features_dim = features_dim
+        self.n_ans = n_ans
+        self._init_weights()
+        # ---- freezing rules (deberta.py:1152-1158, 1334-1339)
+        if freeze_lm:
+            for n, p in self.deberta.named_parameters():
+                if ("linear_video" not in n) and ("adapter" not in n):
+                    if ft_ln and "LayerNorm" in n:
+                        continue
+                    p.requires_grad_(False)
+        if freeze_mlm:
+            for n, p in self.lm_predictions.named_parameters():
+                if ft_ln and "LayerNorm" in n:
+                    continue
+                p.requires_grad_(False)
+        if n_ans:
+            self.answer_embeddings = nn.Embedding(n_ans, H)
+            self.answer_bias = nn.Parameter(torch.zeros(n_ans))
+            if freeze_last:
+                self.answer_embeddings.requires_grad_(False)
+                self.answer_bias.requires_grad_(False)
+        self._engine_obj = None
+        self._flat = None
+        self._anchor = None
+
+    # ------------------------------------------------------------------ init / load
+    def _init_weights(self):
+        """N(0, initializer_range) matrices, zero biases, unit LayerNorm (deberta.py _init_weights);
+        adapters N(0, 1e-3) clamped to +-2e-3, biases included (adapter.py:23-28)."""
+        std = getattr(self.config, "initializer_range", 0.02)
+        for name, m in self.named_modules():
+            if isinstance(m, (nn.Linear, nn.Conv1d)):
+                if ".adapter." in name:
+                    nn.init.normal_(m.weight, std=1e-3)
+                    nn.init.normal_(m.bias, std=1e-3)
+                    m.weight.data.clamp_(-2e-3, 2e-3)
+                    m.bias.data.clamp_(-2e-3, 2e-3)
+                elif isinstance(m, nn.Linear):
+                    m.weight.data.normal_(0.0, std)
+                    if m.bias is not None:
+                        m.bias.data.zero_()
+            elif isinstance(m, nn.Embedding):
+                m.weight.data.normal_(0.0, std)
+                if m.padding_idx is not None:
+                    m.weight.data[m.padding_idx].zero_()
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, local_files_only=True, **kw):
+        """Loads an HF-format DeBERTa-V2 directory (config.json + pytorch_model.bin / model.safetensors),
+        like PreTrainedModel.from_pretrained in the reference (model/__init__.py:34-47)."""
+        from transformers import DebertaV2Config
+
+        path = pretrained_model_name_or_path
+        config = DebertaV2Config.from_pretrained(path, local_files_only=local_files_only)
+        model = cls(config=config, **kw)
+        sd = None
+        st = os.path.join(path, "model.safetensors")
+        pt = os.path.join(path, "pytorch_model.bin")
+        if os.path.exists(st):
+            from safetensors.torch import load_file
+
+            sd = load_file(st)
+        elif os.path.exists(pt):
+            sd = torch.load(pt, map_location="cpu")
+        else:
+            raise FileNotFoundError(f"no model.safetensors / pytorch_model.bin under {path}")
+        sd = {k.replace("lm_predictions.lm_head.LayerNorm.gamma", "lm_predictions.lm_head.LayerNorm.weight")
+               .replace("lm_predictions.lm_head.LayerNorm.beta", "lm_predictions.lm_head.LayerNorm.bias"): v
+              for k, v in sd.items()}
+        model.load_state_dict(sd, strict=False)
+        return model
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    # ------------------------------------------------------------------ flat trainable bucket
+    def _param_dict(self):
+        return OrderedDict((n, p) for n, p in self.named_parameters())
+
+    def _ensure_engine(self):
+        dev = self.device
+        if dev.type != "cuda":
+            raise lib.FbError("frozenbilm_b200 has no CPU path: call model.to('cuda') before forward()")
+        named = self._param_dict()
+        train = [(n, p) for n, p in named.items() if p.requires_grad]
+        sig = tuple((n, p.data_ptr()) for n, p in train)
+        if self._flat is None or self._flat["sig"] != sig or self._flat["flat32"].device != dev:
+            # (re)build the flat fp32 bucket; parameters become views so that one NCCL all-reduce / one
+            # fused Adam kernel covers the whole trainable set
+            total = sum(p.numel() for _, p in train)
+            total_pad = (total + 7) // 8 * 8
+            flat32 = torch.zeros(total_pad, device=dev, dtype=torch.float32)
+            slices, off = {}, 0
+            for n, p in train:
+                k = p.numel()
+                flat32[off:off + k].copy_(p.data.reshape(-1))
+                p.data = flat32[off:off + k].view(p.shape)
+                slices[n] = (off, off + k, tuple(p.shape))
+                off += k
+            self._flat = dict(flat32=flat32, flat16=torch.empty(total_pad, device=dev, dtype=torch.bfloat16),
+                              grad32=torch.zeros(total_pad, device=dev, dtype=torch.float32), slices=slices,
+                              sig=tuple((n, p.data_ptr()) for n, p in train), version=-1, total=total)
+            self._engine_obj = None
+        if self._engine_obj is None:
+            P = {n: p.data for n, p in named.items() if "decoder" not in n}
+            self._engine_obj = DebertaEngine(self.fb, P, dev)
+            self._anchor = torch.zeros(1, device=dev, requires_grad=True)
+            self._flat["version"] = -1
+        fl = self._flat
+        ver = fl["flat32"]._version + sum(p._version for n, p in train)
+        if fl["version"] != ver:
+            self._engine_obj.refresh_trainable(fl["flat32"], fl["flat16"], fl["slices"])
+            fl["version"] = fl["flat32"]._version + sum(p._version for n, p in train)
+        return self._engine_obj
+
+    def flat_buffers(self):
+        """(flat fp32 params, flat fp32 grads, flat bf16 copy) of the trainable set (after the first forward)."""
+        self._ensure_engine()
+        return self._flat["flat32"], self._flat["grad32"], self._flat["flat16"]
+
+    # ------------------------------------------------------------------ reference API
+    def set_answer_embeddings(self, a2tok, freeze_last=True):
+        """Reference deberta.py:1358-1380: mean word embedding of the non-pad answer tokens.  The reference
+        assigns the bias to an ATTRIBUTE (``answer_bias.weight``, :1375), so ``answer_bias`` itself keeps its
+        values; that observable behaviour is reproduced."""
+        we = self.deberta.embeddings.word_embeddings.weight
+        pad = self.fb.pad_token_id
+        a2tok = a2tok.to(we.device)
+        a2v = we.data[a2tok]
+        nz = (a2tok != pad)
+        sum_tokens = nz.sum(1, keepdim=True)
+        if len(a2v) != self.n_ans:
+            assert not self.training
+            self.n_ans = len(a2v)
+            self.answer_embeddings = nn.Embedding(self.n_ans, self.fb.hidden_size).to(we.device)
+            self.answer_bias.requires_grad = False
+            self.answer_bias.resize_(self.n_ans)
+            self.fb = self.fb.replace(n_ans=self.n_ans)
+            self._engine_obj = None
+            self._flat = None
+        self.answer_embeddings.weight.data = torch.div((a2v * nz.float()[:, :, None]).sum(1), sum_tokens.clamp(min=1))
+        if freeze_last:
+            self.answer_embeddings.requires_grad_(False)
+            self.answer_bias.requires_grad_(False)
+        if self._engine_obj is not None:
+            self._engine_obj.P["answer_embeddings.weight"] = self.answer_embeddings.weight.data
+            self._engine_obj.refresh_answer_embeddings()
+
+    def forward(self, input_ids=None, attention_mask=None, token_type_ids=None, position_ids=None, inputs_embeds=None,
+                labels=None, output_attentions=None, return_dict=None, video=None, video_mask=None, mlm=False):
+        if input_ids is None:
+            if inputs_embeds is not None:
+                raise NotImplementedError("inputs_embeds is not supported by the fused path")
+            raise ValueError("You have to specify either input_ids or inputs_embeds")
+        eng = self._ensure_engine()
+        dev = self.device
+        B, Lt = input_ids.shape
+        use_video = bool(self.features_dim) and video is not None
+        F = video.shape[1] if use_video else 0
+        L = F + Lt
+        training = self.training and torch.is_grad_enabled()
+        fb = self.fb
+        if labels is not None:
+            labels = labels.to(dev)
+            flat_lab = torch.cat([torch.full((B, F), -100, dtype=torch.long, device=dev), labels], 1).reshape(-1) \
+                if F else labels.reshape(-1)
+            sel = torch.nonzero(flat_lab != -100).reshape(-1)        # one host sync, before any kernel is queued
+            n_sel = int(sel.numel())
+        with torch.no_grad():
+            eng.forward_encoder(video, video_mask, input_ids, attention_mask, training)
+            if labels is not None:
+                if n_sel == 0:
+                    loss = torch.full((), float("nan"), device=dev)
+                else:
+                    loss = eng.head_mlm_loss(sel, flat_lab[sel].contiguous(), n_sel, want_grad=training)
+            else:
+                logits = self._full_logits(eng, B, L, mlm=mlm)
+        if labels is not None:
+            logits_fn = lambda: self._full_logits(eng, B, L, mlm=True, scratch=True)
+            if training and n_sel > 0:
+                loss = _MLMLossFn.apply(self._anchor, self, loss)
+            return FBMaskedLMOutput(loss=loss, logits_fn=logits_fn)
+        if training:
+            logits = _LogitsFn.apply(self._anchor, self, logits)
+        return FBMaskedLMOutput(logits=logits)
+
+    def _full_logits(self, eng, B, L, mlm, keep_for_backward=False, scratch=False):
+        T = B * L
+        n = self.fb.vocab_size if (mlm or not self.fb.n_ans) else self.fb.n_ans
+        out = torch.empty(T, n, device=self.device, dtype=torch.float32)
+        with torch.no_grad():
+            eng.head_logits(eng.o2_16, T, mlm=(mlm or not self.fb.n_ans), out=out, scratch=scratch)
+        return out.view(B, L, n)
+
+    # ------------------------------------------------------------------ backward bridge
+    def _run_backward(self, scale=None, dlogits=None):
+        eng = self._engine_obj
+        fl = self._flat
+        named = self._param_dict()
+        train = [(n, p) for n, p in named.items() if p.requires_grad]
+        views = {n: fl["grad32"][a:b].view(shape) for n, (a, b, shape) in fl["slices"].items()}
+        aliased = [p.grad is not None and p.grad.data_ptr() == views[n].data_ptr() for n, p in train]
+        if not all(aliased):
+            # fresh step (zero_grad(set_to_none=True)) or foreign .grad tensors: start the bucket from zero
+            foreign = {n: p.grad for (n, p), al in zip(train, aliased) if p.grad is not None and not al}
+            fl["grad32"].zero_()
+        else:
+            foreign = {}
+        eng.backward(views, scale=scale, dlogits=dlogits)
+        for n, p in train:
+            if n in foreign:
+                views[n].add_(foreign[n])
+            p.grad = views[n]

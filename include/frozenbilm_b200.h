@@ -37,12 +37,16 @@ long long fb_launch_count(void);
  * K=3H GEMM), :1545-1556 (head dense + vocab GEMM), :993 (linear_video), and their dX/dW in
  * the selective backward (torch autograd in the reference, main.py:81).
  * ------------------------------------------------------------------------------------------ */
+/* One dropout site: masks are Philox4x32-10(seed; row, col/8, offset) at 16-bit resolution, so the
+ * backward regenerates them from (seed, offset) instead of storing them.  p = 0 disables. */
+typedef struct fb_dropout { float p; unsigned long long seed; unsigned long long offset; } fb_dropout;
+
 enum { FB_ACT_NONE = 0, FB_ACT_GELU = 1, FB_ACT_RELU = 2 };
 enum { FB_AUX_NONE = 0, FB_AUX_MUL_GELU_GRAD = 1, FB_AUX_MUL_RELU_MASK = 2, FB_AUX_ADD = 3 };
 enum { FB_DT_BF16 = 0, FB_DT_F32 = 1 };
 
 typedef struct fb_gemm_args {
-  int M, N, K, batch;
+  int M, N, K, batch;         /* batch = number of OUTER batches (stride_*) */
   /* A: a_mn_major = 0 -> stored [M, K] (lda = row pitch); 1 -> stored [K, M] */
   const void* A; long long lda; long long stride_a; int a_mn_major;
   /* B: b_mn_major = 0 -> stored [N, K] (nn.Linear weight layout); 1 -> stored [K, N] */
@@ -59,6 +63,11 @@ typedef struct fb_gemm_args {
                                  (requires d_dtype = F32 and accumulate semantics; bias/aux/resid
                                  applied by split 0 only) */
   int block_n;                /* 0 = auto, else 64 | 128 | 192 | 256 */
+  /* optional second (inner) batch level, e.g. heads inside a token row: total = batch * batch_inner */
+  int batch_inner; long long stride_a_in, stride_b_in, stride_d_in;
+  const unsigned char* rowmask;  /* optional uint8 [M]: v = 0 for rows with rowmask == 0 (after bias) */
+  fb_dropout drop; int drop_pos; /* 0 none, 1 = after bias/rowmask (before D_pre and act),
+                                    2 = after act/aux (before resid); element id = (row, col) */
 } fb_gemm_args;
 
 int fb_gemm(const fb_gemm_args* args, void* stream);
@@ -85,9 +94,33 @@ typedef struct fb_attn_args {
   float* lse;
   float scale;
   float dropout_p; unsigned long long seed; unsigned long long offset;
+  float* s_out;   /* optional fp32 [B, h, L, ceil128(L)]: masked scaled scores in the log2 domain, kept for
+                     the backward (training only) */
 } fb_attn_args;
 
 int fb_attn_fwd(const fb_attn_args* args, void* stream);
+
+/* Attention backward (autograd through deberta.py:769-808 in the reference), staged so that every
+ * contraction is an fb_gemm:
+ *   dP  = dO . V^T                                  (fb_gemm, batched over (b, h))
+ *   fb_attn_bwd_prep: P = exp2(s2 - lse); dS = P * (dropout_bwd(dP) - rowsum(dO*O)) * scale, written as
+ *        ds [B,h,L,lp], pd [B,h,L,lp] (dropped probabilities), z1 / z2 [h, B*L, rel_rows] = dS regrouped by
+ *        relative position for the c2p / p2c terms
+ *   dV = pd^T . dO ; dQ = ds . K + z1 . PKrel ; dK = ds^T . Q + z2 . PQrel ;
+ *   dPKrel = z1^T . Q ; dPQrel = z2^T . K          (fb_gemm), then fb_rel_to_bucket folds them onto the
+ *   2S bucket rows of d(Linear_{q|k}(rel_emb)). */
+typedef struct fb_attn_bwd_prep_args {
+  int B, L, h, lp, rel_rows, rel_off;
+  const float* s2; const float* lse;        /* from fb_attn_fwd (s_out, lse) */
+  const void* dp;                            /* bf16 [B,h,L,lp] */
+  const void* ctx; const void* dctx; long long ldc;   /* bf16 [B*L, ldc] */
+  void* ds; void* pd; void* z1; void* z2;    /* bf16 outputs */
+  float scale;
+  float dropout_p; unsigned long long seed; unsigned long long offset;
+} fb_attn_bwd_prep_args;
+int fb_attn_bwd_prep(const fb_attn_bwd_prep_args* args, void* stream);
+int fb_rel_to_bucket(const float* gpq, const float* gpk, int H, int h, const int* bucket_of_rel, int rel_rows,
+                     int rel_off, int L, float* out, long long ldo, void* stream);
 
 /* Expands pqk = Linear_{q|k}(rel_emb) ([2S, 2H] bf16: PQ in cols [0,H), PK in [H,2H); deberta.py:847-853)
  * into the per-relative-position tables used above: out[hh][row] = pqk[bucket_of_rel[row - rel_off + 511]].
@@ -95,6 +128,52 @@ int fb_attn_fwd(const fb_attn_args* args, void* stream);
  * (make_log_bucket_position, deberta.py:578-589).  Rows with |rel| >= L are zero. */
 int fb_build_rel_tables(const void* pqk, long long ld, int H, int h, const int* bucket_of_rel, int rel_rows,
                         int rel_off, int L, void* out_pq, void* out_pk, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * HBM-bound row kernels (fb_elementwise.cu).  All matrices are dense row-major [M, H].
+ * ------------------------------------------------------------------------------------------ */
+/* y = dropout(LayerNorm(x) * rowmask): torch LayerNorm (+ "* mask" + StableDropout) at
+ * deberta.py:1043-1054 (embeddings), :259/:333 (sub-layer outputs), :405-417 (conv), :474-478 (relative
+ * embeddings), :1547 (head).  Writes fp32 and/or bf16 copies plus the row statistics for the backward. */
+int fb_layernorm_fwd(const float* x, int M, int H, const float* gamma, const float* beta, float eps,
+                     const unsigned char* rowmask, const fb_dropout* out_drop, float* y_f32, void* y_bf16,
+                     float* mean, float* rstd, void* stream);
+/* Backward of the above (autograd in the reference).  dx_f32: gradient of the LN input; dx_bf16: the same with
+ * the upstream hidden dropout (in_drop) backward applied, ready as a GEMM operand; dgamma/dbeta ACCUMULATE. */
+int fb_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                     int M, int H, const unsigned char* rowmask, const fb_dropout* out_drop,
+                     const fb_dropout* in_drop, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
+                     void* stream);
+/* out[idx_out[r],:] = in[idx_in[r],:] with fp32<->bf16 conversion (null index array = identity, <0 skips):
+ * word_embeddings lookup (deberta.py:1013) and the labelled-position gather/scatter of the MLM head. */
+int fb_move_rows(const void* in, long long ld_in, int in_bf16, const long long* idx_in, const long long* idx_out,
+                 int R, int ncols, void* out, long long ld_out, int out_bf16, void* stream);
+/* out_bf16 = dy * gelu'(pre) [* dropout_bwd] [* rowmask]: GELU backward of the conv branch (deberta.py:401-403)
+ * and of the MLM head transform (deberta.py:1545-1546). */
+int fb_gelu_bwd(const float* dy, const void* pre_bf16, int M, int N, const unsigned char* rowmask,
+                const fb_dropout* drop, void* out_bf16, void* stream);
+/* out[b,l,:] = a[b,l,:] + pos[l,:]: z = position_embeddings + h[-2] of the enhanced mask decoder
+ * (deberta.py:1394-1396); fp32 and bf16 copies. */
+int fb_add_rowbcast(const float* a, const float* b, int B, int L, int H, float* out_f32, void* out_bf16,
+                    void* stream);
+/* Conv1d(H, H, k=3, pad=1) over the sequence (deberta.py:395-400) as a K = 3H GEMM: im2col / col2im. */
+int fb_conv_im2col(const void* x_bf16, int B, int L, int H, void* out_bf16, void* stream);
+int fb_conv_col2im(const void* dcol_bf16, int B, int L, int H, float* dx, int accumulate, void* stream);
+/* out[n] += sum_m x[m, n]: bias gradients of the adapters / linear_video. */
+int fb_colsum_bf16(const void* x, long long ld, int M, int N, float* out, void* stream);
+/* CrossEntropyLoss over fp32 logits [P, V] (deberta.py:1481-1488): *loss_sum += loss_scale * sum_rows CE;
+ * dlogits (bf16, nullable) = (softmax - onehot) * grad_scale. */
+int fb_cross_entropy(const float* logits, long long ld, int P, int V, const long long* labels, float* loss_sum,
+                     float loss_scale, void* dlogits_bf16, long long ldd, float grad_scale, void* stream);
+/* out = dropout(x) as fp32 (optionally accumulating) and/or bf16: relative-embedding dropout, deberta.py:779. */
+int fb_dropout_apply(const float* x, int M, int N, const fb_dropout* drop, float* out_f32, int accumulate,
+                     void* out_bf16, void* stream);
+/* clip_grad_norm_ + Adam over a flat fp32 bucket (main.py:82-84, args.py:246-275), refreshing the bf16 copy. */
+int fb_sumsq(const float* g, long long n, float* out, void* stream);
+int fb_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                 float eps, int step, const float* gnorm_sq, float max_norm, float grad_scale, void* p_bf16,
+                 void* stream);
+int fb_cast_f32_bf16(const float* x, long long n, void* out, void* stream);
 
 #ifdef __cplusplus
 }
