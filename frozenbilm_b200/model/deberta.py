@@ -273,6 +273,12 @@ class DebertaV2ForMaskedLM(nn.Module):
             fl["version"] = fl["flat32"]._version + sum(p._version for n, p in train)
         return self._engine_obj
 
+    def _mark_trainable_fresh(self):
+        """Called by the fused optimizer after it updated flat32 AND its bf16 copy in one kernel."""
+        fl = self._flat
+        train = [p for p in self.parameters() if p.requires_grad]
+        fl["version"] = fl["flat32"]._version + sum(p._version for p in train)
+
     def flat_buffers(self):
         """(flat fp32 params, flat fp32 grads, flat bf16 copy) of the trainable set (after the first forward)."""
         self._ensure_engine()

@@ -1,0 +1,55 @@
+"""Fused clip_grad_norm_ + Adam over the flat trainable bucket (reference main.py:82-84: clip at
+args.max_norm = 0.1, torch.optim.Adam with betas (0.9, 0.95), args.py:246-275), plus the data-parallel
+gradient all-reduce the reference lacks: ONE NCCL all-reduce of the ~29.7 M-element bucket.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import lib
+
+
+class FusedClipAdam:
+    def __init__(self, model, lr=3e-5, betas=(0.9, 0.95), eps=1e-8, max_norm=0.1):
+        self.model = model
+        self.lr, self.betas, self.eps, self.max_norm = lr, betas, eps, max_norm
+        self.step_count = 0
+        self.m = self.v = None
+        self.norm_sq = None
+
+    def _state(self):
+        p32, g32, p16 = self.model.flat_buffers()
+        if self.m is None or self.m.numel() != p32.numel():
+            self.m = torch.zeros_like(p32)
+            self.v = torch.zeros_like(p32)
+            self.norm_sq = torch.zeros(1, device=p32.device)
+        return p32, g32, p16
+
+    def zero_grad(self):
+        _, g32, _ = self._state()
+        g32.zero_()
+
+    def step(self):
+        """all-reduce (if a process group is up) -> global-norm clip -> Adam -> refresh bf16 operand copies."""
+        p32, g32, p16 = self._state()
+        scale = 1.0
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(g32)
+            scale = 1.0 / dist.get_world_size()
+        self.step_count += 1
+        self.norm_sq.zero_()
+        lib.sumsq(g32, self.norm_sq)
+        lib.adam_step(p32, g32, self.m, self.v, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
+                      step=self.step_count, gnorm_sq=self.norm_sq, max_norm=self.max_norm, grad_scale=scale, p16=p16)
+        self.model._mark_trainable_fresh()
+
+
+def broadcast_trainable(model, src=0):
+    """One-time broadcast of the trainable bucket: the reference seeds every rank differently BEFORE building the
+    model (main.py:168-171), so unsynchronised replicas start from different adapters; this build deliberately
+    starts all replicas from rank `src`'s values."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        p32, _, _ = model.flat_buffers()
+        dist.broadcast(p32, src)
+        model._ensure_engine()
