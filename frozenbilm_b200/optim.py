@@ -10,6 +10,26 @@ import torch.distributed as dist
 from . import lib
 
 
+def allreduce_sum_and_scale(flat: torch.Tensor) -> float:
+    """ONE collective over the flat gradient bucket (NCCL over NVLink on GPUs; gloo in the CPU tests).  Returns the
+    1/world factor that the caller folds into the fused clip+Adam kernel instead of a separate scaling pass."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat)
+        return 1.0 / dist.get_world_size()
+    return 1.0
+
+
+def broadcast_flat(flat: torch.Tensor, src: int = 0) -> None:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(flat, src)
+
+
+def shard_seed(base_seed: int, rank: int, step_block: int) -> int:
+    """Per-rank, per-batch seed of the synthetic data shard (each rank draws a different batch, weights share
+    `base_seed`): the data-parallel partition of bench.py."""
+    return base_seed + rank + 1000 * step_block
+
+
 class FusedClipAdam:
     def __init__(self, model, lr=3e-5, betas=(0.9, 0.95), eps=1e-8, max_norm=0.1):
         self.model = model
@@ -33,10 +53,7 @@ class FusedClipAdam:
     def step(self):
         """all-reduce (if a process group is up) -> global-norm clip -> Adam -> refresh bf16 operand copies."""
         p32, g32, p16 = self._state()
-        scale = 1.0
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(g32)
-            scale = 1.0 / dist.get_world_size()
+        scale = allreduce_sum_and_scale(g32)
         self.step_count += 1
         self.norm_sq.zero_()
         lib.sumsq(g32, self.norm_sq)
@@ -51,5 +68,5 @@ def broadcast_trainable(model, src=0):
     starts all replicas from rank `src`'s values."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         p32, _, _ = model.flat_buffers()
-        dist.broadcast(p32, src)
+        broadcast_flat(p32, src)
         model._ensure_engine()
