@@ -257,13 +257,30 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
 }
 
 // ---- math ----
+// erf-GELU (transformers ACT2FN["gelu"]) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below the
+// bf16 operand precision): one rcp + one ex2 + 7 FMA instead of the ~25-instruction erff(), so that the GEMM
+// epilogue stays off the MMA critical path.  `e` = exp(-x^2/2) is shared with the derivative.
+__device__ __forceinline__ float erf_as_core(float x, float& e_out) {
+  const float u = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = exp2f(-u * u * 1.4426950408889634f);
+  e_out = e;
+  return copysignf(fmaf(-poly, e, 1.0f), x);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  float e;
+  const float erfv = erf_as_core(x, e);
+  return 0.5f * x * (1.0f + erfv);
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float e;
+  const float erfv = erf_as_core(x, e);
+  return fmaf(x * 0.39894228040143267794f, e, 0.5f * (1.0f + erfv));
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);

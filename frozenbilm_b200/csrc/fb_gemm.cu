@@ -6,7 +6,8 @@
 //   warp 0      TMA producer: cp.async.bulk.tensor (128B-swizzled boxes) -> smem ring
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma 128 x BN x 16, commits to mbarriers
 //   warp 2      TMEM allocator (2 accumulator stages so the epilogue of tile i overlaps tile i+1)
-//   warps 4-7   epilogue: tcgen05.ld (lane = output row) -> bias/activation/aux/residual -> global
+//   warps 4-11  epilogue (two warpgroups, each half of the tile columns): tcgen05.ld (lane = output row)
+//               -> bias/activation/aux/dropout/residual -> global
 //
 // Both operands may be K-major (nn.Linear layout) or MN-major (the transposed view), selected in
 // the UMMA instruction/smem descriptors, so dX = dY.W and dW = dY^T.X need no explicit transposes.
@@ -28,7 +29,7 @@ namespace fb {
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 static constexpr int A_STAGE_BYTES = BM * BK * 2;
-static constexpr int NUM_THREADS = 256;
+static constexpr int NUM_THREADS = 384;  // warps 0-2: TMA / MMA / TMEM alloc, warp 3 idle, warps 4-11: epilogue
 
 template <int BN>
 struct GemmCfg {
@@ -223,7 +224,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 8);
     }
     fence_barrier_init();
   }
@@ -315,7 +316,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int wq = warp & 3;  // TMEM lane quarter this warp may access
+    const int wq = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;   // which half of the tile's 32-column chunks this warpgroup drains
+    constexpr int CHUNKS = BN / 32, HALF_CHUNKS = (CHUNKS + 1) / 2;
+    const int c_begin = half * HALF_CHUNKS, c_end = (half == 0) ? HALF_CHUNKS : CHUNKS;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       int split, b, mb, nb;
@@ -327,7 +331,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const int row = mb * BM + wq * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * Cfg::ACC_STRIDE;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         uint32_t acc[32];
         tmem_ld_32x32(taddr + c * 32, acc);
         tmem_ld_wait();

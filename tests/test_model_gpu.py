@@ -197,11 +197,11 @@ def test_full_width_properties_xl_dims():
     perm = torch.tensor([2, 0, 3, 1], device=DEV)
     model.zero_grad(set_to_none=True)
     out2 = model(labels=lab[perm], **{k: v[perm] for k, v in kw.items()})
-    (3.0 * out2["loss"]).backward()
+    (4.0 * out2["loss"]).backward()   # power of two: scaled bf16 operands round identically
     g2 = torch.cat([p.grad.reshape(-1).clone() for p in model.parameters() if p.requires_grad])
     assert (out2["logits"] - lg[perm]).abs().max().item() <= 1e-3
     assert abs(out2["loss"].item() - out["loss"].item()) <= 1e-4
-    rel = ((g2 - 3.0 * g1).norm() / (3.0 * g1).norm()).item()
+    rel = ((g2 - 4.0 * g1).norm() / (4.0 * g1).norm()).item()
     assert rel <= 2e-3, rel   # fp32 atomics in split-K dW / LayerNorm gradients make this order-dependent
 
 
