@@ -24,13 +24,14 @@
 
 namespace fb {
 
-static constexpr int AT_THREADS = 192;   // warps 0-3 softmax (thread = query row), 4 = TMA+MMA, 5 = TMEM alloc
+static constexpr int AT_THREADS = 320;   // warps 0-7: two softmax warpgroups (thread = query row, warpgroup =
+                                         // half of the keys), warp 8 = TMA+MMA control, warp 9 = TMEM alloc
 static constexpr int T_PITCH = 136;      // halves per staging row: 272 B -> conflict-free LDS.128
 static constexpr uint32_t OFF_Q = 0, OFF_K = 16384, OFF_V = 32768, OFF_PK = 49152, OFF_PQ = 81920,
                           OFF_P = 114688, OFF_T1 = 147456, OFF_T2 = OFF_T1 + 128 * T_PITCH * 2,
                           OFF_KMASK = OFF_T2 + 128 * T_PITCH * 2, OFF_BARS = OFF_KMASK + 128,
                           AT_SMEM = OFF_BARS + 128 + 1024;
-static constexpr uint32_t TM_S = 0, TM_X = 128, TM_O = 384;
+static constexpr uint32_t TM_S = 0, TM_X = 128, TM_O = 384;   // O: two 64-column halves (one per warpgroup)
 
 struct AttnParams {
   int B, L, h, nkb, rel_off;
@@ -56,9 +57,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint64_t* bar_mma1 = bars + 3;
   uint64_t* bar_xfree = bars + 4;
   uint64_t* bar_mma2 = bars + 5;
-  uint64_t* bar_pready = bars + 6;
-  uint64_t* bar_mma3 = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_pready = bars + 6;   // [2], one per softmax warpgroup
+  uint64_t* bar_mma3 = bars + 8;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
   __half* T1 = reinterpret_cast<__half*>(smem + OFF_T1);
   __half* T2 = reinterpret_cast<__half*>(smem + OFF_T2);
   uint8_t* kmask = smem + OFF_KMASK;
@@ -66,15 +67,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * 128, hh = blockIdx.y, b = blockIdx.z;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
     tma_prefetch_desc(&map_pk); tma_prefetch_desc(&map_pq);
     mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1);
-    mbar_init(bar_mma1, 1); mbar_init(bar_xfree, 4); mbar_init(bar_mma2, 1);
-    mbar_init(bar_pready, 4); mbar_init(bar_mma3, 1);
+    mbar_init(bar_mma1, 1); mbar_init(bar_xfree, 8); mbar_init(bar_mma2, 1);
+    mbar_init(&bar_pready[0], 4); mbar_init(&bar_pready[1], 4);
+    mbar_init(&bar_mma3[0], 1); mbar_init(&bar_mma3[1], 1);
     fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -83,7 +85,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (elect_one_sync()) {
       // ======================= TMA + MMA control thread =======================
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
@@ -122,8 +124,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     make_smem_desc_sw128(sPQ + k * 32, 16, 1024), idesc_band, k > 0);
         umma_commit(bar_mma1);
         if (kb > 0) {
-          // the previous block's P.V must retire before its V tile is overwritten
-          mbar_wait(bar_mma3, (kb - 1) & 1);
+          // the previous block's P.V (both halves) must retire before its V tile is overwritten
+          mbar_wait(&bar_mma3[0], (kb - 1) & 1);
+          mbar_wait(&bar_mma3[1], (kb - 1) & 1);
           load_v(kb);
         }
         mbar_wait(bar_xfree, ph);
@@ -135,23 +138,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         umma_commit(bar_mma2);
         mbar_wait(bar_mma2, ph);  // K / PK / PQ tiles are free again
         if (kb + 1 < p.nkb) load_k(kb + 1);
-        mbar_wait(bar_pready, ph);
-        tc_fence_after();
         mbar_wait(bar_v, ph);
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          // O_g = P[:, 64g:64g+64] . V[64g:64g+64, :]   (each softmax warpgroup owns one half of the keys)
+          mbar_wait(&bar_pready[g], ph);
+          tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem + TM_O, make_smem_desc_sw128(sP + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                    make_smem_desc_sw128(sV + k * 2048, 16, 1024), idesc_pv, k > 0);
-        umma_commit(bar_mma3);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + TM_O + 64 * g, make_smem_desc_sw128(sP + g * 16384 + k * 32, 16, 1024),
+                      make_smem_desc_sw128(sV + (4 * g + k) * 2048, 16, 1024), idesc_pv, k > 0);
+          umma_commit(&bar_mma3[g]);
+        }
       }
     }
     __syncwarp();
-  } else if (warp < 4) {
-    // ======================= softmax warps: thread = query row =======================
-    const int a = threadIdx.x;           // row in tile == TMEM lane
+  } else if (warp < 8) {
+    // ============ softmax warpgroups: thread = query row, warpgroup g = key columns [64g, 64g+64) ============
+    const int g = warp >> 2, wq = warp & 3;
+    const int a = wq * 32 + lane;        // row in tile == TMEM lane
     const int i = i0 + a;
     const bool valid_q = (i < p.L) && (p.mask[(long long)b * p.L + i] != 0);
-    const uint32_t lane_base = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
     const uint32_t rowid = static_cast<uint32_t>((b * p.h + hh) * p.L + i);
     const bool do_drop = p.drop_thresh16 != 0;
     float m_run = -INFINITY, l_run = 0.0f;
@@ -164,15 +172,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const int j0 = kb * 128;
       mbar_wait(bar_mma1, ph);
       tc_fence_after();
-      {
+      if (g == 0) {
         const int j = j0 + a;
         kmask[a] = (j < p.L) ? p.mask[(long long)b * p.L + j] : 0;
       }
-      // ---- p2c: this thread owns KEY row a of X2; scatter its window into T2[query][key]
+      // ---- p2c: lane = KEY row a of X2; scatter its 160-column window into T2[query][key].
+      //      The 5 chunks are shared between the warpgroups (g = 0: chunks 0-2, g = 1: chunks 3-4).
 #pragma unroll 1
-      for (int q = 0; q < 5; ++q) {
+      for (int q = (g == 0 ? 0 : 3); q < (g == 0 ? 3 : 5); ++q) {
         uint32_t v[32];
-        tmem_ld_32x32(lane_base + TM_X + (96 - 32 * warp + 32 * q), v);
+        tmem_ld_32x32(lane_base + TM_X + (96 - 32 * wq + 32 * q), v);
         tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
@@ -185,40 +194,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       if (lane == 0) mbar_arrive(bar_xfree);
       mbar_wait(bar_mma2, ph);
       tc_fence_after();
-      // ---- c2p: this thread owns QUERY row a of X1; un-skew its window into T1[query][key]
+      // ---- c2p: lane = QUERY row a of X1; keys b = a + 127 - c.  Warpgroup g needs b in [64g, 64g+64):
+      //      columns c in [a + 64(1-g), a + 64(1-g) + 63] -> 3 chunks starting at 32*wq + 64*(1-g).
 #pragma unroll 1
-      for (int q = 0; q < 5; ++q) {
+      for (int q = 0; q < 3; ++q) {
         uint32_t v[32];
-        tmem_ld_32x32(lane_base + TM_X + (32 * warp + 32 * q), v);
+        const int cbase = 32 * wq + 64 * (1 - g) + 32 * q;
+        tmem_ld_32x32(lane_base + TM_X + cbase, v);
         tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          const int bb = lane + 127 - 32 * q - e;
-          if (bb >= 0 && bb < 128) T1[a * T_PITCH + bb] = __float2half_rn(__uint_as_float(v[e]));
+          const int bb = a + 127 - (cbase + e);
+          if (bb >= 64 * g && bb < 64 * g + 64) T1[a * T_PITCH + bb] = __float2half_rn(__uint_as_float(v[e]));
         }
       }
-      named_bar_sync(1, 128);  // T2 / kmask were written by other threads
-      // ---- pass A: combine the three terms, mask, row max; park s in the S columns of TMEM
+      named_bar_sync(1, 256);  // T2 / kmask were written by other threads
+      // ---- pass A: combine the three terms, mask, row max over this warpgroup's 64 keys; park s in TMEM
       float mblk = -INFINITY;
 #pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 2; ++q) {
+        const int c0 = 64 * g + 32 * q;
         uint32_t v[32];
-        tmem_ld_32x32(lane_base + TM_S + 32 * q, v);
+        tmem_ld_32x32(lane_base + TM_S + c0, v);
         tmem_ld_wait();
-        const uint4* t1 = reinterpret_cast<const uint4*>(T1 + a * T_PITCH + 32 * q);
-        const uint4* t2 = reinterpret_cast<const uint4*>(T2 + a * T_PITCH + 32 * q);
-        const uint4 km0 = *reinterpret_cast<const uint4*>(kmask + 32 * q);
-        const uint4 km1 = *reinterpret_cast<const uint4*>(kmask + 32 * q + 16);
+        const uint4* t1 = reinterpret_cast<const uint4*>(T1 + a * T_PITCH + c0);
+        const uint4* t2 = reinterpret_cast<const uint4*>(T2 + a * T_PITCH + c0);
+        const uint4 km0 = *reinterpret_cast<const uint4*>(kmask + c0);
+        const uint4 km1 = *reinterpret_cast<const uint4*>(kmask + c0 + 16);
         const uint32_t kmw[8] = {km0.x, km0.y, km0.z, km0.w, km1.x, km1.y, km1.z, km1.w};
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint4 c1 = t1[g], c2 = t2[g];
+        for (int gg = 0; gg < 4; ++gg) {
+          const uint4 c1 = t1[gg], c2 = t2[gg];
           const uint32_t w1[4] = {c1.x, c1.y, c1.z, c1.w}, w2[4] = {c2.x, c2.y, c2.z, c2.w};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&w1[u]));
             const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w2[u]));
-            const int e = g * 8 + u * 2;
+            const int e = gg * 8 + u * 2;
             float s0 = (__uint_as_float(v[e]) + f1.x + f2.x) * p.scale_log2;
             float s1 = (__uint_as_float(v[e + 1]) + f1.y + f2.y) * p.scale_log2;
             if (!valid_q || ((kmw[e >> 2] >> (8 * (e & 3))) & 0xFF) == 0) s0 = -INFINITY;
@@ -228,25 +240,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             v[e + 1] = __float_as_uint(s1);
           }
         }
-        tmem_st_32x32(lane_base + TM_S + 32 * q, v);
+        tmem_st_32x32(lane_base + TM_S + c0, v);
         if (p.s_out != nullptr && i < p.L) {
-          float4* dst = reinterpret_cast<float4*>(p.s_out + (((long long)b * p.h + hh) * p.L + i) * p.lp + j0 + 32 * q);
+          float4* dst = reinterpret_cast<float4*>(p.s_out + (((long long)b * p.h + hh) * p.L + i) * p.lp + j0 + c0);
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            dst[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
-                                 __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+          for (int gg = 0; gg < 8; ++gg)
+            dst[gg] = make_float4(__uint_as_float(v[4 * gg]), __uint_as_float(v[4 * gg + 1]),
+                                  __uint_as_float(v[4 * gg + 2]), __uint_as_float(v[4 * gg + 3]));
         }
       }
       tmem_st_wait();
       const float m_new = fmaxf(m_run, mblk);
       const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
       const float alpha = exp2f(m_run - m_use);
-      // ---- pass B: probabilities -> bf16 A-operand tile (128B-swizzled, K-major), row sum
+      // ---- pass B: probabilities -> bf16 A-operand chunk g (128B-swizzled, K-major), partial row sum
       float rsum = 0.0f;
 #pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 2; ++q) {
+        const int c0 = 64 * g + 32 * q;
         uint32_t v[32];
-        tmem_ld_32x32(lane_base + TM_S + 32 * q, v);
+        tmem_ld_32x32(lane_base + TM_S + c0, v);
         tmem_ld_wait();
         float pr[32];
 #pragma unroll
@@ -256,20 +269,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         if (do_drop) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t keep = dropout_keep8(rowid, (j0 + 32 * q + 8 * g) >> 3, p.drop_thresh16, p.seed_lo,
+          for (int gg = 0; gg < 4; ++gg) {
+            const uint32_t keep = dropout_keep8(rowid, (j0 + c0 + 8 * gg) >> 3, p.drop_thresh16, p.seed_lo,
                                                 p.seed_hi, p.off_lo, p.off_hi);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) pr[8 * g + e] = ((keep >> e) & 1) ? pr[8 * g + e] * p.inv_keep : 0.0f;
+            for (int e = 0; e < 8; ++e) pr[8 * gg + e] = ((keep >> e) & 1) ? pr[8 * gg + e] * p.inv_keep : 0.0f;
           }
         }
-        // columns 32q .. 32q+31 -> chunk (q>>1), 16-byte units 4*(q&1) .. +3 of row a
-        uint8_t* prow = smem + OFF_P + (q >> 1) * 16384 + a * 128;
+        uint8_t* prow = smem + OFF_P + g * 16384 + a * 128;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint4 pk = make_uint4(pack_bf16(pr[8 * g], pr[8 * g + 1]), pack_bf16(pr[8 * g + 2], pr[8 * g + 3]),
-                                      pack_bf16(pr[8 * g + 4], pr[8 * g + 5]), pack_bf16(pr[8 * g + 6], pr[8 * g + 7]));
-          const int unit = ((q & 1) * 4 + g) ^ (a & 7);
+        for (int gg = 0; gg < 4; ++gg) {
+          const uint4 pk = make_uint4(pack_bf16(pr[8 * gg], pr[8 * gg + 1]), pack_bf16(pr[8 * gg + 2], pr[8 * gg + 3]),
+                                      pack_bf16(pr[8 * gg + 4], pr[8 * gg + 5]), pack_bf16(pr[8 * gg + 6], pr[8 * gg + 7]));
+          const int unit = (q * 4 + gg) ^ (a & 7);
           *reinterpret_cast<uint4*>(prow + unit * 16) = pk;
         }
       }
@@ -278,38 +290,54 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       fence_proxy_async_smem();  // generic-proxy writes of P -> visible to the MMA (async proxy)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_pready);
-      // ---- O accumulation in registers (rescaled), O_blk from TMEM
-      mbar_wait(bar_mma3, ph);
+      if (lane == 0) mbar_arrive(&bar_pready[g]);
+      // ---- O_g accumulation in registers (rescaled)
+      mbar_wait(&bar_mma3[g], ph);
       tc_fence_after();
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         uint32_t v[32];
-        tmem_ld_32x32(lane_base + TM_O + 32 * q, v);
+        tmem_ld_32x32(lane_base + TM_O + 64 * g + 32 * q, v);
         tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 32; ++e) o[32 * q + e] = o[32 * q + e] * alpha + __uint_as_float(v[e]);
       }
     }
-    // ---- epilogue: normalise, write ctx row and the log2-domain LSE
-    if (i < p.L) {
-      const float inv_l = (l_run > 0.0f) ? 1.0f / l_run : 0.0f;
+    // ---- merge the two key halves (flash-decoding style) through shared memory, then write ctx / LSE
+    tc_fence_before();
+    named_bar_sync(1, 256);                      // all staging reads are done: reuse T1/T2 as exchange space
+    float* xch = reinterpret_cast<float*>(smem + OFF_T1);   // [128][66] floats = 33.8 KB <= 2 * 34.8 KB
+    if (g == 1) {
+      float* dstx = xch + a * 66;
+      dstx[0] = m_run; dstx[1] = l_run;
+#pragma unroll
+      for (int k = 0; k < 64; ++k) dstx[2 + k] = o[k];
+    }
+    named_bar_sync(1, 256);
+    if (g == 0 && i < p.L) {
+      const float* srcx = xch + a * 66;
+      const float m1 = srcx[0], l1 = srcx[1];
+      const float m_all = fmaxf(m_run, m1);
+      const float m_use = (m_all == -INFINITY) ? 0.0f : m_all;
+      const float a0 = exp2f(m_run - m_use), a1 = exp2f(m1 - m_use);
+      const float l_all = l_run * a0 + l1 * a1;
+      const float inv_l = (l_all > 0.0f) ? 1.0f / l_all : 0.0f;
       __nv_bfloat16* dst = p.ctx + ((long long)b * p.L + i) * p.ldc + hh * 64;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const uint4 pk = make_uint4(pack_bf16(o[8 * g] * inv_l, o[8 * g + 1] * inv_l),
-                                    pack_bf16(o[8 * g + 2] * inv_l, o[8 * g + 3] * inv_l),
-                                    pack_bf16(o[8 * g + 4] * inv_l, o[8 * g + 5] * inv_l),
-                                    pack_bf16(o[8 * g + 6] * inv_l, o[8 * g + 7] * inv_l));
-        reinterpret_cast<uint4*>(dst)[g] = pk;
+      for (int gg = 0; gg < 8; ++gg) {
+        float r[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r[e] = (o[8 * gg + e] * a0 + srcx[2 + 8 * gg + e] * a1) * inv_l;
+        reinterpret_cast<uint4*>(dst)[gg] = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]),
+                                                        pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
       }
-      p.lse[((long long)b * p.h + hh) * p.L + i] = (l_run > 0.0f) ? (m_run + log2f(l_run)) : INFINITY;
+      p.lse[((long long)b * p.h + hh) * p.L + i] = (l_all > 0.0f) ? (m_all + log2f(l_all)) : INFINITY;
     }
-    tc_fence_before();
   }
 
+  tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }

@@ -34,6 +34,9 @@ int num_sms();
 // Generic bf16 tiled tensor map (rank <= 4), 128B swizzle, inner box = 64 elements (128 B).
 int make_tmap_bf16_nd(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
                       const uint64_t* strides_elems /*rank-1*/, const uint32_t* box);
+// 2-D output map for the TMA-store epilogue: [rows, cols] row-major, box {32 cols, 128 rows};
+// bf16 -> 64B swizzle (64-byte rows), fp32 -> 128B swizzle (128-byte rows).
+int make_tmap_store_2d(CUtensorMap* out, const void* ptr, int is_f32, uint64_t cols, uint64_t rows, uint64_t ld_elems);
 const char* last_error();
 void count_launch();  // bumps the library-wide kernel-launch counter (fb_launch_count)
 
@@ -127,6 +130,22 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+
+// TMA store of a staged tile (smem -> global, clipped at the tensor bounds), bulk-group completion.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- tcgen05 ----
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -260,15 +279,25 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
 // erf-GELU (transformers ACT2FN["gelu"]) with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below the
 // bf16 operand precision): one rcp + one ex2 + 7 FMA instead of the ~25-instruction erff(), so that the GEMM
 // epilogue stays off the MMA critical path.  `e` = exp(-x^2/2) is shared with the derivative.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float erf_as_core(float x, float& e_out) {
   const float u = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  const float e = exp2f(-u * u * 1.4426950408889634f);
+  const float e = ex2_approx(-u * u * 1.4426950408889634f);
   e_out = e;
   return copysignf(fmaf(-poly, e, 1.0f), x);
 }

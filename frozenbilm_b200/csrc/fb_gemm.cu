@@ -35,10 +35,11 @@ template <int BN>
 struct GemmCfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192) ? 5 : (BN == 128) ? 6 : 8;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192) ? 4 : (BN == 128) ? 6 : 8;
   static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STORE_STAGE_BYTES = 16384;  // one 128 x 32 chunk (fp32) per epilogue warpgroup
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STORE_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct GemmParams {
@@ -56,6 +57,7 @@ struct GemmParams {
   const __nv_bfloat16* aux; long long ld_aux; int aux_op;
   const float* resid; long long ld_resid;
   int accumulate;
+  int tma_store;   // epilogue stages 128x32 chunks in smem and writes them with cp.async.bulk.tensor stores
 };
 
 __device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int& split, int& b,
@@ -194,16 +196,118 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
   }
 }
 
+
+// value pipeline of the epilogue for one 32-column chunk (no stores), in two halves so that the pre-activation
+// can be stored between them: epi_pre = alpha, bias, row mask, early dropout; epi_post = activation, aux,
+// late dropout, residual.
+__device__ __forceinline__ void epi_pre(const GemmParams& p, int row, int col0, const uint32_t (&acc)[32],
+                                        float (&v)[32]) {
+  const bool in_rows = row < p.M;
+  const bool full = (col0 + 32 <= p.N);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * p.alpha;
+  if (p.bias) {
+    if (full && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 q = __ldg(b4 + i);
+        v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+    }
+  }
+  if (p.rowmask && in_rows && p.rowmask[row] == 0) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+  }
+  if (p.drop_pos == 1) apply_dropout32(p.drop, row, col0, v);
+}
+__device__ __forceinline__ void epi_post(const GemmParams& p, int row, int col0, float (&v)[32]) {
+  const bool in_rows = row < p.M;
+  const bool full = (col0 + 32 <= p.N);
+  if (p.act == FB_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  } else if (p.act == FB_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+  }
+  if (p.aux_op != FB_AUX_NONE && in_rows) {
+    const __nv_bfloat16* src = p.aux + (long long)row * p.ld_aux + col0;
+    float a[32];
+    if (full && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 q = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        float2 f0 = unpack_bf16(q.x), f1 = unpack_bf16(q.y), f2 = unpack_bf16(q.z), f3 = unpack_bf16(q.w);
+        a[8 * i] = f0.x; a[8 * i + 1] = f0.y; a[8 * i + 2] = f1.x; a[8 * i + 3] = f1.y;
+        a[8 * i + 4] = f2.x; a[8 * i + 5] = f2.y; a[8 * i + 6] = f3.x; a[8 * i + 7] = f3.y;
+      }
+    } else {
+      for (int i = 0; i < 32; ++i) a[i] = (col0 + i < p.N) ? __bfloat162float(src[i]) : 0.0f;
+    }
+    if (p.aux_op == FB_AUX_MUL_GELU_GRAD) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] *= gelu_erf_grad(a[i]);
+    } else if (p.aux_op == FB_AUX_MUL_RELU_MASK) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = (a[i] > 0.0f) ? v[i] : 0.0f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += a[i];
+    }
+  }
+  if (p.drop_pos == 2) apply_dropout32(p.drop, row, col0, v);
+  if (p.resid && in_rows) {
+    const float* src = p.resid + (long long)row * p.ld_resid + col0;
+    if (full && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 q = __ldg(reinterpret_cast<const float4*>(src) + i);
+        v[4 * i] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+      }
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.N) v[i] += src[i];
+    }
+  }
+}
+
+// stage one row segment of a 128 x 32 chunk into the warpgroup's smem buffer (TMA swizzle layouts):
+// bf16: 64-byte rows, 16B unit u -> u ^ ((r >> 1) & 3)   (CU_TENSOR_MAP_SWIZZLE_64B)
+// fp32: 128-byte rows, unit u -> u ^ (r & 7)              (CU_TENSOR_MAP_SWIZZLE_128B)
+__device__ __forceinline__ void stage_row_bf16(uint8_t* buf, int r, const float (&v)[32]) {
+  uint8_t* rowp = buf + r * 64;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const uint4 q = make_uint4(pack_bf16(v[8 * u], v[8 * u + 1]), pack_bf16(v[8 * u + 2], v[8 * u + 3]),
+                               pack_bf16(v[8 * u + 4], v[8 * u + 5]), pack_bf16(v[8 * u + 6], v[8 * u + 7]));
+    *reinterpret_cast<uint4*>(rowp + ((u ^ ((r >> 1) & 3)) << 4)) = q;
+  }
+}
+__device__ __forceinline__ void stage_row_f32(uint8_t* buf, int r, const float (&v)[32]) {
+  uint8_t* rowp = buf + r * 128;
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    *reinterpret_cast<float4*>(rowp + ((u ^ (r & 7)) << 4)) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+}
+
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+            const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_pre,
             const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* smem_store = smem + Cfg::STAGES * Cfg::STAGE_BYTES;   // 2 x 16 KB epilogue staging (TMA stores)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_store + 2 * Cfg::STORE_STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::STAGES;
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
@@ -320,6 +424,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const int half = (warp - 4) >> 2;   // which half of the tile's 32-column chunks this warpgroup drains
     constexpr int CHUNKS = BN / 32, HALF_CHUNKS = (CHUNKS + 1) / 2;
     const int c_begin = half * HALF_CHUNKS, c_end = (half == 0) ? HALF_CHUNKS : CHUNKS;
+    uint32_t nstore = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       int split, b, mb, nb;
@@ -330,17 +435,57 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       tc_fence_after();
       const int row = mb * BM + wq * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * Cfg::ACC_STRIDE;
+      if (!p.tma_store) {
 #pragma unroll 1
-      for (int c = c_begin; c < c_end; ++c) {
-        uint32_t acc[32];
-        tmem_ld_32x32(taddr + c * 32, acc);
-        tmem_ld_wait();
-        epilogue_chunk<BN>(p, b, row, nb * BN + c * 32, acc, split == 0);
+        for (int c = c_begin; c < c_end; ++c) {
+          uint32_t acc[32];
+          tmem_ld_32x32(taddr + c * 32, acc);
+          tmem_ld_wait();
+          epilogue_chunk<BN>(p, b, row, nb * BN + c * 32, acc, split == 0);
+        }
+      } else {
+        // coalesced path: each warpgroup stages a 128 x 32 chunk in smem and one thread issues a TMA store
+        uint8_t* buf0 = smem_store + half * Cfg::STORE_STAGE_BYTES;
+        const int r = wq * 32 + lane;
+        const bool leader = (wq == 0 && lane == 0);
+        const int n_pass = p.D_pre ? 2 : 1;
+        // bf16 chunks are 8 KB: two of them double-buffer inside the warpgroup's 16 KB so that a store drains
+        // while the next chunk is computed; fp32 chunks (16 KB) are single-buffered
+        const bool dbl = !p.d_f32;
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; ++c) {
+          const int col0 = nb * BN + c * 32;
+          if (col0 >= p.N) break;
+          uint32_t acc[32];
+          tmem_ld_32x32(taddr + c * 32, acc);
+          tmem_ld_wait();
+          float v[32];
+          epi_pre(p, row, col0, acc, v);
+#pragma unroll 1
+          for (int pass = 0; pass < n_pass; ++pass) {
+            const bool pre_only = (n_pass == 2 && pass == 0);
+            if (!pre_only) epi_post(p, row, col0, v);
+            uint8_t* buf = buf0 + ((dbl && (nstore & 1)) ? 8192 : 0);
+            ++nstore;
+            if (leader) {                            // the store that last used this buffer has finished reading it
+              if (dbl) tma_store_wait_read1(); else tma_store_wait_read0();
+            }
+            named_bar_sync(1 + half, 128);
+            if (pre_only || !p.d_f32) stage_row_bf16(buf, r, v); else stage_row_f32(buf, r, v);
+            fence_proxy_async_smem();
+            named_bar_sync(1 + half, 128);
+            if (leader) {
+              tma_store_2d(pre_only ? &map_pre : &map_d, buf, col0, mb * BM);
+              tma_store_commit();
+            }
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
     }
+    if (p.tma_store && (warp & 3) == 0 && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -395,6 +540,21 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+int make_tmap_store_2d(CUtensorMap* out, const void* ptr, int is_f32, uint64_t cols, uint64_t rows, uint64_t ld_elems) {
+  PFN_encodeTiled enc = get_encode();
+  FB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  const uint64_t esz = is_f32 ? 4 : 2;
+  cuuint64_t d[2] = {cols, rows};
+  cuuint64_t st[1] = {ld_elems * esz};
+  cuuint32_t bx[2] = {32, 128}, es[2] = {1, 1};
+  CUresult r = enc(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(ptr), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   is_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(store) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 int make_tmap_bf16_nd(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
                       const uint64_t* strides_elems, const uint32_t* box) {
   PFN_encodeTiled enc = get_encode();
@@ -436,7 +596,8 @@ static int make_tmap_operand(CUtensorMap* out, const void* ptr, uint64_t inner, 
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& mpre,
+                       const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   auto kern = gemm_kernel<BN, A_MN, B_MN>;
@@ -446,19 +607,19 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmP
   }
   int grid = std::min(p.total_tiles, num_sms());
   FB_REQUIRE(grid > 0, "no CUDA device / empty GEMM");
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, md, mpre, p);
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int BN>
-static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p,
-                          cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(ma, mb, p, st);
-  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(ma, mb, p, st);
-  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(ma, mb, p, st);
-  return launch_gemm<BN, true, true>(ma, mb, p, st);
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
+                          const CUtensorMap& mpre, const GemmParams& p, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(ma, mb, md, mpre, p, st);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(ma, mb, md, mpre, p, st);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(ma, mb, md, mpre, p, st);
+  return launch_gemm<BN, true, true>(ma, mb, md, mpre, p, st);
 }
 
 static int pick_block_n(int M, int N, int batch, int split_k) {
@@ -533,11 +694,24 @@ int gemm(const fb_gemm_args* a, cudaStream_t st) {
   p.resid = a->resid; p.ld_resid = a->ld_resid;
   p.accumulate = (a->accumulate || split_k > 1) ? 1 : 0;
 
+  // coalesced TMA-store epilogue whenever the output is a plain (unbatched, non-accumulating) matrix with
+  // 16-byte aligned rows; otherwise the per-thread direct-store path
+  CUtensorMap md, mpre;
+  memset(&md, 0, sizeof(md));
+  memset(&mpre, 0, sizeof(mpre));
+  const uint64_t dsz = p.d_f32 ? 4 : 2;
+  const bool d_ok = ((uintptr_t)a->D % 16 == 0) && ((uint64_t)a->ldd * dsz % 16 == 0);
+  const bool pre_ok = !a->D_pre || (((uintptr_t)a->D_pre % 16 == 0) && ((uint64_t)a->ld_pre * 2 % 16 == 0));
+  p.tma_store = (batch_total == 1 && p.split_k == 1 && !p.accumulate && d_ok && pre_ok && a->M >= 32) ? 1 : 0;
+  if (p.tma_store) {
+    if ((rc = make_tmap_store_2d(&md, a->D, p.d_f32, a->N, a->M, a->ldd))) return rc;
+    if (a->D_pre && (rc = make_tmap_store_2d(&mpre, a->D_pre, 0, a->N, a->M, a->ld_pre))) return rc;
+  }
   switch (bn) {
-    case 64: return dispatch_major<64>(a->a_mn_major, a->b_mn_major, ma, mb, p, st);
-    case 128: return dispatch_major<128>(a->a_mn_major, a->b_mn_major, ma, mb, p, st);
-    case 192: return dispatch_major<192>(a->a_mn_major, a->b_mn_major, ma, mb, p, st);
-    default: return dispatch_major<256>(a->a_mn_major, a->b_mn_major, ma, mb, p, st);
+    case 64: return dispatch_major<64>(a->a_mn_major, a->b_mn_major, ma, mb, md, mpre, p, st);
+    case 128: return dispatch_major<128>(a->a_mn_major, a->b_mn_major, ma, mb, md, mpre, p, st);
+    case 192: return dispatch_major<192>(a->a_mn_major, a->b_mn_major, ma, mb, md, mpre, p, st);
+    default: return dispatch_major<256>(a->a_mn_major, a->b_mn_major, ma, mb, md, mpre, p, st);
   }
 }
 
