@@ -34,6 +34,10 @@ class FBConfig:
     freeze_mlm: bool = True
     ft_ln: bool = True
     freeze_last: bool = True
+    # "deberta" (model/deberta.py) or "bert" (model/bert.py: absolute positions + token types, no adapters,
+    # no relative attention / conv / enhanced mask decoder, additive key mask)
+    arch: str = "deberta"
+    type_vocab_size: int = 0
 
     @property
     def head_dim(self) -> int:
@@ -57,6 +61,17 @@ class FBConfig:
 
     def to_hf(self):
         """A transformers.DebertaV2Config carrying the XL switches."""
+        if self.arch == "bert":
+            from transformers import BertConfig
+
+            return BertConfig(hidden_size=self.hidden_size, num_hidden_layers=self.num_hidden_layers,
+                              num_attention_heads=self.num_attention_heads,
+                              intermediate_size=self.intermediate_size, vocab_size=self.vocab_size,
+                              max_position_embeddings=self.max_position_embeddings,
+                              type_vocab_size=self.type_vocab_size, layer_norm_eps=self.layer_norm_eps,
+                              hidden_act="gelu", hidden_dropout_prob=self.hidden_dropout_prob,
+                              attention_probs_dropout_prob=self.attention_probs_dropout_prob,
+                              pad_token_id=self.pad_token_id)
         from transformers import DebertaV2Config
 
         return DebertaV2Config(
@@ -109,6 +124,23 @@ class FBConfig:
             pad_token_id=getattr(hf, "pad_token_id", 0) or 0, **extra)
 
 
+def bert_from_hf(hf, **extra) -> FBConfig:
+    """FBConfig of a transformers.BertConfig (reference model/bert.py path)."""
+    if getattr(hf, "hidden_act", "gelu") != "gelu":
+        raise NotImplementedError("hidden_act must be gelu")
+    if getattr(hf, "position_embedding_type", "absolute") != "absolute" or getattr(hf, "is_decoder", False):
+        raise NotImplementedError("only the absolute-position bidirectional BERT encoder is supported")
+    return FBConfig(hidden_size=hf.hidden_size, num_hidden_layers=hf.num_hidden_layers,
+                    num_attention_heads=hf.num_attention_heads, intermediate_size=hf.intermediate_size,
+                    vocab_size=hf.vocab_size, max_position_embeddings=hf.max_position_embeddings,
+                    position_buckets=0, layer_norm_eps=hf.layer_norm_eps,
+                    hidden_dropout_prob=hf.hidden_dropout_prob,
+                    attention_probs_dropout_prob=hf.attention_probs_dropout_prob,
+                    pad_token_id=getattr(hf, "pad_token_id", 0) or 0, arch="bert",
+                    type_vocab_size=hf.type_vocab_size, ds_factor_attn=0, ds_factor_ff=0, adapter_dropout=0.0,
+                    **extra)
+
+
 # BASELINE.json configs[0]: the CPU-runnable parity case (DeBERTa-base dims + XL switches)
 CONFIG_BASE = FBConfig(hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
                        intermediate_size=3072, vocab_size=128100, max_feats=2,
@@ -122,3 +154,11 @@ CONFIG_TINY = FBConfig(hidden_size=256, num_hidden_layers=2, num_attention_heads
                        intermediate_size=1024, vocab_size=1000, max_feats=10,
                        hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
                        adapter_dropout=0.0)
+# BERT variant (reference model/bert.py; BASELINE.json configs[4] uses BERT-large dims)
+CONFIG_BERT_TINY = FBConfig(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=1024,
+                            vocab_size=1000, max_feats=10, position_buckets=0, layer_norm_eps=1e-12,
+                            hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, adapter_dropout=0.0,
+                            ds_factor_attn=0, ds_factor_ff=0, arch="bert", type_vocab_size=2)
+CONFIG_BERT_LARGE = CONFIG_BERT_TINY.replace(hidden_size=1024, num_hidden_layers=24, num_attention_heads=16,
+                                             intermediate_size=4096, vocab_size=30522, hidden_dropout_prob=0.1,
+                                             attention_probs_dropout_prob=0.1)

@@ -40,10 +40,12 @@ struct AttnParams {
   float* lse;
   float* s_out; int lp;   // optional [B, h, L, lp] fp32 copy of the masked, scaled scores (log2 domain)
   float scale_log2;
+  int mask_queries;                        // DeBERTa: M[i,j] = m_i * m_j;  BERT: key mask only
   float inv_keep; uint32_t drop_thresh16;  // keep iff rnd16 >= thresh
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
 };
 
+template <bool REL>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_pk,
@@ -95,11 +97,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                      sPK = smem_u32(smem + OFF_PK), sPQ = smem_u32(smem + OFF_PQ), sP = smem_u32(smem + OFF_P);
       auto load_k = [&](int kb) {
         const int j0 = kb * 128;
-        mbar_arrive_expect_tx(bar_k, 16384 + 2 * 32768);
+        mbar_arrive_expect_tx(bar_k, REL ? 16384 + 2 * 32768 : 16384);
         tma_load_4d(smem + OFF_K, &map_k, bar_k, 0, hh, j0, b);
-        const int band0 = i0 - j0 - 127 + p.rel_off;
-        tma_load_3d(smem + OFF_PK, &map_pk, bar_k, 0, band0, hh);
-        tma_load_3d(smem + OFF_PQ, &map_pq, bar_k, 0, band0, hh);
+        if constexpr (REL) {
+          const int band0 = i0 - j0 - 127 + p.rel_off;
+          tma_load_3d(smem + OFF_PK, &map_pk, bar_k, 0, band0, hh);
+          tma_load_3d(smem + OFF_PQ, &map_pq, bar_k, 0, band0, hh);
+        }
       };
       auto load_v = [&](int kb) {
         mbar_arrive_expect_tx(bar_v, 16384);
@@ -118,10 +122,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         for (int k = 0; k < 4; ++k)
           umma_bf16(tmem + TM_S, make_smem_desc_sw128(sQ + k * 32, 16, 1024),
                     make_smem_desc_sw128(sK + k * 32, 16, 1024), idesc_qk, k > 0);
+        if constexpr (REL) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + TM_X, make_smem_desc_sw128(sK + k * 32, 16, 1024),
-                    make_smem_desc_sw128(sPQ + k * 32, 16, 1024), idesc_band, k > 0);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + TM_X, make_smem_desc_sw128(sK + k * 32, 16, 1024),
+                      make_smem_desc_sw128(sPQ + k * 32, 16, 1024), idesc_band, k > 0);
+        }
         umma_commit(bar_mma1);
         if (kb > 0) {
           // the previous block's P.V (both halves) must retire before its V tile is overwritten
@@ -131,10 +137,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         mbar_wait(bar_xfree, ph);
         tc_fence_after();
+        if constexpr (REL) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem + TM_X, make_smem_desc_sw128(sQ + k * 32, 16, 1024),
-                    make_smem_desc_sw128(sPK + k * 32, 16, 1024), idesc_band, k > 0);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + TM_X, make_smem_desc_sw128(sQ + k * 32, 16, 1024),
+                      make_smem_desc_sw128(sPK + k * 32, 16, 1024), idesc_band, k > 0);
+        }
         umma_commit(bar_mma2);
         mbar_wait(bar_mma2, ph);  // K / PK / PQ tiles are free again
         if (kb + 1 < p.nkb) load_k(kb + 1);
@@ -158,7 +166,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const int g = warp >> 2, wq = warp & 3;
     const int a = wq * 32 + lane;        // row in tile == TMEM lane
     const int i = i0 + a;
-    const bool valid_q = (i < p.L) && (p.mask[(long long)b * p.L + i] != 0);
+    const bool valid_q = (i < p.L) && (!p.mask_queries || p.mask[(long long)b * p.L + i] != 0);
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
     const uint32_t rowid = static_cast<uint32_t>((b * p.h + hh) * p.L + i);
     const bool do_drop = p.drop_thresh16 != 0;
@@ -179,7 +187,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       // ---- p2c: lane = KEY row a of X2; scatter its 160-column window into T2[query][key].
       //      The 5 chunks are shared between the warpgroups (g = 0: chunks 0-2, g = 1: chunks 3-4).
 #pragma unroll 1
-      for (int q = (g == 0 ? 0 : 3); q < (g == 0 ? 3 : 5); ++q) {
+      for (int q = (g == 0 ? 0 : 3); REL && q < (g == 0 ? 3 : 5); ++q) {
         uint32_t v[32];
         tmem_ld_32x32(lane_base + TM_X + (96 - 32 * wq + 32 * q), v);
         tmem_ld_wait();
@@ -197,7 +205,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       // ---- c2p: lane = QUERY row a of X1; keys b = a + 127 - c.  Warpgroup g needs b in [64g, 64g+64):
       //      columns c in [a + 64(1-g), a + 64(1-g) + 63] -> 3 chunks starting at 32*wq + 64*(1-g).
 #pragma unroll 1
-      for (int q = 0; q < 3; ++q) {
+      for (int q = 0; REL && q < 3; ++q) {
         uint32_t v[32];
         const int cbase = 32 * wq + 64 * (1 - g) + 32 * q;
         tmem_ld_32x32(lane_base + TM_X + cbase, v);
@@ -228,8 +236,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           const uint32_t w1[4] = {c1.x, c1.y, c1.z, c1.w}, w2[4] = {c2.x, c2.y, c2.z, c2.w};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&w1[u]));
-            const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w2[u]));
+            float2 f1 = make_float2(0.f, 0.f), f2 = make_float2(0.f, 0.f);
+            if constexpr (REL) {
+              f1 = __half22float2(*reinterpret_cast<const __half2*>(&w1[u]));
+              f2 = __half22float2(*reinterpret_cast<const __half2*>(&w2[u]));
+            }
             const int e = gg * 8 + u * 2;
             float s0 = (__uint_as_float(v[e]) + f1.x + f2.x) * p.scale_log2;
             float s1 = (__uint_as_float(v[e + 1]) + f1.y + f2.y) * p.scale_log2;
@@ -377,49 +388,65 @@ struct AttnBwdParams {
   float scale; DropSpec drop;
 };
 
-__global__ void __launch_bounds__(128) attn_bwd_ds_kernel(const AttnBwdParams p) {
-  __shared__ float sds[512];
-  __shared__ float sD;
-  const int i = blockIdx.x, hh = blockIdx.y, b = blockIdx.z;
-  const long long row = ((long long)b * p.h + hh) * p.L + i;
-  const int tid = threadIdx.x;
-  if (tid < 32) {
+__global__ void __launch_bounds__(256) attn_bwd_ds_kernel(const AttnBwdParams p) {
+  // one warp per score row; 16-byte accesses throughout (the kernel is HBM-bound: 14 B/element read+written)
+  __shared__ __align__(16) __nv_bfloat16 srow[8][512];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;   // (b * h + hh) * L + i
+  const long long nrows = (long long)p.B * p.h * p.L;
+  if (row >= nrows) return;
+  const int i = (int)(row % p.L);
+  const int hh = (int)((row / p.L) % p.h);
+  const int b = (int)(row / ((long long)p.L * p.h));
+  float d;
+  {
     const __nv_bfloat16* o = p.ctx + ((long long)b * p.L + i) * p.ldc + hh * 64;
     const __nv_bfloat16* g = p.dctx + ((long long)b * p.L + i) * p.ldc + hh * 64;
-    const float2 o2 = unpack_bf16(*reinterpret_cast<const uint32_t*>(o + 2 * tid));
-    const float2 g2 = unpack_bf16(*reinterpret_cast<const uint32_t*>(g + 2 * tid));
-    float d = o2.x * g2.x + o2.y * g2.y;
+    const float2 o2 = unpack_bf16(*reinterpret_cast<const uint32_t*>(o + 2 * lane));
+    const float2 g2 = unpack_bf16(*reinterpret_cast<const uint32_t*>(g + 2 * lane));
+    d = o2.x * g2.x + o2.y * g2.y;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-    if (tid == 0) sD = d;
   }
-  __syncthreads();
-  const float D = sD, lse = p.lse[row];
+  const float D = d, lse = p.lse[row];
   const uint32_t rowid = (uint32_t)row;
-  for (int j = tid; j < p.lp; j += 128) {
-    float ds = 0.0f, pd = 0.0f;
-    if (j < p.L) {
-      const float s = p.s2[row * p.lp + j];
-      const float pr = exp2f(s - lse);   // s = -inf (masked) or lse = +inf (dead row) -> 0
-      float dpv = __bfloat162float(p.dp[row * p.lp + j]);
-      pd = pr;
-      if (p.drop.thresh16) {
-        const uint32_t keep = drop_keep8(p.drop, rowid, (uint32_t)j >> 3);
-        const float f = ((keep >> (j & 7)) & 1) ? p.drop.inv_keep : 0.0f;
-        dpv *= f;
-        pd *= f;
+  for (int j0 = lane * 4; j0 < p.lp; j0 += 128) {
+    float dsv[4] = {0.f, 0.f, 0.f, 0.f}, pdv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (j0 < p.L) {   // L is a multiple of 4 or the tail columns are masked scores (-inf) anyway
+      const float4 s4 = *reinterpret_cast<const float4*>(p.s2 + row * p.lp + j0);
+      const uint2 dp2 = *reinterpret_cast<const uint2*>(p.dp + row * p.lp + j0);
+      const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+      const float2 d01 = unpack_bf16(dp2.x), d23 = unpack_bf16(dp2.y);
+      float dpv[4] = {d01.x, d01.y, d23.x, d23.y};
+      uint32_t keep = 0xF;
+      if (p.drop.thresh16) keep = (drop_keep8(p.drop, rowid, (uint32_t)j0 >> 3) >> (j0 & 4)) & 0xF;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool in = (j0 + e) < p.L;
+        const float pr = in ? exp2f(sv[e] - lse) : 0.0f;   // s = -inf (masked) or lse = +inf (dead row) -> 0
+        const float f = ((keep >> e) & 1) ? p.drop.inv_keep : 0.0f;
+        pdv[e] = pr * f;
+        dsv[e] = (pr > 0.0f) ? pr * ((in ? dpv[e] : 0.0f) * f - D) * p.scale : 0.0f;
       }
-      ds = (pr > 0.0f) ? pr * (dpv - D) * p.scale : 0.0f;
     }
-    sds[j] = ds;
-    p.ds[row * p.lp + j] = __float2bfloat16_rn(ds);
-    p.pd[row * p.lp + j] = __float2bfloat16_rn(pd);
+    const uint2 dsq = make_uint2(pack_bf16(dsv[0], dsv[1]), pack_bf16(dsv[2], dsv[3]));
+    *reinterpret_cast<uint2*>(p.ds + row * p.lp + j0) = dsq;
+    *reinterpret_cast<uint2*>(p.pd + row * p.lp + j0) = make_uint2(pack_bf16(pdv[0], pdv[1]), pack_bf16(pdv[2], pdv[3]));
+    *reinterpret_cast<uint2*>(&srow[warp][j0]) = dsq;
   }
-  __syncthreads();
+  if (p.z1 == nullptr) return;   // plain attention (BERT): no positional terms
+  __syncwarp();
+  // Z1 row: z[r] = dS[i, j = i - (r - rel_off)], eight entries (16 bytes) per store
   __nv_bfloat16* z = p.z1 + ((long long)hh * p.B * p.L + (long long)b * p.L + i) * p.rel_rows;
-  for (int r = tid; r < p.rel_rows; r += 128) {
-    const int j = i - (r - p.rel_off);
-    z[r] = __float2bfloat16_rn((j >= 0 && j < p.L) ? sds[j] : 0.0f);
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.0f);
+  for (int r0 = lane * 8; r0 < p.rel_rows; r0 += 256) {
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int j = i - (r0 + e - p.rel_off);
+      v[e] = (j >= 0 && j < p.L) ? srow[warp][j] : zero;
+    }
+    *reinterpret_cast<uint4*>(z + r0) = *reinterpret_cast<const uint4*>(v);
   }
 }
 
@@ -476,18 +503,24 @@ static int make_rel_map(CUtensorMap* m, const void* ptr, int rel_rows, int h) {
 }
 
 int attn_fwd(const fb_attn_args* a, cudaStream_t st) {
-  FB_REQUIRE(a && a->Q && a->K && a->V && a->PKrel && a->PQrel && a->mask && a->ctx && a->lse, "fb_attn_fwd: null arg");
+  FB_REQUIRE(a && a->Q && a->K && a->V && a->mask && a->ctx && a->lse, "fb_attn_fwd: null arg");
   FB_REQUIRE(a->B > 0 && a->h > 0 && a->L > 0 && a->L <= 512, "fb_attn_fwd: need 0 < L <= 512 (got %d)", a->L);
   const int lpad = (a->L + 127) / 128 * 128;
-  FB_REQUIRE(a->rel_off >= lpad && a->rel_rows >= a->rel_off + lpad + 1,
+  const bool rel = a->PKrel != nullptr;
+  FB_REQUIRE(!rel || a->PQrel, "fb_attn_fwd: PKrel and PQrel must be given together");
+  FB_REQUIRE(!rel || (a->rel_off >= lpad && a->rel_rows >= a->rel_off + lpad + 1),
              "fb_attn_fwd: relative tables too small (rel_rows=%d rel_off=%d L=%d)", a->rel_rows, a->rel_off, a->L);
   CUtensorMap mq, mk, mv, mpk, mpq;
   int rc;
   if ((rc = make_qkv_map(&mq, a->Q, a->ldq, a->B, a->L, a->h))) return rc;
   if ((rc = make_qkv_map(&mk, a->K, a->ldk, a->B, a->L, a->h))) return rc;
   if ((rc = make_qkv_map(&mv, a->V, a->ldv, a->B, a->L, a->h))) return rc;
-  if ((rc = make_rel_map(&mpk, a->PKrel, a->rel_rows, a->h))) return rc;
-  if ((rc = make_rel_map(&mpq, a->PQrel, a->rel_rows, a->h))) return rc;
+  if (rel) {
+    if ((rc = make_rel_map(&mpk, a->PKrel, a->rel_rows, a->h))) return rc;
+    if ((rc = make_rel_map(&mpq, a->PQrel, a->rel_rows, a->h))) return rc;
+  } else {
+    mpk = mk; mpq = mk;   // never dereferenced by the plain-attention instantiation
+  }
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.B = a->B; p.L = a->L; p.h = a->h; p.nkb = lpad / 128; p.rel_off = a->rel_off;
@@ -496,6 +529,7 @@ int attn_fwd(const fb_attn_args* a, cudaStream_t st) {
   p.lse = a->lse;
   p.s_out = a->s_out; p.lp = lpad;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.mask_queries = a->key_mask_only ? 0 : 1;
   if (a->dropout_p > 0.0f) {
     FB_REQUIRE(a->dropout_p < 1.0f, "fb_attn_fwd: dropout_p must be < 1");
     p.drop_thresh16 = (uint32_t)(a->dropout_p * 65536.0f + 0.5f);
@@ -507,11 +541,15 @@ int attn_fwd(const fb_attn_args* a, cudaStream_t st) {
   p.off_lo = (uint32_t)a->offset; p.off_hi = (uint32_t)(a->offset >> 32);
   static bool configured = false;
   if (!configured) {
-    FB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    FB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    FB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     configured = true;
   }
   dim3 grid(lpad / 128, a->h, a->B);
-  attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(mq, mk, mv, mpk, mpq, p);
+  if (rel)
+    attn_fwd_kernel<true><<<grid, AT_THREADS, AT_SMEM, st>>>(mq, mk, mv, mpk, mpq, p);
+  else
+    attn_fwd_kernel<false><<<grid, AT_THREADS, AT_SMEM, st>>>(mq, mk, mv, mpk, mpq, p);
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -531,8 +569,8 @@ int build_rel_tables(const void* pqk, long long ld, int H, int h, const int* buc
 }
 
 int attn_bwd_prep(const fb_attn_bwd_prep_args* a, cudaStream_t st) {
-  FB_REQUIRE(a && a->s2 && a->lse && a->dp && a->ctx && a->dctx && a->ds && a->pd && a->z1 && a->z2,
-             "fb_attn_bwd_prep: null arg");
+  FB_REQUIRE(a && a->s2 && a->lse && a->dp && a->ctx && a->dctx && a->ds && a->pd, "fb_attn_bwd_prep: null arg");
+  FB_REQUIRE((a->z1 == nullptr) == (a->z2 == nullptr), "fb_attn_bwd_prep: z1 and z2 go together");
   FB_REQUIRE(a->L > 0 && a->L <= 512 && a->lp >= a->L && a->lp <= 512, "fb_attn_bwd_prep: bad L/lp");
   AttnBwdParams p;
   p.B = a->B; p.L = a->L; p.h = a->h; p.lp = a->lp; p.rel_rows = a->rel_rows; p.rel_off = a->rel_off;
@@ -540,9 +578,12 @@ int attn_bwd_prep(const fb_attn_bwd_prep_args* a, cudaStream_t st) {
   p.dctx = (const __nv_bfloat16*)a->dctx; p.ldc = a->ldc;
   p.ds = (__nv_bfloat16*)a->ds; p.pd = (__nv_bfloat16*)a->pd; p.z1 = (__nv_bfloat16*)a->z1;
   p.scale = a->scale; p.drop = make_drop(a->dropout_p, a->seed, a->offset);
-  attn_bwd_ds_kernel<<<dim3(a->L, a->h, a->B), 128, 0, st>>>(p);
+  FB_REQUIRE((a->z1 == nullptr || a->rel_rows % 8 == 0) && a->lp % 4 == 0, "fb_attn_bwd_prep: rel_rows %% 8 / lp %% 4");
+  const long long nrows = (long long)a->B * a->h * a->L;
+  attn_bwd_ds_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(p);
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
+  if (a->z2 == nullptr) return 0;
   const int smem = a->L * 34 * 2;
   attn_bwd_z2_kernel<<<dim3((a->L + 31) / 32, a->h, a->B), 256, smem, st>>>(
       (const __nv_bfloat16*)a->ds, a->B, a->L, a->h, a->lp, a->rel_rows, a->rel_off, (__nv_bfloat16*)a->z2);

@@ -75,11 +75,18 @@ class DebertaEngine:
         self.step_seed = 0x5EED0000
         if cfg.head_dim != 64:
             raise NotImplementedError("the fused attention kernel is specialised for head_dim = 64")
+        self.use_rel = True                                   # disentangled (c2p + p2c) attention
+        self.attn_scale = 1.0 / math.sqrt(3 * 64)             # deberta.py:769-777
+        self.layer_prefix = "deberta.encoder.layer."
         if cfg.hidden_size % 128 != 0:
             raise NotImplementedError("hidden_size must be a multiple of 128")
-        self.bucket_of_rel = torch.from_numpy(bucket_of_rel(cfg.position_buckets, cfg.max_position_embeddings)).to(device)
+        self.bucket_of_rel = torch.from_numpy(bucket_of_rel(cfg.position_buckets, cfg.max_position_embeddings)).to(device) \
+            if cfg.position_buckets > 0 else None
         self._frozen_versions = None
         self.W = {}
+        # head parameter names (DeBERTa: lm_predictions.lm_head.*; BERT: cls.predictions.*)
+        self.hn = dict(dense_b="lm_predictions.lm_head.dense.bias", ln_w="lm_predictions.lm_head.LayerNorm.weight",
+                       ln_b="lm_predictions.lm_head.LayerNorm.bias", bias="lm_predictions.lm_head.bias")
         self.prepare_frozen()
 
     # ------------------------------------------------------------------ weight preparation
@@ -314,14 +321,15 @@ class DebertaEngine:
         H, h, I = cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size
         tag = tag if tag is not None else str(pass_id)
         sfx = f".{tag}" if training else ""
-        p = f"deberta.encoder.layer.{i}."
-        pq, pk = self._rel_tables(i, pass_id, L)
+        p = f"{self.layer_prefix}{i}."
+        pq, pk = self._rel_tables(i, pass_id, L) if self.use_rel else (None, None)
         ctx16 = ws.get("ctx" + sfx, (T, H), BF16)
         lse = ws.get("lse" + sfx, (B, h, L), F32)
         att_drop = self.drop(cfg.attention_probs_dropout_prob, pass_id * 8 + SITE_PROBS)
         s2 = ws.get("s2" + sfx, (B, h, L, (L + 127) // 128 * 128), F32) if training else None
-        lib.attn_fwd(Q, K, V, pk, pq, self.mask_u8, ctx16, lse, B=B, L=L, h=h, scale=1.0 / math.sqrt(3 * 64),
-                     dropout_p=att_drop.p, seed=att_drop.seed, offset=att_drop.offset, s_out=s2)
+        lib.attn_fwd(Q, K, V, pk, pq, self.mask_u8, ctx16, lse, B=B, L=L, h=h, scale=self.attn_scale,
+                     dropout_p=att_drop.p, seed=att_drop.seed, offset=att_drop.offset, s_out=s2,
+                     key_mask_only=not self.use_rel)
         a32, a16, rec1 = self._sublayer_out("att", i, pass_id, ctx16, W[f"o.w.{i}"], P[p + "attention.output.dense.bias"],
                                             p + "attention.output.adapter.", p + "attention.output.LayerNorm.",
                                             xq32, SITE_AD1, SITE_HID1, training, tag)
@@ -343,19 +351,19 @@ class DebertaEngine:
         ``scratch`` uses separate buffers and leaves the state saved for the backward untouched."""
         cfg, P, W, ws = self.cfg, self.P, self.W, self.ws
         H = cfg.hidden_size
-        hp = "lm_predictions.lm_head."
+        hn = self.hn
         pfx = "headx." if scratch else "head."
         hd32 = ws.rows(pfx + "hd32", n_rows, H, F32)
         pre16 = ws.rows(pfx + "pre16", n_rows, H, BF16)
-        lib.gemm(rows16, W["head.w"], hd32, bias=P[hp + "dense.bias"], act=lib.FB_ACT_GELU, D_pre=pre16)
+        lib.gemm(rows16, W["head.w"], hd32, bias=P[hn["dense_b"]], act=lib.FB_ACT_GELU, D_pre=pre16)
         t16 = ws.rows(pfx + "t16", n_rows, H, BF16)
         mean, rstd = ws.rows(pfx + "mean", n_rows, 1, F32), ws.rows(pfx + "rstd", n_rows, 1, F32)
-        lib.layernorm_fwd(hd32, P[hp + "LayerNorm.weight"], P[hp + "LayerNorm.bias"], cfg.layer_norm_eps, y16=t16,
+        lib.layernorm_fwd(hd32, P[hn["ln_w"]], P[hn["ln_b"]], cfg.layer_norm_eps, y16=t16,
                           mean=mean, rstd=rstd)
         if cfg.n_ans and not mlm:
             E, bias, V = W["ans16"], P["answer_bias"], W["ans_n"]
         else:
-            E, bias, V = W["emb16"], P[hp + "bias"], cfg.vocab_size
+            E, bias, V = W["emb16"], P[hn["bias"]], cfg.vocab_size
         if out is None:
             out = ws.rows(pfx + "logits", n_rows, _ceil8(V), F32)
         lib.gemm(t16, E, out, bias=bias, N=V)
@@ -386,8 +394,16 @@ class DebertaEngine:
             raise lib.FbError("backward() without a training-mode forward")
         B, L, F, Lt, T = self.dims
         H = cfg.hidden_size
-        hp = "lm_predictions.lm_head."
         self.g = gviews
+        dy32 = self._bwd_head(scale, dlogits)
+        self._bwd_encoder(dy32)
+        self.saved = None
+
+    def _bwd_head(self, scale, dlogits):
+        cfg, P, W, ws, hs = self.cfg, self.P, self.W, self.ws, self.head_saved
+        B, L, F, Lt, T = self.dims
+        H = cfg.hidden_size
+        hn = self.hn
         n = hs["n_rows"]
         # ---- head: logits -> t -> LN -> gelu -> dense
         dt32 = ws.rows("bw.dt32", n, H, F32)
@@ -401,8 +417,8 @@ class DebertaEngine:
             d16[:, :nans] = dlogits.reshape(n, nans).to(BF16)
             lib.gemm(d16, hs["E"], dt32, b_mn_major=True, N=H)
         dhd32 = ws.rows("bw.dhd32", n, H, F32)
-        lib.layernorm_bwd(dt32, hs["hd32"], hs["mean"], hs["rstd"], P[hp + "LayerNorm.weight"], dx32=dhd32,
-                          dgamma=self._g(hp + "LayerNorm.weight"), dbeta=self._g(hp + "LayerNorm.bias"))
+        lib.layernorm_bwd(dt32, hs["hd32"], hs["mean"], hs["rstd"], P[hn["ln_w"]], dx32=dhd32,
+                          dgamma=self._g(hn["ln_w"]), dbeta=self._g(hn["ln_b"]))
         dpre16 = ws.rows("bw.dpre16", n, H, BF16)
         lib.gelu_bwd(dhd32, hs["pre16"], dpre16)
         dy32 = ws.get("bw.dy32.a", (T, H), F32)
@@ -413,6 +429,12 @@ class DebertaEngine:
             lib.move_rows(drows32, dy32, idx_out=hs["sel"])
         else:
             lib.gemm(dpre16, W["head.w"], dy32, b_mn_major=True)
+        return dy32
+
+    def _bwd_encoder(self, dy32):
+        cfg, P, W, ws, sv = self.cfg, self.P, self.W, self.ws, self.saved
+        B, L, F, Lt, T = self.dims
+        H = cfg.hidden_size
         self._dR32 = ws.get("bw.dR32", (2 * cfg.position_buckets, H), F32, zero=True)
         passes = sv["passes"]
         NL = cfg.num_hidden_layers
@@ -443,11 +465,20 @@ class DebertaEngine:
             dx32 = self._bwd_pass(rec, dx32, emd=False, slot=rec["pass_id"] % 2)
         if dcol16 is not None:
             lib.conv_col2im(dcol16, B, L, H, dx32, accumulate=True)
-        # ---- embeddings: dropout -> * mask -> LayerNorm -> [linear_video ; word_emb (frozen)]
-        e = "deberta.embeddings."
+        self._bwd_embeddings(dx32, "deberta.embeddings.", rowmask=self.mask_u8)
+        # ---- relative-embedding LayerNorm (trainable under ft_ln): gamma/beta only, the table is frozen
+        lib.layernorm_bwd(self._dR32, P[c + "rel_embeddings.weight"], sv["rel_mean"], sv["rel_rstd"],
+                          P[c + "LayerNorm.weight"], dgamma=self._g(c + "LayerNorm.weight"),
+                          dbeta=self._g(c + "LayerNorm.bias"))
+
+    def _bwd_embeddings(self, dx32, e, rowmask):
+        """dropout -> (* mask) -> LayerNorm -> [linear_video ; word_emb (frozen)]"""
+        cfg, P, ws, sv = self.cfg, self.P, self.ws, self.saved
+        B, L, F, Lt, T = self.dims
+        H = cfg.hidden_size
         de16 = ws.get("bw.de16", (T, H), BF16)
         lib.layernorm_bwd(dx32, sv["e32"], sv["emb_mean"], sv["emb_rstd"], P[e + "LayerNorm.weight"],
-                          rowmask=self.mask_u8, out_drop=self.drop(cfg.hidden_dropout_prob, OFF_EMB), dx16=de16,
+                          rowmask=rowmask, out_drop=self.drop(cfg.hidden_dropout_prob, OFF_EMB), dx16=de16,
                           dgamma=self._g(e + "LayerNorm.weight"), dbeta=self._g(e + "LayerNorm.bias"))
         if sv["use_video"]:
             dv16 = ws.get("bw.dv16", (B * F, H), BF16)
@@ -457,11 +488,6 @@ class DebertaEngine:
             lib.gemm(dv16, v16, self._g(e + "linear_video.weight"), a_mn_major=True, b_mn_major=True,
                      N=cfg.features_dim, accumulate=True)
             lib.colsum_bf16(dv16, self._g(e + "linear_video.bias"))
-        # ---- relative-embedding LayerNorm (trainable under ft_ln): gamma/beta only, the table is frozen
-        lib.layernorm_bwd(self._dR32, P[c + "rel_embeddings.weight"], sv["rel_mean"], sv["rel_rstd"],
-                          P[c + "LayerNorm.weight"], dgamma=self._g(c + "LayerNorm.weight"),
-                          dbeta=self._g(c + "LayerNorm.bias"))
-        self.saved = None
 
     def _g(self, name):
         """fp32 gradient view of a trainable tensor, or None when it is frozen (kernels skip null outputs)."""
@@ -504,7 +530,7 @@ class DebertaEngine:
         B, L, F, Lt, T = self.dims
         H, h, I = cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size
         i, pass_id = rec["layer"], rec["pass_id"]
-        p = f"deberta.encoder.layer.{i}."
+        p = f"{self.layer_prefix}{i}."
         # ---- FFN sub-layer
         ds2, du2 = self._bwd_sublayer("ffn", rec["ffn"], dy32, p + "output.adapter.", p + "output.LayerNorm.",
                                       W[f"ffn2.w.{i}"], pass_id, SITE_AD2, SITE_HID2, slot)
@@ -537,23 +563,24 @@ class DebertaEngine:
         Q, K, V = rec["Q"], rec["K"], rec["V"]
         lp = (L + 127) // 128 * 128
         rel_rows, rel_off = lib.rel_table_geometry(L)
-        scale = 1.0 / math.sqrt(3 * 64)
-        bh = {"outer": None, "inner": None}
+        scale = self.attn_scale
+        rel = self.use_rel
         # dP = dO . V^T
         dp = ws.get("bw.dp", (B, h, L, lp), BF16)
         lib.gemm(dctx16, V, dp.view(-1, lp), M=L, N=L, K=64,
                  batch={"outer": (B, L * H, L * V.stride(0), h * L * lp), "inner": (h, 64, 64, L * lp)})
         ds = ws.get("bw.ds", (B, h, L, lp), BF16)
         pd = ws.get("bw.pd", (B, h, L, lp), BF16)
-        z1 = ws.get("bw.z1", (h, B * L, rel_rows), BF16)
-        z2 = ws.get("bw.z2", (h, B * L, rel_rows), BF16)
+        z1 = ws.get("bw.z1", (h, B * L, rel_rows), BF16) if rel else None
+        z2 = ws.get("bw.z2", (h, B * L, rel_rows), BF16) if rel else None
         ad = self.drop(cfg.attention_probs_dropout_prob, pass_id * 8 + SITE_PROBS)
         lib.attn_bwd_prep(rec["s2"], rec["lse"], dp, rec["ctx"], dctx16, ds, pd, z1, z2, B=B, L=L, h=h, scale=scale,
                           dropout_p=ad.p, seed=ad.seed, offset=ad.offset)
         dqkv32 = ws.get("bw.dqkv32", (T, 3 * H), F32)
         ds2d, pd2d = ds.view(-1, lp), pd.view(-1, lp)
-        z1_2d, z2_2d = z1.view(-1, rel_rows), z2.view(-1, rel_rows)
-        pk2d, pq2d = rec["pk"].view(-1, 64), rec["pq"].view(-1, 64)
+        if rel:
+            z1_2d, z2_2d = z1.view(-1, rel_rows), z2.view(-1, rel_rows)
+            pk2d, pq2d = rec["pk"].view(-1, 64), rec["pq"].view(-1, 64)
         dq32, dk32, dv32 = dqkv32[:, :H], dqkv32[:, H:2 * H], dqkv32[:, 2 * H:]
         sq, sk_, svv = Q.stride(0), K.stride(0), V.stride(0)
         o3 = 3 * H
@@ -563,11 +590,14 @@ class DebertaEngine:
         # dQ = dS . K + Z1 . PKrel
         lib.gemm(ds2d, K, dq32, b_mn_major=True, M=L, N=64, K=L,
                  batch={"outer": (B, h * L * lp, L * sk_, L * o3), "inner": (h, L * lp, 64, 64)})
-        lib.gemm(z1_2d, pk2d, dq32, b_mn_major=True, M=L, N=64, K=rel_rows, accumulate=True,
-                 batch={"outer": (B, L * rel_rows, 0, L * o3), "inner": (h, B * L * rel_rows, rel_rows * 64, 64)})
+        if rel:
+            lib.gemm(z1_2d, pk2d, dq32, b_mn_major=True, M=L, N=64, K=rel_rows, accumulate=True,
+                     batch={"outer": (B, L * rel_rows, 0, L * o3), "inner": (h, B * L * rel_rows, rel_rows * 64, 64)})
         # dK = dS^T . Q + Z2 . PQrel
         lib.gemm(ds2d, Q, dk32, a_mn_major=True, b_mn_major=True, M=L, N=64, K=L,
                  batch={"outer": (B, h * L * lp, L * sq, L * o3), "inner": (h, L * lp, 64, 64)})
+        if not rel:
+            return dqkv32
         lib.gemm(z2_2d, pq2d, dk32, b_mn_major=True, M=L, N=64, K=rel_rows, accumulate=True,
                  batch={"outer": (B, L * rel_rows, 0, L * o3), "inner": (h, B * L * rel_rows, rel_rows * 64, 64)})
         # positional projections: dPKrel = Z1^T . Q, dPQrel = Z2^T . K (sum over batch inside the K dimension)
@@ -587,3 +617,111 @@ class DebertaEngine:
         lib.dropout_apply(dRd32, self.drop(cfg.hidden_dropout_prob, pass_id * 8 + SITE_POS), out32=self._dR32,
                           accumulate=True)
         return dqkv32
+
+
+class BertEngine(DebertaEngine):
+    """BERT variant of the path (reference model/bert.py, BASELINE.json configs[4]): visual prefix + absolute
+    position / token-type embeddings (:246-278), plain attention with an additive key mask (:141-191), post-LN
+    blocks without adapters (:281-292, 349-360), MLM head on ``cls.predictions.decoder`` (:74-96).  Same kernels
+    as the DeBERTa path: fb_attn_fwd in plain mode (no relative tables), the same GEMM / LayerNorm schedule."""
+
+    def __init__(self, cfg, params, device):
+        super().__init__(cfg, params, device)
+        self.use_rel = False
+        self.attn_scale = 1.0 / math.sqrt(64)
+        self.layer_prefix = "bert.encoder.layer."
+        self.hn = dict(dense_b="cls.predictions.transform.dense.bias", ln_w="cls.predictions.transform.LayerNorm.weight",
+                       ln_b="cls.predictions.transform.LayerNorm.bias", bias="cls.predictions.bias")
+
+    def prepare_frozen(self):
+        cfg, P, W = self.cfg, self.P, self.W
+        with torch.no_grad():
+            for i in range(cfg.num_hidden_layers):
+                p = f"bert.encoder.layer.{i}."
+                a = p + "attention.self."
+                W[f"qkv.w.{i}"] = torch.cat([P[a + "query.weight"], P[a + "key.weight"], P[a + "value.weight"]],
+                                            0).to(BF16).contiguous()
+                W[f"qkv.b.{i}"] = torch.cat([P[a + "query.bias"], P[a + "key.bias"], P[a + "value.bias"]],
+                                            0).float().contiguous()
+                W[f"o.w.{i}"] = P[p + "attention.output.dense.weight"].to(BF16).contiguous()
+                W[f"ffn1.w.{i}"] = P[p + "intermediate.dense.weight"].to(BF16).contiguous()
+                W[f"ffn2.w.{i}"] = P[p + "output.dense.weight"].to(BF16).contiguous()
+            W["head.w"] = P["cls.predictions.transform.dense.weight"].to(BF16).contiguous()
+            W["emb16"] = P["cls.predictions.decoder.weight"].to(BF16).contiguous()
+            if cfg.n_ans:
+                self.refresh_answer_embeddings()
+        self._frozen_versions = self._frozen_sig()
+
+    def forward_encoder(self, video, video_mask, input_ids, attention_mask, training):
+        cfg, P, W, ws = self.cfg, self.P, self.W, self.ws
+        if self._frozen_versions != self._frozen_sig():
+            self.prepare_frozen()
+        self.training = bool(training)
+        self.step_seed += 1
+        dev = self.device
+        H, NL = cfg.hidden_size, cfg.num_hidden_layers
+        B, Lt = input_ids.shape
+        use_video = bool(cfg.features_dim) and video is not None
+        F = video.shape[1] if use_video else 0
+        L = F + Lt
+        T = B * L
+        if L > cfg.max_position_embeddings or L > 512:
+            raise ValueError(f"sequence length {L} exceeds max_position_embeddings / kernel limit 512")
+        self.dims = (B, L, F, Lt, T)
+        e = "bert.embeddings."
+        sv = {"passes": []} if training else None
+        if attention_mask is None:
+            attention_mask = torch.ones(B, Lt, device=dev, dtype=torch.long)
+        if use_video:
+            if video_mask is None:
+                video_mask = torch.ones(B, F, device=dev, dtype=torch.long)
+            m = torch.cat([video_mask.to(dev), attention_mask.to(dev)], 1)
+        else:
+            m = attention_mask.to(dev)
+        self.mask_u8 = (m != 0).to(torch.uint8).contiguous()
+        # ---- embeddings: [linear_video(video) ; word_emb[ids]] + pos + type(0) -> LN -> dropout (no mask multiply)
+        g32 = ws.get("g32", (T, H), F32)
+        v16 = None
+        if use_video:
+            Dv = cfg.features_dim
+            v16 = ws.get("video16", (B * F, _ceil8(Dv)), BF16)
+            vin = video.to(dev, F32).reshape(B * F, Dv).contiguous()
+            if _ceil8(Dv) != Dv:
+                v16.zero_()
+                v16[:, :Dv] = vin.to(BF16)
+            else:
+                lib.cast_bf16(vin, v16)
+            lib.gemm(v16, self.t16(e + "linear_video.weight"), g32, bias=P[e + "linear_video.bias"], M=F, N=H, K=Dv,
+                     batch={"outer": (B, F * v16.stride(0), 0, L * H)})
+            idx_out = (torch.arange(B, device=dev)[:, None] * L + F + torch.arange(Lt, device=dev)[None, :]).reshape(-1)
+        else:
+            idx_out = None
+        lib.move_rows(P[e + "word_embeddings.weight"], g32, idx_in=input_ids.to(dev).reshape(-1).contiguous(),
+                      idx_out=idx_out.contiguous() if idx_out is not None else None)
+        pos_type = (P[e + "position_embeddings.weight"][:L] + P[e + "token_type_embeddings.weight"][0]).contiguous()
+        e32 = ws.get("e32", (T, H), F32)
+        lib.add_rowbcast(g32, pos_type, B, L, H, e32)
+        x32, x16 = ws.get("x32.0", (T, H), F32), ws.get("x16.0", (T, H), BF16)
+        emb_mean, emb_rstd = ws.get("emb.mean", (T,), F32), ws.get("emb.rstd", (T,), F32)
+        lib.layernorm_fwd(e32, P[e + "LayerNorm.weight"], P[e + "LayerNorm.bias"], cfg.layer_norm_eps,
+                          out_drop=self.drop(cfg.hidden_dropout_prob, OFF_EMB), y32=x32, y16=x16, mean=emb_mean,
+                          rstd=emb_rstd)
+        for i in range(NL):
+            qkv = ws.get(f"qkv.{i}" if training else "qkv", (T, 3 * H), BF16)
+            lib.gemm(x16, W[f"qkv.w.{i}"], qkv, bias=W[f"qkv.b.{i}"])
+            x32, x16, rec = self._layer_pass(i, i, x32, qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], training)
+            if training:
+                rec["qkv"] = qkv
+                sv["passes"].append(rec)
+        if training:
+            sv.update(e32=e32, emb_mean=emb_mean, emb_rstd=emb_rstd, video16=v16, use_video=use_video)
+            self.saved = sv
+        self.o2_32, self.o2_16 = x32, x16
+        return x32, x16
+
+    def _bwd_encoder(self, dy32):
+        sv = self.saved
+        dx32 = dy32
+        for rec in reversed(sv["passes"]):
+            dx32 = self._bwd_pass(rec, dx32, emd=False, slot=rec["pass_id"] % 2)
+        self._bwd_embeddings(dx32, "bert.embeddings.", rowmask=None)

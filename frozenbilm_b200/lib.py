@@ -65,6 +65,7 @@ class AttnArgs(C.Structure):
         ("scale", C.c_float),
         ("dropout_p", C.c_float), ("seed", C.c_ulonglong), ("offset", C.c_ulonglong),
         ("s_out", C.c_void_p),
+        ("key_mask_only", C.c_int),
     ]
 
 
@@ -236,11 +237,13 @@ def build_rel_tables(pqk: torch.Tensor, bucket_of_rel: torch.Tensor, L: int, h: 
 
 
 def attn_fwd(Q, K, V, PKrel, PQrel, mask_u8, ctx, lse, *, B, L, h, scale, dropout_p=0.0, seed=0, offset=0,
-             s_out=None):
+             s_out=None, key_mask_only=False):
     """Q/K/V: bf16 2-D views [B*L, >= h*64] (row pitch = stride(0)); ctx: bf16 [B*L, H]; lse: fp32 [B, h, L]."""
     rel_rows, rel_off = rel_table_geometry(L)
-    assert PKrel.shape[1] == rel_rows and mask_u8.dtype == torch.uint8 and lse.dtype == torch.float32
+    assert mask_u8.dtype == torch.uint8 and lse.dtype == torch.float32
+    assert PKrel is None or PKrel.shape[1] == rel_rows
     a = AttnArgs()
+    a.key_mask_only = int(key_mask_only)
     a.B, a.L, a.h = B, L, h
     a.Q, a.ldq = _ptr(Q), Q.stride(0)
     a.K, a.ldk = _ptr(K), K.stride(0)
@@ -341,7 +344,8 @@ def cast_bf16(x32, out16):
     check(load().fb_cast_f32_bf16(_ptr(x32), x32.numel(), _ptr(out16), stream_ptr()), "fb_cast_f32_bf16")
 
 
-def attn_bwd_prep(s2, lse, dp, ctx, dctx, ds, pd, z1, z2, *, B, L, h, scale, dropout_p=0.0, seed=0, offset=0):
+def attn_bwd_prep(s2, lse, dp, ctx, dctx, ds, pd, z1=None, z2=None, *, B, L, h, scale, dropout_p=0.0, seed=0,
+                  offset=0):
     rel_rows, rel_off = rel_table_geometry(L)
     a = AttnBwdPrepArgs()
     a.B, a.L, a.h, a.lp, a.rel_rows, a.rel_off = B, L, h, s2.shape[-1], rel_rows, rel_off

@@ -7,6 +7,7 @@ reference's parameter names, ``forward`` signature and outputs; the compute runs
 libfrozenbilm_sm100.so.  Only the BiLM hot path is provided: DeBERTa-V2 (+adapters) and BERT.  The
 autoregressive GPT-Neo / GPT-J baselines are out of scope and raise NotImplementedError like an unknown name.
 """
+from .bert import BertForMaskedLM
 from .deberta import DebertaV2ForMaskedLM
 
 
@@ -26,7 +27,10 @@ def build_model(args):
         return DebertaV2ForMaskedLM.from_pretrained(pretrained_model_name_or_path=name, local_files_only=True, **kw)
     if "bert" in name:
         assert (not args.ds_factor_ff) and (not args.ds_factor_attn) and (not args.scratch)
-        raise NotImplementedError("BERT variant (reference model/bert.py) is scheduled after the DeBERTa path")
+        return BertForMaskedLM.from_pretrained(
+            features_dim=args.features_dim if args.use_video else 0, max_feats=args.max_feats,
+            freeze_lm=args.freeze_lm, freeze_mlm=args.freeze_mlm, ft_ln=args.ft_ln, n_ans=args.n_ans,
+            freeze_last=args.freeze_last, pretrained_model_name_or_path=name, local_files_only=True)
     raise NotImplementedError
 
 

@@ -92,150 +92,36 @@ class _LogitsFn(torch.autograd.Function):
         return None, None, None
 
 
-class DebertaV2ForMaskedLM(nn.Module):
-    def __init__(self, config, max_feats=10, features_dim=768, freeze_lm=True, freeze_mlm=True, ds_factor_attn=8,
-                 ds_factor_ff=8, ft_ln=True, dropout=0.1, n_ans=0, freeze_last=True):
-        super().__init__()
-        self.config = config
-        self.fb = FBConfig.from_hf(config, features_dim=features_dim, max_feats=max_feats,
-                                   ds_factor_attn=ds_factor_attn, ds_factor_ff=ds_factor_ff,
-                                   adapter_dropout=dropout, n_ans=n_ans, freeze_lm=freeze_lm, freeze_mlm=freeze_mlm,
-                                   ft_ln=ft_ln, freeze_last=freeze_last)
-        fb = self.fb
-        H, I, V = fb.hidden_size, fb.intermediate_size, fb.vocab_size
-        eps = fb.layer_norm_eps
-        # ---- parameter holders with the reference's module tree (deberta.py:950-995, 420-472, 1523-1570)
-        deb = _Holder()
-        emb = _Holder()
-        emb.word_embeddings = nn.Embedding(V, H, padding_idx=fb.pad_token_id)
-        emb.position_embeddings = nn.Embedding(fb.max_position_embeddings, H)
-        emb.LayerNorm = nn.LayerNorm(H, eps)
-        emb.register_buffer("position_ids", torch.arange(fb.max_position_embeddings).expand((1, -1)))
-        if features_dim:
-            emb.linear_video = nn.Linear(features_dim, H)
-        deb.embeddings = emb
-        enc = _Holder()
-        layers = []
-        for _ in range(fb.num_hidden_layers):
-            lay = _Holder()
-            att = _Holder()
-            sa = _Holder()
-            sa.query_proj, sa.key_proj, sa.value_proj = nn.Linear(H, H), nn.Linear(H, H), nn.Linear(H, H)
-            att.self = sa
-            ao = _Holder()
-            ao.dense = nn.Linear(H, H)
-            ao.LayerNorm = nn.LayerNorm(H, eps)
-            if ds_factor_attn:
-                ao.adapter = _adapter(ds_factor_attn, H)
-            att.output = ao
-            lay.attention = att
-            inter = _Holder()
-            inter.dense = nn.Linear(H, I)
-            lay.intermediate = inter
-            out = _Holder()
-            out.dense = nn.Linear(I, H)
-            out.LayerNorm = nn.LayerNorm(H, eps)
-            if ds_factor_ff:
-                out.adapter = _adapter(ds_factor_ff, H)
-            lay.output = out
-            layers.append(lay)
-        enc.layer = nn.ModuleList(layers)
-        enc.rel_embeddings = nn.Embedding(2 * fb.position_buckets, H)
-        enc.LayerNorm = nn.LayerNorm(H, eps, elementwise_affine=True)
-        conv = _Holder()
-        conv.conv = nn.Conv1d(H, H, 3, padding=1)
-        conv.LayerNorm = nn.LayerNorm(H, eps)
-        enc.conv = conv
-        deb.encoder = enc
-        self.deberta = deb
-        head = _Holder()
-        lm = _Holder()
-        lm.dense = nn.Linear(H, H)
-        lm.LayerNorm = nn.LayerNorm(H, eps=eps)
-        lm.decoder = nn.Linear(H, V, bias=False)   # allocated but unused by forward, like the reference (:1535-1542)
-        lm.bias = nn.Parameter(torch.zeros(V))
-        lm.decoder.bias = lm.bias
-        head.lm_head = lm
-        self.lm_predictions = head
-        self.features_dim = features_dim
-        self.n_ans = n_ans
-        self._init_weights()
-        # ---- freezing rules (deberta.py:1152-1158, 1334-1339)
-        if freeze_lm:
-            for n, p in self.deberta.named_parameters():
-                if ("linear_video" not in n) and ("adapter" not in n):
-                    if ft_ln and "LayerNorm" in n:
-                        continue
-                    p.requires_grad_(False)
-        if freeze_mlm:
-            for n, p in self.lm_predictions.named_parameters():
-                if ft_ln and "LayerNorm" in n:
-                    continue
-                p.requires_grad_(False)
-        if n_ans:
-            self.answer_embeddings = nn.Embedding(n_ans, H)
-            self.answer_bias = nn.Parameter(torch.zeros(n_ans))
-            if freeze_last:
-                self.answer_embeddings.requires_grad_(False)
-                self.answer_bias.requires_grad_(False)
+class FrozenBiLMBase(nn.Module):
+    """Everything the two architectures share: the flat trainable bucket, the engine life-cycle, the forward
+    contract (loss / logits, lazy full logits) and the autograd bridge.  Sub-classes build the parameter holders
+    with the reference's names and set ``engine_cls``."""
+
+    engine_cls = DebertaEngine
+    word_embeddings_path = ("deberta", "embeddings", "word_embeddings")
+    head_bias_name = "lm_predictions.lm_head.bias"
+
+    def _post_init_state(self):
         self._engine_obj = None
         self._flat = None
         self._anchor = None
-
-    # ------------------------------------------------------------------ init / load
-    def _init_weights(self):
-        """N(0, initializer_range) matrices, zero biases, unit LayerNorm (deberta.py _init_weights);
-        adapters N(0, 1e-3) clamped to +-2e-3, biases included (adapter.py:23-28)."""
-        std = getattr(self.config, "initializer_range", 0.02)
-        for name, m in self.named_modules():
-            if isinstance(m, (nn.Linear, nn.Conv1d)):
-                if ".adapter." in name:
-                    nn.init.normal_(m.weight, std=1e-3)
-                    nn.init.normal_(m.bias, std=1e-3)
-                    m.weight.data.clamp_(-2e-3, 2e-3)
-                    m.bias.data.clamp_(-2e-3, 2e-3)
-                elif isinstance(m, nn.Linear):
-                    m.weight.data.normal_(0.0, std)
-                    if m.bias is not None:
-                        m.bias.data.zero_()
-            elif isinstance(m, nn.Embedding):
-                m.weight.data.normal_(0.0, std)
-                if m.padding_idx is not None:
-                    m.weight.data[m.padding_idx].zero_()
-
-    @classmethod
-    def from_pretrained(cls, pretrained_model_name_or_path, local_files_only=True, **kw):
-        """Loads an HF-format DeBERTa-V2 directory (config.json + pytorch_model.bin / model.safetensors),
-        like PreTrainedModel.from_pretrained in the reference (model/__init__.py:34-47)."""
-        from transformers import DebertaV2Config
-
-        path = pretrained_model_name_or_path
-        config = DebertaV2Config.from_pretrained(path, local_files_only=local_files_only)
-        model = cls(config=config, **kw)
-        sd = None
-        st = os.path.join(path, "model.safetensors")
-        pt = os.path.join(path, "pytorch_model.bin")
-        if os.path.exists(st):
-            from safetensors.torch import load_file
-
-            sd = load_file(st)
-        elif os.path.exists(pt):
-            sd = torch.load(pt, map_location="cpu")
-        else:
-            raise FileNotFoundError(f"no model.safetensors / pytorch_model.bin under {path}")
-        sd = {k.replace("lm_predictions.lm_head.LayerNorm.gamma", "lm_predictions.lm_head.LayerNorm.weight")
-               .replace("lm_predictions.lm_head.LayerNorm.beta", "lm_predictions.lm_head.LayerNorm.bias"): v
-              for k, v in sd.items()}
-        model.load_state_dict(sd, strict=False)
-        return model
 
     @property
     def device(self):
         return next(self.parameters()).device
 
+    def _word_embeddings(self):
+        m = self
+        for k in self.word_embeddings_path:
+            m = getattr(m, k)
+        return m
+
     # ------------------------------------------------------------------ flat trainable bucket
     def _param_dict(self):
         return OrderedDict((n, p) for n, p in self.named_parameters())
+
+    def _engine_params(self, named):
+        return {n: p.data for n, p in named.items()}
 
     def _ensure_engine(self):
         dev = self.device
@@ -262,8 +148,7 @@ class DebertaV2ForMaskedLM(nn.Module):
                               sig=tuple((n, p.data_ptr()) for n, p in train), version=-1, total=total)
             self._engine_obj = None
         if self._engine_obj is None:
-            P = {n: p.data for n, p in named.items() if "decoder" not in n}
-            self._engine_obj = DebertaEngine(self.fb, P, dev)
+            self._engine_obj = self.engine_cls(self.fb, self._engine_params(named), dev)
             self._anchor = torch.zeros(1, device=dev, requires_grad=True)
             self._flat["version"] = -1
         fl = self._flat
@@ -289,7 +174,7 @@ class DebertaV2ForMaskedLM(nn.Module):
         """Reference deberta.py:1358-1380: mean word embedding of the non-pad answer tokens.  The reference
         assigns the bias to an ATTRIBUTE (``answer_bias.weight``, :1375), so ``answer_bias`` itself keeps its
         values; that observable behaviour is reproduced."""
-        we = self.deberta.embeddings.word_embeddings.weight
+        we = self._word_embeddings().weight
         pad = self.fb.pad_token_id
         a2tok = a2tok.to(we.device)
         a2v = we.data[a2tok]
@@ -377,3 +262,144 @@ class DebertaV2ForMaskedLM(nn.Module):
             if n in foreign:
                 views[n].add_(foreign[n])
             p.grad = views[n]
+
+
+
+class DebertaV2ForMaskedLM(FrozenBiLMBase):
+    def __init__(self, config, max_feats=10, features_dim=768, freeze_lm=True, freeze_mlm=True, ds_factor_attn=8,
+                 ds_factor_ff=8, ft_ln=True, dropout=0.1, n_ans=0, freeze_last=True):
+        super().__init__()
+        self.config = config
+        self.fb = FBConfig.from_hf(config, features_dim=features_dim, max_feats=max_feats,
+                                   ds_factor_attn=ds_factor_attn, ds_factor_ff=ds_factor_ff,
+                                   adapter_dropout=dropout, n_ans=n_ans, freeze_lm=freeze_lm, freeze_mlm=freeze_mlm,
+                                   ft_ln=ft_ln, freeze_last=freeze_last)
+        fb = self.fb
+        H, I, V = fb.hidden_size, fb.intermediate_size, fb.vocab_size
+        eps = fb.layer_norm_eps
+        # ---- parameter holders with the reference's module tree (deberta.py:950-995, 420-472, 1523-1570)
+        deb = _Holder()
+        emb = _Holder()
+        emb.word_embeddings = nn.Embedding(V, H, padding_idx=fb.pad_token_id)
+        emb.position_embeddings = nn.Embedding(fb.max_position_embeddings, H)
+        emb.LayerNorm = nn.LayerNorm(H, eps)
+        emb.register_buffer("position_ids", torch.arange(fb.max_position_embeddings).expand((1, -1)))
+        if features_dim:
+            emb.linear_video = nn.Linear(features_dim, H)
+        deb.embeddings = emb
+        enc = _Holder()
+        layers = []
+        for _ in range(fb.num_hidden_layers):
+            lay = _Holder()
+            att = _Holder()
+            sa = _Holder()
+            sa.query_proj, sa.key_proj, sa.value_proj = nn.Linear(H, H), nn.Linear(H, H), nn.Linear(H, H)
+            att.self = sa
+            ao = _Holder()
+            ao.dense = nn.Linear(H, H)
+            ao.LayerNorm = nn.LayerNorm(H, eps)
+            if ds_factor_attn:
+                ao.adapter = _adapter(ds_factor_attn, H)
+            att.output = ao
+            lay.attention = att
+            inter = _Holder()
+            inter.dense = nn.Linear(H, I)
+            lay.intermediate = inter
+            out = _Holder()
+            out.dense = nn.Linear(I, H)
+            out.LayerNorm = nn.LayerNorm(H, eps)
+            if ds_factor_ff:
+                out.adapter = _adapter(ds_factor_ff, H)
+            lay.output = out
+            layers.append(lay)
+        enc.layer = nn.ModuleList(layers)
+        enc.rel_embeddings = nn.Embedding(2 * fb.position_buckets, H)
+        enc.LayerNorm = nn.LayerNorm(H, eps, elementwise_affine=True)
+        conv = _Holder()
+        conv.conv = nn.Conv1d(H, H, 3, padding=1)
+        conv.LayerNorm = nn.LayerNorm(H, eps)
+        enc.conv = conv
+        deb.encoder = enc
+        self.deberta = deb
+        head = _Holder()
+        lm = _Holder()
+        lm.dense = nn.Linear(H, H)
+        lm.LayerNorm = nn.LayerNorm(H, eps=eps)
+        lm.decoder = nn.Linear(H, V, bias=False)   # allocated but unused by forward, like the reference (:1535-1542)
+        lm.bias = nn.Parameter(torch.zeros(V))
+        lm.decoder.bias = lm.bias
+        head.lm_head = lm
+        self.lm_predictions = head
+        self.features_dim = features_dim
+        self.n_ans = n_ans
+        self._init_weights()
+        # ---- freezing rules (deberta.py:1152-1158, 1334-1339)
+        if freeze_lm:
+            for n, p in self.deberta.named_parameters():
+                if ("linear_video" not in n) and ("adapter" not in n):
+                    if ft_ln and "LayerNorm" in n:
+                        continue
+                    p.requires_grad_(False)
+        if freeze_mlm:
+            for n, p in self.lm_predictions.named_parameters():
+                if ft_ln and "LayerNorm" in n:
+                    continue
+                p.requires_grad_(False)
+        if n_ans:
+            self.answer_embeddings = nn.Embedding(n_ans, H)
+            self.answer_bias = nn.Parameter(torch.zeros(n_ans))
+            if freeze_last:
+                self.answer_embeddings.requires_grad_(False)
+                self.answer_bias.requires_grad_(False)
+        self._post_init_state()
+
+    def _engine_params(self, named):
+        return {n: p.data for n, p in named.items() if "decoder" not in n}   # lm_head.decoder is unused (:1535-1542)
+
+    # ------------------------------------------------------------------ init / load
+    def _init_weights(self):
+        """N(0, initializer_range) matrices, zero biases, unit LayerNorm (deberta.py _init_weights);
+        adapters N(0, 1e-3) clamped to +-2e-3, biases included (adapter.py:23-28)."""
+        std = getattr(self.config, "initializer_range", 0.02)
+        for name, m in self.named_modules():
+            if isinstance(m, (nn.Linear, nn.Conv1d)):
+                if ".adapter." in name:
+                    nn.init.normal_(m.weight, std=1e-3)
+                    nn.init.normal_(m.bias, std=1e-3)
+                    m.weight.data.clamp_(-2e-3, 2e-3)
+                    m.bias.data.clamp_(-2e-3, 2e-3)
+                elif isinstance(m, nn.Linear):
+                    m.weight.data.normal_(0.0, std)
+                    if m.bias is not None:
+                        m.bias.data.zero_()
+            elif isinstance(m, nn.Embedding):
+                m.weight.data.normal_(0.0, std)
+                if m.padding_idx is not None:
+                    m.weight.data[m.padding_idx].zero_()
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, local_files_only=True, **kw):
+        """Loads an HF-format DeBERTa-V2 directory (config.json + pytorch_model.bin / model.safetensors),
+        like PreTrainedModel.from_pretrained in the reference (model/__init__.py:34-47)."""
+        from transformers import DebertaV2Config
+
+        path = pretrained_model_name_or_path
+        config = DebertaV2Config.from_pretrained(path, local_files_only=local_files_only)
+        model = cls(config=config, **kw)
+        sd = None
+        st = os.path.join(path, "model.safetensors")
+        pt = os.path.join(path, "pytorch_model.bin")
+        if os.path.exists(st):
+            from safetensors.torch import load_file
+
+            sd = load_file(st)
+        elif os.path.exists(pt):
+            sd = torch.load(pt, map_location="cpu")
+        else:
+            raise FileNotFoundError(f"no model.safetensors / pytorch_model.bin under {path}")
+        sd = {k.replace("lm_predictions.lm_head.LayerNorm.gamma", "lm_predictions.lm_head.LayerNorm.weight")
+               .replace("lm_predictions.lm_head.LayerNorm.beta", "lm_predictions.lm_head.LayerNorm.bias"): v
+              for k, v in sd.items()}
+        model.load_state_dict(sd, strict=False)
+        return model
+

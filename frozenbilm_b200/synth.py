@@ -18,6 +18,42 @@ def param_spec(cfg: FBConfig) -> "OrderedDict[str, tuple]":
     """name -> shape for every tensor the hot path reads (reference model/deberta.py)."""
     H, I, V = cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size
     s = OrderedDict()
+    if cfg.arch == "bert":
+        e = "bert.embeddings."
+        s[e + "word_embeddings.weight"] = (V, H)
+        s[e + "position_embeddings.weight"] = (cfg.max_position_embeddings, H)
+        s[e + "token_type_embeddings.weight"] = (cfg.type_vocab_size, H)
+        s[e + "LayerNorm.weight"] = (H,)
+        s[e + "LayerNorm.bias"] = (H,)
+        if cfg.features_dim:
+            s[e + "linear_video.weight"] = (H, cfg.features_dim)
+            s[e + "linear_video.bias"] = (H,)
+        for i in range(cfg.num_hidden_layers):
+            p = f"bert.encoder.layer.{i}."
+            for nm in ("query", "key", "value"):
+                s[p + f"attention.self.{nm}.weight"] = (H, H)
+                s[p + f"attention.self.{nm}.bias"] = (H,)
+            s[p + "attention.output.dense.weight"] = (H, H)
+            s[p + "attention.output.dense.bias"] = (H,)
+            s[p + "attention.output.LayerNorm.weight"] = (H,)
+            s[p + "attention.output.LayerNorm.bias"] = (H,)
+            s[p + "intermediate.dense.weight"] = (I, H)
+            s[p + "intermediate.dense.bias"] = (I,)
+            s[p + "output.dense.weight"] = (H, I)
+            s[p + "output.dense.bias"] = (H,)
+            s[p + "output.LayerNorm.weight"] = (H,)
+            s[p + "output.LayerNorm.bias"] = (H,)
+        h = "cls.predictions."
+        s[h + "bias"] = (V,)
+        s[h + "transform.dense.weight"] = (H, H)
+        s[h + "transform.dense.bias"] = (H,)
+        s[h + "transform.LayerNorm.weight"] = (H,)
+        s[h + "transform.LayerNorm.bias"] = (H,)
+        s[h + "decoder.weight"] = (V, H)
+        if cfg.n_ans:
+            s["answer_embeddings.weight"] = (cfg.n_ans, H)
+            s["answer_bias"] = (cfg.n_ans,)
+        return s
     e = "deberta.embeddings."
     s[e + "word_embeddings.weight"] = (V, H)
     s[e + "position_embeddings.weight"] = (cfg.max_position_embeddings, H)
@@ -78,6 +114,8 @@ def is_trainable(name: str, cfg: FBConfig) -> bool:
     1348-1350 (answer embeddings)."""
     if name.startswith("answer_"):
         return not cfg.freeze_last
+    if name.startswith("cls."):
+        return not cfg.freeze_mlm   # bert.py:748-750 freezes the WHOLE head, its LayerNorm included
     if name.startswith("lm_predictions."):
         if not cfg.freeze_mlm:
             return True
@@ -109,9 +147,12 @@ def synth_params(cfg: FBConfig, seed: int = 1234, visible: bool = True) -> "Orde
             t = (0.02 if visible else 0.0) * torch.randn(shape, generator=g)
         elif "rel_embeddings" in name or "position_embeddings" in name:
             t = (0.5 if visible else 0.02) * torch.randn(shape, generator=g)
-        elif "word_embeddings" in name or name == "answer_embeddings.weight":
+        elif "word_embeddings" in name or name == "answer_embeddings.weight" or name == "cls.predictions.decoder.weight":
             t = (0.05 if visible else 0.02) * torch.randn(shape, generator=g)
-        elif name.endswith("query_proj.weight") or name.endswith("key_proj.weight"):
+        elif "token_type_embeddings" in name:
+            t = (0.5 if visible else 0.02) * torch.randn(shape, generator=g)
+        elif name.endswith("query_proj.weight") or name.endswith("key_proj.weight") or \
+                name.endswith("self.query.weight") or name.endswith("self.key.weight"):
             # larger q/k weights give non-flat attention so softmax/bias bugs are visible
             t = (0.06 if visible else 0.02) * torch.randn(shape, generator=g)
         else:

@@ -96,6 +96,9 @@ typedef struct fb_attn_args {
   float dropout_p; unsigned long long seed; unsigned long long offset;
   float* s_out;   /* optional fp32 [B, h, L, ceil128(L)]: masked scaled scores in the log2 domain, kept for
                      the backward (training only) */
+  int key_mask_only; /* 0: DeBERTa mask M[i,j] = m_i*m_j (deberta.py:480-490); 1: BERT additive key mask
+                        (bert.py:165-169): padded QUERY rows are computed normally.  PKrel = PQrel = NULL selects
+                        plain attention (BertSelfAttention, bert.py:141-191). */
 } fb_attn_args;
 
 int fb_attn_fwd(const fb_attn_args* args, void* stream);

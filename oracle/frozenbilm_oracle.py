@@ -233,10 +233,68 @@ def forward(P, cfg, *, video, video_mask, input_ids, attention_mask, labels=None
     return out
 
 
+def bert_forward(P, cfg, *, video, video_mask, input_ids, attention_mask, labels=None, mlm=False,
+                 bf16_gemm_inputs=False, return_hidden=False):
+    """BERT variant, reference model/bert.py: embeddings :246-278 (visual prefix + absolute positions + token type 0,
+    LayerNorm, NO mask multiply), BertSelfAttention :141-191 (scores / sqrt(d) + (1 - m_key) * -10000, every query
+    row computed), BertSelfOutput / BertOutput :281-292, 349-360 (post-LN, no adapters), BertLMPredictionHead
+    :74-96 (decoder weight in MLM mode, answer embeddings downstream), loss :846-860."""
+    ctx = _Ctx(bf16_gemm_inputs)
+    eps = cfg.layer_norm_eps
+    e = "bert.embeddings."
+    B, Lt = input_ids.shape
+    emb = P[e + "word_embeddings.weight"][input_ids]
+    if cfg.features_dim and video is not None:
+        v = ctx.lin(video, P[e + "linear_video.weight"], P[e + "linear_video.bias"])
+        emb = torch.cat([v, emb], 1)
+        if video_mask is None:
+            video_mask = torch.ones(video.shape[:2], dtype=attention_mask.dtype)
+        m = torch.cat([video_mask, attention_mask], 1)
+    else:
+        m = attention_mask
+    L = emb.shape[1]
+    emb = emb + P[e + "position_embeddings.weight"][:L] + P[e + "token_type_embeddings.weight"][0]
+    x = layer_norm(emb, P[e + "LayerNorm.weight"], P[e + "LayerNorm.bias"], eps)
+    ext = (1.0 - m.to(emb.dtype))[:, None, None, :] * -10000.0
+    h, d = cfg.num_attention_heads, cfg.head_dim
+    hidden = [x]
+    for i in range(cfg.num_hidden_layers):
+        p = f"bert.encoder.layer.{i}."
+        a = p + "attention.self."
+        Q = heads(ctx.lin(x, P[a + "query.weight"], P[a + "query.bias"]), h)
+        K = heads(ctx.lin(x, P[a + "key.weight"], P[a + "key.bias"]), h)
+        V = heads(ctx.lin(x, P[a + "value.weight"], P[a + "value.bias"]), h)
+        s = ctx.r(Q) @ ctx.r(K).transpose(-1, -2) / math.sqrt(d) + ext
+        pr = torch.softmax(s, -1)
+        c = (ctx.r(pr) @ ctx.r(V)).permute(0, 2, 1, 3).reshape(B, L, h * d)
+        u = ctx.lin(c, P[p + "attention.output.dense.weight"], P[p + "attention.output.dense.bias"])
+        a1 = layer_norm(u + x, P[p + "attention.output.LayerNorm.weight"], P[p + "attention.output.LayerNorm.bias"], eps)
+        f = gelu(ctx.lin(a1, P[p + "intermediate.dense.weight"], P[p + "intermediate.dense.bias"]))
+        y = ctx.lin(f, P[p + "output.dense.weight"], P[p + "output.dense.bias"])
+        x = layer_norm(y + a1, P[p + "output.LayerNorm.weight"], P[p + "output.LayerNorm.bias"], eps)
+        hidden.append(x)
+    hp = "cls.predictions."
+    t = layer_norm(gelu(ctx.lin(x, P[hp + "transform.dense.weight"], P[hp + "transform.dense.bias"])),
+                   P[hp + "transform.LayerNorm.weight"], P[hp + "transform.LayerNorm.bias"], eps)
+    if cfg.n_ans and not mlm:
+        logits = ctx.lin(t, P["answer_embeddings.weight"]) + P["answer_bias"]
+    else:
+        logits = ctx.lin(t, P[hp + "decoder.weight"]) + P[hp + "bias"]
+    loss = None
+    if labels is not None:
+        if cfg.features_dim and video is not None:
+            labels = torch.cat([torch.full((B, L - Lt), -100, dtype=labels.dtype), labels], 1)
+        loss = Fnn.cross_entropy(logits.reshape(-1, logits.shape[-1]), labels.reshape(-1), ignore_index=-100)
+    out = dict(logits=logits, loss=loss)
+    if return_hidden:
+        out["hidden"] = hidden
+    return out
+
+
 def forward_backward(P, cfg, trainable_names, **kw):
     """Runs forward + autograd backward; returns (out, {name: grad}) for the trainable set."""
     Pg = {k: (v.clone().requires_grad_(True) if k in trainable_names else v) for k, v in P.items()}
-    out = forward(Pg, cfg, **kw)
+    out = (bert_forward if cfg.arch == "bert" else forward)(Pg, cfg, **kw)
     out["loss"].backward()
     grads = {k: Pg[k].grad for k in trainable_names if Pg[k].grad is not None}
     return out, grads

@@ -78,3 +78,34 @@ def build_reference_deberta(hf_config, *, max_feats, features_dim=768, ds_factor
         ds_factor_ff=ds_factor_ff, ft_ln=ft_ln, dropout=dropout, n_ans=n_ans,
         freeze_last=freeze_last)
     return model
+
+
+def load_reference_bert():
+    """Returns the reference's model.bert module (shims 5-7 of SURVEY.md section 8c)."""
+    if "bert" in _cache:
+        return _cache["bert"]
+    import transformers.modeling_utils as mu
+    import transformers.pytorch_utils as pu
+
+    for name in ("apply_chunking_to_forward", "prune_linear_layer"):
+        if not hasattr(mu, name):
+            setattr(mu, name, getattr(pu, name))
+    if not hasattr(mu, "find_pruneable_heads_and_indices"):
+        mu.find_pruneable_heads_and_indices = None
+    bert = _load("_ref_model_bert", os.path.join(REF_ROOT, "model", "bert.py"))
+    # transformers 4.17.0 semantics of the additive key mask: (1 - m) * -10000 (requirements.txt:10)
+    bert.BertModel.get_extended_attention_mask = \
+        lambda self, m, shape, device=None: (1.0 - m[:, None, None, :].float()) * -10000.0
+    bert.BertModel.get_head_mask = lambda self, hm, n, *a, **k: [None] * n
+    bert.BertPreTrainedModel.init_weights = lambda self: self.apply(self._init_weights)
+    bert.BertPreTrainedModel.post_init = lambda self: self.apply(self._init_weights)
+    _cache["bert"] = bert
+    return bert
+
+
+def build_reference_bert(hf_config, *, max_feats, features_dim=768, n_ans=0, freeze_lm=True, freeze_mlm=True,
+                         ft_ln=True, freeze_last=True):
+    bert = load_reference_bert()
+    return bert.BertForMaskedLM(config=hf_config, max_feats=max_feats, features_dim=features_dim,
+                                freeze_lm=freeze_lm, freeze_mlm=freeze_mlm, ft_ln=ft_ln, n_ans=n_ans,
+                                freeze_last=freeze_last)

@@ -16,9 +16,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from frozenbilm_b200.config import CONFIG_BASE, CONFIG_TINY  # noqa: E402
+from frozenbilm_b200.config import CONFIG_BASE, CONFIG_BERT_TINY, CONFIG_TINY  # noqa: E402
 from frozenbilm_b200.synth import synth_params, synth_batch, is_trainable  # noqa: E402
-from oracle.ref_loader import build_reference_deberta  # noqa: E402
+from oracle.ref_loader import build_reference_bert, build_reference_deberta  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -32,6 +32,9 @@ CASES = {
     "tiny_ans2_b2_f10_t22": (CONFIG_TINY.replace(n_ans=2), 2, 22, 10, True, "ans"),
     # BASELINE.json configs[0]
     "base_b2_f2_t32": (CONFIG_BASE, 2, 32, 2, True, "mlm"),
+    # BERT variant (reference model/bert.py): plain attention, absolute positions, no adapters
+    "bert_tiny_b3_f10_t118": (CONFIG_BERT_TINY, 3, 118, 10, True, "mlm"),
+    "bert_tiny_ans2_b2_f10_t22": (CONFIG_BERT_TINY.replace(n_ans=2), 2, 22, 10, True, "ans"),
 }
 
 LOGIT_COLS = 97   # stride over the vocab axis
@@ -48,10 +51,14 @@ def run_case(name, cfg, B, Lt, F, ragged, mode, seed=1234):
     torch.manual_seed(0)
     P = synth_params(cfg, seed)
     batch = synth_batch(cfg, B, Lt, seed + 1, n_frames=F, ragged=ragged)
-    model = build_reference_deberta(
-        cfg.to_hf(), max_feats=cfg.max_feats, features_dim=cfg.features_dim,
-        ds_factor_attn=cfg.ds_factor_attn, ds_factor_ff=cfg.ds_factor_ff, dropout=cfg.adapter_dropout,
-        n_ans=cfg.n_ans)
+    if cfg.arch == "bert":
+        model = build_reference_bert(cfg.to_hf(), max_feats=cfg.max_feats, features_dim=cfg.features_dim,
+                                     n_ans=cfg.n_ans)
+    else:
+        model = build_reference_deberta(
+            cfg.to_hf(), max_feats=cfg.max_feats, features_dim=cfg.features_dim,
+            ds_factor_attn=cfg.ds_factor_attn, ds_factor_ff=cfg.ds_factor_ff, dropout=cfg.adapter_dropout,
+            n_ans=cfg.n_ans)
     missing, unexpected = model.load_state_dict(P, strict=False)
     assert not unexpected, unexpected
     assert all(("decoder" in k or "position_ids" in k) for k in missing), missing
@@ -62,7 +69,7 @@ def run_case(name, cfg, B, Lt, F, ragged, mode, seed=1234):
               attention_mask=batch["attention_mask"])
     fx = {}
     if mode == "mlm":
-        out = model(labels=batch["labels"], **kw)
+        out = model(labels=batch["labels"], output_hidden_states=True, **kw)
         out.loss.backward()
         fx["loss"] = np.float64(out.loss.item())
         for n, p in model.named_parameters():
@@ -72,7 +79,7 @@ def run_case(name, cfg, B, Lt, F, ragged, mode, seed=1234):
                 fx["gslice/" + n] = g[::GRAD_STRIDE].numpy().copy()
     else:
         with torch.no_grad():
-            out = model(**kw)
+            out = model(output_hidden_states=True, **kw)
     lg = out.logits.detach().numpy()
     sl, cols = logit_slice(lg)
     fx["logits_slice"] = sl.copy()

@@ -25,10 +25,13 @@ DEV = "cuda"
 
 
 def build(cfg, P):
-    from frozenbilm_b200.model import DebertaV2ForMaskedLM
-    m = DebertaV2ForMaskedLM(cfg.to_hf(), max_feats=cfg.max_feats, features_dim=cfg.features_dim,
-                             ds_factor_attn=cfg.ds_factor_attn, ds_factor_ff=cfg.ds_factor_ff,
-                             dropout=cfg.adapter_dropout, n_ans=cfg.n_ans)
+    from frozenbilm_b200.model import BertForMaskedLM, DebertaV2ForMaskedLM
+    if cfg.arch == "bert":
+        m = BertForMaskedLM(cfg.to_hf(), max_feats=cfg.max_feats, features_dim=cfg.features_dim, n_ans=cfg.n_ans)
+    else:
+        m = DebertaV2ForMaskedLM(cfg.to_hf(), max_feats=cfg.max_feats, features_dim=cfg.features_dim,
+                                 ds_factor_attn=cfg.ds_factor_attn, ds_factor_ff=cfg.ds_factor_ff,
+                                 dropout=cfg.adapter_dropout, n_ans=cfg.n_ans)
     missing, unexpected = m.load_state_dict(P, strict=False)
     assert not unexpected
     return m.to(DEV)
@@ -74,7 +77,7 @@ def test_golden_logits_and_grads(name):
     assert np.abs(lg2[..., cols] - fx["logits_slice"]).max() <= 0.06 * scale
 
 
-@pytest.mark.parametrize("name", ["tiny_b3_f10_t118", "tiny_b2_f10_t342"])
+@pytest.mark.parametrize("name", ["tiny_b3_f10_t118", "tiny_b2_f10_t342", "bert_tiny_b3_f10_t118"])
 def test_against_oracle_with_bf16_operands(name):
     """Same rounding points on both sides -> tight tolerances, catches errors the fp32 comparison would hide."""
     from oracle import frozenbilm_oracle as orc
@@ -230,3 +233,25 @@ def test_fused_optimizer_matches_torch_adam():
         assert (p32 - ref_p.data).abs().max().item() <= 2e-6, it
         assert (p16.float() - p32).abs().max().item() <= 1e-2 * p32.abs().max().item()
         m1.zero_grad()
+
+
+def test_bert_large_width_train_step():
+    """BASELINE configs[4] dimensions (H=1024, 16 heads, L=266) with 2 layers and dropout on: one train step runs,
+    loss/grads finite, and only linear_video + the encoder LayerNorms receive gradients (bert.py:547-553, 748-750)."""
+    from frozenbilm_b200.config import CONFIG_BERT_LARGE
+    cfg = CONFIG_BERT_LARGE.replace(num_hidden_layers=2, vocab_size=4096)
+    P = synth_params(cfg, 13)
+    b = synth_batch(cfg, 4, 256, 14)
+    model = build(cfg, P).train()
+    out = model(labels=b["labels"].to(DEV), **to_dev(b))
+    out["loss"].backward()
+    assert torch.isfinite(out["loss"])
+    n = 0
+    for name, p in model.named_parameters():
+        if p.requires_grad:
+            assert ("LayerNorm" in name and name.startswith("bert.")) or "linear_video" in name
+            assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().max() > 0, name
+            n += 1
+        else:
+            assert p.grad is None
+    assert n == 2 + 2 + 2 * 2 * 2

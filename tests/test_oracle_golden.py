@@ -23,7 +23,7 @@ def test_oracle_matches_reference_golden(name):
         assert abs(out["loss"].item() - float(fx["loss"])) < 2e-5 * max(1.0, abs(float(fx["loss"])))
     else:
         with torch.no_grad():
-            out = orc.forward(P, cfg, return_hidden=True, **kw)
+            out = (orc.bert_forward if cfg.arch == "bert" else orc.forward)(P, cfg, return_hidden=True, **kw)
         assert out["loss"] is None
     lg = out["logits"].detach().numpy()
     cols = fx["logits_cols"]
