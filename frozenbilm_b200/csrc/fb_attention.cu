@@ -51,7 +51,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_pk,
                 const __grid_constant__ CUtensorMap map_pq, const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (128B swizzle atoms) by pointer arithmetic on the __shared__ array, so that the compiler
+  // keeps the shared address space (STS/LDS instead of generic ST/LD)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
   uint64_t* bar_q = bars + 0;
   uint64_t* bar_k = bars + 1;
@@ -181,20 +183,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_wait(bar_mma1, ph);
       tc_fence_after();
       if (g == 0) {
+        // key-validity bits of this block: word wq covers keys [32 wq, 32 wq + 32)
         const int j = j0 + a;
-        kmask[a] = (j < p.L) ? p.mask[(long long)b * p.L + j] : 0;
+        const bool ok = (j < p.L) && (p.mask[(long long)b * p.L + j] != 0);
+        const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) reinterpret_cast<uint32_t*>(kmask)[wq] = bits;
       }
       // ---- p2c: lane = KEY row a of X2; scatter its 160-column window into T2[query][key].
-      //      The 5 chunks are shared between the warpgroups (g = 0: chunks 0-2, g = 1: chunks 3-4).
+      //      Window offset t = 32q + e is valid for 31 - lane <= t < 159 - lane: chunk 0 needs e >= 31 - lane,
+      //      chunks 1-3 are valid for every lane, chunk 4 needs e < 31 - lane.  (g = 0: chunks 0-2, g = 1: 3-4.)
+      if constexpr (REL) {
 #pragma unroll 1
-      for (int q = (g == 0 ? 0 : 3); REL && q < (g == 0 ? 3 : 5); ++q) {
-        uint32_t v[32];
-        tmem_ld_32x32(lane_base + TM_X + (96 - 32 * wq + 32 * q), v);
-        tmem_ld_wait();
+        for (int q = (g == 0 ? 0 : 3); q < (g == 0 ? 3 : 5); ++q) {
+          uint32_t v[32];
+          tmem_ld_32x32(lane_base + TM_X + (96 - 32 * wq + 32 * q), v);
+          tmem_ld_wait();
+          __half* dst = T2 + (32 * q + lane - 31) * T_PITCH + a;   // element e -> dst[e * T_PITCH]
+          const int thr = 31 - lane;
+          if (q == 0) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int aa = 32 * q + e + lane - 31;
-          if (aa >= 0 && aa < 128) T2[aa * T_PITCH + a] = __float2half_rn(__uint_as_float(v[e]));
+            for (int e = 0; e < 32; ++e)
+              if (e >= thr) dst[e * T_PITCH] = __float2half_rn(__uint_as_float(v[e]));
+          } else if (q == 4) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e < thr) dst[e * T_PITCH] = __float2half_rn(__uint_as_float(v[e]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) dst[e * T_PITCH] = __float2half_rn(__uint_as_float(v[e]));
+          }
         }
       }
       tc_fence_before();
@@ -203,17 +220,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       mbar_wait(bar_mma2, ph);
       tc_fence_after();
       // ---- c2p: lane = QUERY row a of X1; keys b = a + 127 - c.  Warpgroup g needs b in [64g, 64g+64):
-      //      columns c in [a + 64(1-g), a + 64(1-g) + 63] -> 3 chunks starting at 32*wq + 64*(1-g).
+      //      3 chunks starting at column 32*wq + 64*(1-g); key of element e in chunk q: 64g + lane + 63 - 32q - e.
+      //      chunk 0 needs e >= lane, chunk 1 is valid for every lane, chunk 2 needs e < lane.
+      if constexpr (REL) {
 #pragma unroll 1
-      for (int q = 0; REL && q < 3; ++q) {
-        uint32_t v[32];
-        const int cbase = 32 * wq + 64 * (1 - g) + 32 * q;
-        tmem_ld_32x32(lane_base + TM_X + cbase, v);
-        tmem_ld_wait();
+        for (int q = 0; q < 3; ++q) {
+          uint32_t v[32];
+          tmem_ld_32x32(lane_base + TM_X + 32 * wq + 64 * (1 - g) + 32 * q, v);
+          tmem_ld_wait();
+          __half* dst = T1 + a * T_PITCH + 64 * g + lane + 63 - 32 * q;   // element e -> dst[-e]
+          if (q == 0) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int bb = a + 127 - (cbase + e);
-          if (bb >= 64 * g && bb < 64 * g + 64) T1[a * T_PITCH + bb] = __float2half_rn(__uint_as_float(v[e]));
+            for (int e = 0; e < 32; ++e)
+              if (e >= lane) dst[-e] = __float2half_rn(__uint_as_float(v[e]));
+          } else if (q == 2) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e < lane) dst[-e] = __float2half_rn(__uint_as_float(v[e]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) dst[-e] = __float2half_rn(__uint_as_float(v[e]));
+          }
         }
       }
       named_bar_sync(1, 256);  // T2 / kmask were written by other threads
@@ -224,32 +251,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int c0 = 64 * g + 32 * q;
         uint32_t v[32];
         tmem_ld_32x32(lane_base + TM_S + c0, v);
+        const uint32_t kbits = valid_q ? reinterpret_cast<const uint32_t*>(kmask)[2 * g + q] : 0u;
         tmem_ld_wait();
-        const uint4* t1 = reinterpret_cast<const uint4*>(T1 + a * T_PITCH + c0);
-        const uint4* t2 = reinterpret_cast<const uint4*>(T2 + a * T_PITCH + c0);
-        const uint4 km0 = *reinterpret_cast<const uint4*>(kmask + c0);
-        const uint4 km1 = *reinterpret_cast<const uint4*>(kmask + c0 + 16);
-        const uint32_t kmw[8] = {km0.x, km0.y, km0.z, km0.w, km1.x, km1.y, km1.z, km1.w};
+        if constexpr (REL) {
+          const uint4* t1 = reinterpret_cast<const uint4*>(T1 + a * T_PITCH + c0);
+          const uint4* t2 = reinterpret_cast<const uint4*>(T2 + a * T_PITCH + c0);
 #pragma unroll
-        for (int gg = 0; gg < 4; ++gg) {
-          const uint4 c1 = t1[gg], c2 = t2[gg];
-          const uint32_t w1[4] = {c1.x, c1.y, c1.z, c1.w}, w2[4] = {c2.x, c2.y, c2.z, c2.w};
+          for (int gg = 0; gg < 4; ++gg) {
+            const uint4 c1 = t1[gg], c2 = t2[gg];
+            const uint32_t w1[4] = {c1.x, c1.y, c1.z, c1.w}, w2[4] = {c2.x, c2.y, c2.z, c2.w};
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float2 f1 = make_float2(0.f, 0.f), f2 = make_float2(0.f, 0.f);
-            if constexpr (REL) {
-              f1 = __half22float2(*reinterpret_cast<const __half2*>(&w1[u]));
-              f2 = __half22float2(*reinterpret_cast<const __half2*>(&w2[u]));
+            for (int u = 0; u < 4; ++u) {
+              // positional terms: fp16 pair sum (one HADD2), then widen
+              const __half2 hs = __hadd2(*reinterpret_cast<const __half2*>(&w1[u]),
+                                         *reinterpret_cast<const __half2*>(&w2[u]));
+              const float2 f = __half22float2(hs);
+              const int e = gg * 8 + u * 2;
+              v[e] = __float_as_uint(__uint_as_float(v[e]) + f.x);
+              v[e + 1] = __float_as_uint(__uint_as_float(v[e + 1]) + f.y);
             }
-            const int e = gg * 8 + u * 2;
-            float s0 = (__uint_as_float(v[e]) + f1.x + f2.x) * p.scale_log2;
-            float s1 = (__uint_as_float(v[e + 1]) + f1.y + f2.y) * p.scale_log2;
-            if (!valid_q || ((kmw[e >> 2] >> (8 * (e & 3))) & 0xFF) == 0) s0 = -INFINITY;
-            if (!valid_q || ((kmw[(e + 1) >> 2] >> (8 * ((e + 1) & 3))) & 0xFF) == 0) s1 = -INFINITY;
-            mblk = fmaxf(mblk, fmaxf(s0, s1));
-            v[e] = __float_as_uint(s0);
-            v[e + 1] = __float_as_uint(s1);
           }
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float sc = ((kbits >> e) & 1u) ? __uint_as_float(v[e]) * p.scale_log2 : -INFINITY;
+          mblk = fmaxf(mblk, sc);
+          v[e] = __float_as_uint(sc);
         }
         tmem_st_32x32(lane_base + TM_S + c0, v);
         if (p.s_out != nullptr && i < p.L) {
@@ -275,7 +302,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         float pr[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          pr[e] = exp2f(__uint_as_float(v[e]) - m_use);
+          pr[e] = ex2_approx(__uint_as_float(v[e]) - m_use);   // ex2(-inf) = +0
           rsum += pr[e];
         }
         if (do_drop) {

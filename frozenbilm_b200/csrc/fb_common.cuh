@@ -336,17 +336,29 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c
 }
 
 // 8 Bernoulli(keep) decisions (bit e = keep element 8*group+e of row `rowid`), 16-bit resolution:
-// keep iff rnd16 >= thresh16 with thresh16 = round(p * 65536).
+// keep iff rnd16 >= thresh16 with thresh16 = round(p * 65536).  Counter-based: a 32-bit avalanche hash
+// (two multiply-xorshift rounds, "lowbias32" constants) of (seed, offset, row, group) expanded to four words.
+// Any (seed, offset, row, group) regenerates the same mask, so the backward never stores dropout masks; the
+// generator costs ~5 integer ops per element (Philox4x32-10 was ~12 and dominated the softmax epilogues).
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
+  return x;
+}
 __device__ __forceinline__ uint32_t dropout_keep8(uint32_t rowid, uint32_t group, uint32_t thresh16,
                                                   uint32_t seed_lo, uint32_t seed_hi, uint32_t off_lo,
                                                   uint32_t off_hi) {
-  const uint4 r = philox4x32(rowid, group, off_lo, off_hi, seed_lo, seed_hi);
-  uint32_t m = 0;
-  m |= ((r.x & 0xFFFF) >= thresh16) << 0; m |= ((r.x >> 16) >= thresh16) << 1;
-  m |= ((r.y & 0xFFFF) >= thresh16) << 2; m |= ((r.y >> 16) >= thresh16) << 3;
-  m |= ((r.z & 0xFFFF) >= thresh16) << 4; m |= ((r.z >> 16) >= thresh16) << 5;
-  m |= ((r.w & 0xFFFF) >= thresh16) << 6; m |= ((r.w >> 16) >= thresh16) << 7;
-  return m;
+  const uint32_t k0 = seed_lo ^ (off_lo * 0x9E3779B1u) ^ (off_hi * 0x85EBCA77u);   // loop-invariant
+  const uint32_t k1 = (seed_hi ^ 0xC2B2AE3Du) + off_lo * 0x27D4EB2Fu;
+  const uint32_t a = mix32((rowid * 0x9E3779B1u) ^ (group * 0x85EBCA6Bu + k0)) ^ k1;
+  const uint32_t th2 = thresh16 * 0x00010001u;
+  // __vsetgeu2: per 16-bit half 1 if r >= th else 0
+  const uint32_t c0 = __vsetgeu2(mix32(a), th2);
+  const uint32_t c1 = __vsetgeu2(mix32(a + 0x9E3779B9u), th2);
+  const uint32_t c2 = __vsetgeu2(mix32(a + 0x3C6EF372u), th2);
+  const uint32_t c3 = __vsetgeu2(mix32(a + 0xDAA66D2Bu), th2);
+  // halves -> bits 0..7
+  return (c0 & 1u) | ((c0 >> 15) & 2u) | ((c1 & 1u) << 2) | ((c1 >> 13) & 8u) | ((c2 & 1u) << 4) |
+         ((c2 >> 11) & 32u) | ((c3 & 1u) << 6) | ((c3 >> 9) & 128u);
 }
 
 // Host-side description of one dropout site (plain data, passed by value into kernels).

@@ -303,7 +303,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (128B swizzle atoms) by pointer arithmetic on the __shared__ array, so that the compiler
+  // keeps the shared address space (STS/LDS instead of generic ST/LD)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::STAGES * A_STAGE_BYTES;
   uint8_t* smem_store = smem + Cfg::STAGES * Cfg::STAGE_BYTES;   // 2 x 16 KB epilogue staging (TMA stores)
