@@ -96,29 +96,71 @@ ln_fwd_kernel(const float* __restrict__ x, int M, const float* __restrict__ gamm
 // copy with the UPSTREAM hidden dropout's backward applied (the operand of the next dX/dW GEMMs).
 // ---------------------------------------------------------------------------------------------
 template <int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, const float* __restrict__ gamma, int M,
               const uint8_t* __restrict__ rowmask, DropSpec out_drop, DropSpec in_drop, float* __restrict__ dx32,
-              __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+              __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta,
+              float* __restrict__ dx16_colsum) {
+  // TWO warps per row (64 lanes x NV/2 float4 each): halves the per-thread dgamma/dbeta/column-sum accumulators so
+  // that two CTAs (16 warps) fit per SM; the row is streamed twice (second read hits L1/L2).
   constexpr int H = NV * 128;
-  __shared__ float red[8][128];
+  constexpr int NK = NV / 2;
+  __shared__ float red[4][256];
+  __shared__ float rowsum[4][2][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 ag[NV], ab[NV];
+  const int pair = warp >> 1, half = warp & 1;
+  const int l64 = half * 32 + lane;
+  float4 ag[NK], ab[NK], ac[NK];
 #pragma unroll
-  for (int k = 0; k < NV; ++k) { ag[k] = make_float4(0, 0, 0, 0); ab[k] = make_float4(0, 0, 0, 0); }
-  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    const float rm = rowmask ? (rowmask[row] ? 1.0f : 0.0f) : 1.0f;
-    const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * H);
-    const float4* dr = reinterpret_cast<const float4*>(dy + (long long)row * H);
-    float4 g[NV], xh[NV];
+  for (int k = 0; k < NK; ++k) {
+    ag[k] = make_float4(0, 0, 0, 0); ab[k] = make_float4(0, 0, 0, 0); ac[k] = make_float4(0, 0, 0, 0);
+  }
+  const int row_iters = (M + gridDim.x * 4 - 1) / (gridDim.x * 4);
+  for (int it = 0; it < row_iters; ++it) {
+    const int row = (it * gridDim.x + blockIdx.x) * 4 + pair;
+    const bool live = row < M;                       // both warps of a pair agree; barriers stay uniform
+    float mean = 0.f, rstd = 0.f, rm = 0.f;
+    const float4* xr = nullptr;
+    const float4* dr = nullptr;
     float s1 = 0.0f, s2 = 0.0f;
+    if (live) {
+      mean = mean_in[row]; rstd = rstd_in[row];
+      rm = rowmask ? (rowmask[row] ? 1.0f : 0.0f) : 1.0f;
+      xr = reinterpret_cast<const float4*>(x + (long long)row * H);
+      dr = reinterpret_cast<const float4*>(dy + (long long)row * H);
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int col = (lane + 32 * k) * 4;
-      const float4 xv = __ldg(xr + lane + 32 * k);
-      float4 d = __ldg(dr + lane + 32 * k);
+      for (int k = 0; k < NK; ++k) {
+        const int c4 = l64 + 64 * k, col = c4 * 4;
+        const float4 xv = __ldg(xr + c4);
+        float4 d = __ldg(dr + c4);
+        if (out_drop.thresh16) {
+          float f[4];
+          drop_factors4(out_drop, (uint32_t)row, col, f);
+          d.x *= f[0]; d.y *= f[1]; d.z *= f[2]; d.w *= f[3];
+        }
+        d.x *= rm; d.y *= rm; d.z *= rm; d.w *= rm;
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + col));
+        const float4 xh = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
+        ag[k].x += d.x * xh.x; ag[k].y += d.y * xh.y; ag[k].z += d.z * xh.z; ag[k].w += d.w * xh.w;
+        const float4 g = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        s1 += g.x + g.y + g.z + g.w;
+        s2 += g.x * xh.x + g.y * xh.y + g.z * xh.z + g.w * xh.w;
+      }
+      s1 = warp_sum(s1); s2 = warp_sum(s2);
+      if (lane == 0) { rowsum[pair][half][0] = s1; rowsum[pair][half][1] = s2; }
+    }
+    __syncthreads();
+    const float m1 = (rowsum[pair][0][0] + rowsum[pair][1][0]) * (1.0f / H);
+    const float m2 = (rowsum[pair][0][1] + rowsum[pair][1][1]) * (1.0f / H);
+    __syncthreads();
+    if (!live || (!dx32 && !dx16)) continue;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const int c4 = l64 + 64 * k, col = c4 * 4;
+      const float4 xv = __ldg(xr + c4);
+      float4 d = __ldg(dr + c4);
       if (out_drop.thresh16) {
         float f[4];
         drop_factors4(out_drop, (uint32_t)row, col, f);
@@ -126,19 +168,9 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
       }
       d.x *= rm; d.y *= rm; d.z *= rm; d.w *= rm;
       const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + col));
-      xh[k] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
-      ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
-      ag[k].x += d.x * xh[k].x; ag[k].y += d.y * xh[k].y; ag[k].z += d.z * xh[k].z; ag[k].w += d.w * xh[k].w;
-      g[k] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
-      s1 += g[k].x + g[k].y + g[k].z + g[k].w;
-      s2 += g[k].x * xh[k].x + g[k].y * xh[k].y + g[k].z * xh[k].z + g[k].w * xh[k].w;
-    }
-    const float m1 = warp_sum(s1) * (1.0f / H), m2 = warp_sum(s2) * (1.0f / H);
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int col = (lane + 32 * k) * 4;
-      float o[4] = {rstd * (g[k].x - m1 - xh[k].x * m2), rstd * (g[k].y - m1 - xh[k].y * m2),
-                    rstd * (g[k].z - m1 - xh[k].z * m2), rstd * (g[k].w - m1 - xh[k].w * m2)};
+      const float xh[4] = {(xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd};
+      float o[4] = {rstd * (d.x * gm.x - m1 - xh[0] * m2), rstd * (d.y * gm.y - m1 - xh[1] * m2),
+                    rstd * (d.z * gm.z - m1 - xh[2] * m2), rstd * (d.w * gm.w - m1 - xh[3] * m2)};
       if (dx32) *reinterpret_cast<float4*>(dx32 + (long long)row * H + col) = make_float4(o[0], o[1], o[2], o[3]);
       if (dx16) {
         if (in_drop.thresh16) {
@@ -147,30 +179,29 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
 #pragma unroll
           for (int e = 0; e < 4; ++e) o[e] *= f[e];
         }
-        *reinterpret_cast<uint2*>(dx16 + (long long)row * H + col) =
-            make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+        const uint2 q = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+        *reinterpret_cast<uint2*>(dx16 + (long long)row * H + col) = q;
+        if (dx16_colsum) {   // sums of the ROUNDED values, i.e. exactly colsum(dx16)
+          const float2 r0 = unpack_bf16(q.x), r1 = unpack_bf16(q.y);
+          ac[k].x += r0.x; ac[k].y += r0.y; ac[k].z += r1.x; ac[k].w += r1.y;
+        }
       }
     }
   }
-  if (!dgamma && !dbeta) return;
-  // cross-warp reduction of the per-lane column partials, 128 columns (one k) at a time
+  // cross-pair reduction of the per-lane column partials: 256 columns (one k of the 64-lane pair) at a time
 #pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    float* dst = pass == 0 ? dgamma : dbeta;
+  for (int pass = 0; pass < 3; ++pass) {
+    float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dx16_colsum);
     if (!dst) continue;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const float4 a = pass == 0 ? ag[k] : ab[k];
+    for (int k = 0; k < NK; ++k) {
+      const float4 a = pass == 0 ? ag[k] : (pass == 1 ? ab[k] : ac[k]);
       __syncthreads();
-      red[warp][lane * 4 + 0] = a.x; red[warp][lane * 4 + 1] = a.y;
-      red[warp][lane * 4 + 2] = a.z; red[warp][lane * 4 + 3] = a.w;
+      red[pair][l64 * 4 + 0] = a.x; red[pair][l64 * 4 + 1] = a.y;
+      red[pair][l64 * 4 + 2] = a.z; red[pair][l64 * 4 + 3] = a.w;
       __syncthreads();
-      if (threadIdx.x < 128) {
-        float t = 0.0f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
-        atomicAdd(dst + k * 128 + threadIdx.x, t);
-      }
+      atomicAdd(dst + k * 256 + threadIdx.x,
+                red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
     }
   }
 }
@@ -202,12 +233,13 @@ int layernorm_fwd(const float* x, int M, int H, const float* gamma, const float*
 
 int layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int M,
                   int H, const uint8_t* rowmask, const fb_dropout* out_drop, const fb_dropout* in_drop, float* dx32,
-                  void* dx16, float* dgamma, float* dbeta, cudaStream_t st) {
+                  void* dx16, float* dgamma, float* dbeta, float* dx16_colsum, cudaStream_t st) {
   FB_REQUIRE(dy && x && mean && rstd && gamma && M > 0 && H % 128 == 0, "fb_layernorm_bwd: bad args");
   const DropSpec od = drop_from(out_drop), id = drop_from(in_drop);
-  const int grid = std::max(1, std::min((M + 7) / 8, 2 * num_sms()));
+  const int grid = std::max(1, std::min((M + 3) / 4, 2 * num_sms()));
   FB_DISPATCH_NV(H, (ln_bwd_kernel<NV><<<grid, 256, 0, st>>>(dy, x, mean, rstd, gamma, M, rowmask, od, id, dx32,
-                                                            reinterpret_cast<__nv_bfloat16*>(dx16), dgamma, dbeta)));
+                                                            reinterpret_cast<__nv_bfloat16*>(dx16), dgamma, dbeta,
+                                                            dx16_colsum)));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -473,9 +505,9 @@ int fb_layernorm_fwd(const float* x, int M, int H, const float* gamma, const flo
 int fb_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                      int M, int H, const unsigned char* rowmask, const fb_dropout* out_drop,
                      const fb_dropout* in_drop, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
-                     void* stream) {
+                     float* dx_bf16_colsum, void* stream) {
   return layernorm_bwd(dy, x, mean, rstd, gamma, M, H, rowmask, out_drop, in_drop, dx_f32, dx_bf16, dgamma, dbeta,
-                       ST(stream));
+                       dx_bf16_colsum, ST(stream));
 }
 int fb_move_rows(const void* in, long long ld_in, int in_bf16, const long long* idx_in, const long long* idx_out,
                  int R, int ncols, void* out, long long ld_out, int out_bf16, void* stream) {
@@ -522,7 +554,7 @@ int fb_conv_col2im(const void* dcol_bf16, int B, int L, int H, float* dx, int ac
 }
 int fb_colsum_bf16(const void* x, long long ld, int M, int N, float* out, void* stream) {
   FB_REQUIRE(x && out && M > 0 && N > 0 && (ld % 2 == 0), "fb_colsum_bf16: bad args");
-  const int rows_per_cta = 256;
+  const int rows_per_cta = 64;
   dim3 grid(((N + 1) / 2 + 127) / 128, (M + rows_per_cta - 1) / rows_per_cta);
   colsum_kernel<<<grid, 128, 0, ST(stream)>>>((const __nv_bfloat16*)x, ld, M, N, rows_per_cta, out);
   count_launch();

@@ -462,11 +462,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           tmem_ld_32x32(taddr + c * 32, acc);
           tmem_ld_wait();
           float v[32];
-          epi_pre(p, row, col0, acc, v);
+          if (split == 0) {
+            epi_pre(p, row, col0, acc, v);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * p.alpha;
+          }
 #pragma unroll 1
           for (int pass = 0; pass < n_pass; ++pass) {
             const bool pre_only = (n_pass == 2 && pass == 0);
-            if (!pre_only) epi_post(p, row, col0, v);
+            if (!pre_only && split == 0) epi_post(p, row, col0, v);
             uint8_t* buf = buf0 + ((dbl && (nstore & 1)) ? 8192 : 0);
             ++nstore;
             if (leader) {                            // the store that last used this buffer has finished reading it
@@ -477,7 +482,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             fence_proxy_async_smem();
             named_bar_sync(1 + half, 128);
             if (leader) {
-              tma_store_2d(pre_only ? &map_pre : &map_d, buf, col0, mb * BM);
+              if (p.tma_store == 2 && !pre_only)
+                tma_reduce_add_2d(&map_d, buf, col0, mb * BM);   // D += tile (split-K / accumulate)
+              else
+                tma_store_2d(pre_only ? &map_pre : &map_d, buf, col0, mb * BM);
               tma_store_commit();
             }
           }
@@ -704,7 +712,8 @@ int gemm(const fb_gemm_args* a, cudaStream_t st) {
   const uint64_t dsz = p.d_f32 ? 4 : 2;
   const bool d_ok = ((uintptr_t)a->D % 16 == 0) && ((uint64_t)a->ldd * dsz % 16 == 0);
   const bool pre_ok = !a->D_pre || (((uintptr_t)a->D_pre % 16 == 0) && ((uint64_t)a->ld_pre * 2 % 16 == 0));
-  p.tma_store = (batch_total == 1 && p.split_k == 1 && !p.accumulate && d_ok && pre_ok && a->M >= 32) ? 1 : 0;
+  p.tma_store = (batch_total == 1 && d_ok && pre_ok && a->M >= 32) ? 1 : 0;
+  if (p.tma_store && (p.split_k > 1 || p.accumulate)) p.tma_store = (p.d_f32 && !a->D_pre) ? 2 : 0;
   if (p.tma_store) {
     if ((rc = make_tmap_store_2d(&md, a->D, p.d_f32, a->N, a->M, a->ldd))) return rc;
     if (a->D_pre && (rc = make_tmap_store_2d(&mpre, a->D_pre, 0, a->N, a->M, a->ld_pre))) return rc;

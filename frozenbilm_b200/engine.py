@@ -503,7 +503,8 @@ class DebertaEngine:
         gw16 = ws.get(f"bw.{name}.gw16", (T, H), BF16)
         lib.layernorm_bwd(dy32, rec["s"], rec["mean"], rec["rstd"], P[ln_prefix + "weight"],
                           in_drop=self.drop(cfg.hidden_dropout_prob, pass_id * 8 + site_hid), dx32=ds32, dx16=gw16,
-                          dgamma=self._g(ln_prefix + "weight"), dbeta=self._g(ln_prefix + "bias"))
+                          dgamma=self._g(ln_prefix + "weight"), dbeta=self._g(ln_prefix + "bias"),
+                          dx16_colsum=self._g(ad_prefix + "up.bias") if r else None)
         if r:
             u16, z16 = rec["u"], rec["z"]
             wu, wd = self.t16(ad_prefix + "up.weight"), self.t16(ad_prefix + "down.weight")
@@ -515,7 +516,6 @@ class DebertaEngine:
             sk = max(1, min(32, T // 512))
             lib.gemm(gw16, z16, self._g(ad_prefix + "up.weight"), a_mn_major=True, b_mn_major=True, split_k=sk,
                      accumulate=True)
-            lib.colsum_bf16(gw16, self._g(ad_prefix + "up.bias"))
             lib.gemm(dz16, u16, self._g(ad_prefix + "down.weight"), a_mn_major=True, b_mn_major=True, split_k=sk,
                      accumulate=True)
             lib.colsum_bf16(dz16, self._g(ad_prefix + "down.bias"))

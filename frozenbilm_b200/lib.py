@@ -103,7 +103,7 @@ def load() -> C.CDLL:
     vp, ll, i, f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
     dp = C.POINTER(Dropout)
     lib.fb_layernorm_fwd.argtypes = [vp, i, i, vp, vp, f, vp, dp, vp, vp, vp, vp, vp]
-    lib.fb_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, vp, dp, dp, vp, vp, vp, vp, vp]
+    lib.fb_layernorm_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, vp, dp, dp, vp, vp, vp, vp, vp, vp]
     lib.fb_move_rows.argtypes = [vp, ll, i, vp, vp, i, i, vp, ll, i, vp]
     lib.fb_gelu_bwd.argtypes = [vp, vp, i, i, vp, dp, vp, vp]
     lib.fb_add_rowbcast.argtypes = [vp, vp, i, i, i, vp, vp, vp]
@@ -269,12 +269,12 @@ def layernorm_fwd(x, gamma, beta, eps, *, rowmask=None, out_drop=None, y32=None,
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, *, rowmask=None, out_drop=None, in_drop=None, dx32=None, dx16=None,
-                  dgamma=None, dbeta=None):
+                  dgamma=None, dbeta=None, dx16_colsum=None):
     M, H = x.shape
     assert dy.dtype == torch.float32 and dy.is_contiguous() and x.is_contiguous()
     check(load().fb_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), M, H, _ptr(rowmask),
                                   _dp(out_drop), _dp(in_drop), _ptr(dx32), _ptr(dx16), _ptr(dgamma), _ptr(dbeta),
-                                  stream_ptr()), "fb_layernorm_bwd")
+                                  _ptr(dx16_colsum), stream_ptr()), "fb_layernorm_bwd")
 
 
 def move_rows(src, dst, *, idx_in=None, idx_out=None, R=None, ncols=None):

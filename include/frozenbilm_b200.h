@@ -142,11 +142,12 @@ int fb_layernorm_fwd(const float* x, int M, int H, const float* gamma, const flo
                      const unsigned char* rowmask, const fb_dropout* out_drop, float* y_f32, void* y_bf16,
                      float* mean, float* rstd, void* stream);
 /* Backward of the above (autograd in the reference).  dx_f32: gradient of the LN input; dx_bf16: the same with
- * the upstream hidden dropout (in_drop) backward applied, ready as a GEMM operand; dgamma/dbeta ACCUMULATE. */
+ * the upstream hidden dropout (in_drop) backward applied, ready as a GEMM operand; dgamma/dbeta ACCUMULATE;
+ * dx_bf16_colsum (nullable, [H], accumulates) = column sums of dx_bf16 = the adapter up-projection bias gradient. */
 int fb_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                      int M, int H, const unsigned char* rowmask, const fb_dropout* out_drop,
                      const fb_dropout* in_drop, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
-                     void* stream);
+                     float* dx_bf16_colsum, void* stream);
 /* out[idx_out[r],:] = in[idx_in[r],:] with fp32<->bf16 conversion (null index array = identity, <0 skips):
  * word_embeddings lookup (deberta.py:1013) and the labelled-position gather/scatter of the MLM head. */
 int fb_move_rows(const void* in, long long ld_in, int in_bf16, const long long* idx_in, const long long* idx_out,
