@@ -151,6 +151,9 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", type=int, default=0, help="debug: override the layer count")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="profiling aid (ncu --profile-from-start off): warm up, bracket ONE resident step with "
+                         "cudaProfilerStart/Stop, print nothing, exit")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -233,6 +236,13 @@ def main():
     for i in range(args.warmup):
         step_resident(i)
     barrier()
+
+    if args.profile_step:
+        torch.cuda.profiler.start()
+        step_resident(args.warmup)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
 
     # ---- per-kernel roofline probe: the dominant kernel is the FFN up-projection GEMM
     #      (M = B*L tokens, N = 4H, K = H), timed live with CUDA events around each of its launches

@@ -1,0 +1,688 @@
+// Fused disentangled-attention backward for sm_100a (tcgen05 + TMA), head_dim = 64.
+//
+// Autograd of DisentangledSelfAttention.forward + disentangled_attention_bias + XSoftmax + XDropout
+// (reference model/deberta.py:717-947, 100-138, 171-194; torch autograd in the reference, main.py:81).
+// With  s[i,j] = scale * (Q_i.K_j + Q_i.PKrel[i-j] + K_j.PQrel[i-j]),  P = softmax(s),  Pd = dropout(P),
+// O = Pd.V  and the saved masked scores s2 (log2 domain) / row log-sum-exp of fb_attn_fwd:
+//
+//   dP   = dO . V^T                                   tcgen05.mma 128x128x64
+//   dS   = P * (dropout_bwd(dP) - rowsum(dO*O)) * scale      (registers, thread = query row)
+//   dV_J += Pd^T . dO_I        dQ_I += dS . K_J        dK_J += dS^T . Q_I         (128x64x128 each)
+//   dQ_I += Z1 . PKband        dK_J += Z2 . PQband                                 (128x64x256 each)
+//   dPKrel[band] += Z1^T . Q_I ,  dPQrel[band] += Z2^T . K_J                        (fb_attn_bwd_rel)
+//
+// Z1[a][c] = dS[a][b] and Z2[b][c] = dS[a][b] with c = a - b + 127 are the score gradients regrouped by
+// RELATIVE POSITION inside a (128-query, 128-key) tile pair: the band of 256 table rows such a pair
+// touches is contiguous (row = (i-j) + rel_off), so the positional terms become plain MMAs against
+// one TMA box of the per-relative-position tables (same convention as the forward kernel).
+//
+// fb_attn_bwd:      one CTA per (batch, head); all key blocks x query tiles; dQ (per query tile), dK and dV
+//                   (per key block) accumulate in TMEM, so there are no atomics and dQ/dK/dV are written
+//                   once, as bf16, straight into the operand buffer of the following dX GEMM.
+//                   dS is also written (bf16 [B,h,L,lp]) for fb_attn_bwd_rel.
+// fb_attn_bwd_rel:  gradients of the positional projections.  They are sums over batch AND over all tile
+//                   pairs of one diagonal, so a CTA owns (head, diagonal, slice of the batch), keeps the two
+//                   [256 x 64] fp32 band accumulators in TMEM across its whole slice and flushes once.
+#include <cstring>
+
+#include "../../include/frozenbilm_b200.h"
+#include "fb_common.cuh"
+
+namespace fb {
+
+static constexpr int AB_THREADS = 320;  // warps 0-7: two compute warpgroups (thread = tile row, warpgroup = 64-col
+                                        // half), warp 8 = TMA + MMA control, warp 9 = TMEM alloc
+// shared memory map (bytes); every operand tile is 1024-aligned (128B swizzle atoms)
+static constexpr uint32_t B_OFF_Q = 0, B_OFF_DO = 16384, B_OFF_K = 32768, B_OFF_V = 49152, B_OFF_PK = 65536,
+                          B_OFF_PQ = 98304, B_OFF_S0 = 131072,           // S0: 64 KB staging: [Pd | dS] or Z1 or Z2
+                          B_OFF_D = B_OFF_S0 + 65536,                    // D[512] fp32 = rowsum(dO * O)
+                          B_OFF_LSE = B_OFF_D + 2048,                    // lse[512] fp32
+                          B_OFF_BARS = B_OFF_LSE + 2048, AB_SMEM = B_OFF_BARS + 256 + 1024;
+// TMEM columns: dP tile, 4 dQ accumulators (L <= 512), dK, dV
+static constexpr uint32_t TB_DP = 0, TB_DQ = 128, TB_DK = 384, TB_DV = 448;
+
+struct AttnBwdFusedParams {
+  int B, L, h, nb, lp, rel_off;
+  const float* s2; const float* lse;
+  const __nv_bfloat16* ctx; const __nv_bfloat16* dctx; long long ldc;
+  __nv_bfloat16* dq; long long lddq;
+  __nv_bfloat16* dk; long long lddk;
+  __nv_bfloat16* dv; long long lddv;
+  __nv_bfloat16* ds_out;
+  float scale; DropSpec drop;
+};
+
+// 16-byte units of one 128-byte row of a 128B-swizzled K-major tile: unit u of row r lives at (u ^ (r & 7)).
+__device__ __forceinline__ uint32_t sw_off(int row, int col /* element index inside the 64-wide chunk */) {
+  return static_cast<uint32_t>(row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1)));
+}
+
+// zero the 64 KB staging region with all 256 compute threads (conflict-free 16-byte stores)
+__device__ __forceinline__ void zero_s0(uint8_t* s0, int ctid) {
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) *reinterpret_cast<uint4*>(s0 + k * 4096 + ctid * 16) = z;
+}
+
+// Z1[a][c] = dS[a][jj], c = a - jj + 127, for this thread's 64 keys jj = 64 g + e (dsb = packed bf16 pairs)
+__device__ __forceinline__ void scatter_z1(uint8_t* s0, int a, int g, const uint32_t (&dsb)[32]) {
+#pragma unroll
+  for (int e = 0; e < 64; ++e) {
+    const int c = a - (64 * g + e) + 127;
+    const uint16_t v = static_cast<uint16_t>((e & 1) ? (dsb[e >> 1] >> 16) : (dsb[e >> 1] & 0xFFFFu));
+    *reinterpret_cast<uint16_t*>(s0 + (c >> 6) * 16384 + sw_off(a, c & 63)) = v;
+  }
+}
+// Z2[jj][c] = dS[a][jj], same c
+__device__ __forceinline__ void scatter_z2(uint8_t* s0, int a, int g, const uint32_t (&dsb)[32]) {
+#pragma unroll
+  for (int e = 0; e < 64; ++e) {
+    const int jj = 64 * g + e;
+    const int c = a - jj + 127;
+    const uint16_t v = static_cast<uint16_t>((e & 1) ? (dsb[e >> 1] >> 16) : (dsb[e >> 1] & 0xFFFFu));
+    *reinterpret_cast<uint16_t*>(s0 + (c >> 6) * 16384 + sw_off(jj, c & 63)) = v;
+  }
+}
+
+// signal "operands staged in shared memory" from the 8 compute warps to the MMA thread
+__device__ __forceinline__ void compute_arrive(uint64_t* bar, int lane) {
+  fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+template <bool REL>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
+                const __grid_constant__ CUtensorMap map_pk, const __grid_constant__ CUtensorMap map_pq,
+                const __grid_constant__ AttnBwdFusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF_BARS);
+  uint64_t* bar_q = bars + 0;    // TMA: Q_I
+  uint64_t* bar_do = bars + 1;   // TMA: dO_I
+  uint64_t* bar_k = bars + 2;    // TMA: K_J
+  uint64_t* bar_v = bars + 3;    // TMA: V_J
+  uint64_t* bar_pk = bars + 4;   // TMA: PKband
+  uint64_t* bar_pq = bars + 5;   // TMA: PQband
+  uint64_t* bar_dp = bars + 6;   // MMA: dP complete
+  uint64_t* bar_rdyA = bars + 7;   // compute -> MMA: Pd | dS staged
+  uint64_t* bar_rdyB = bars + 8;   // compute -> MMA: Z1 staged
+  uint64_t* bar_rdyC = bars + 9;   // compute -> MMA: Z2 staged
+  uint64_t* bar_mmaA = bars + 10;  // MMA: dV, dQ, dK (content terms) complete
+  uint64_t* bar_mmaB = bars + 11;  // MMA: dQ += Z1.PK complete
+  uint64_t* bar_mmaC = bars + 12;  // MMA: dK += Z2.PQ complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  float* Dsm = reinterpret_cast<float*>(smem + B_OFF_D);
+  float* Lsm = reinterpret_cast<float*>(smem + B_OFF_LSE);
+  uint8_t* s0 = smem + B_OFF_S0;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hh = blockIdx.x, b = blockIdx.y;
+  const int nb = p.nb;            // number of 128-row tiles (queries and keys)
+  const int npairs = nb * nb;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_do);
+    if constexpr (REL) { tma_prefetch_desc(&map_pk); tma_prefetch_desc(&map_pq); }
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    mbar_init(bar_rdyA, 8); mbar_init(bar_rdyB, 8); mbar_init(bar_rdyC, 8);
+    mbar_init(bar_mmaA, 1); mbar_init(bar_mmaB, 1); mbar_init(bar_mmaC, 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (warp < 8) {
+    // D = rowsum(dO * O) and the row log-sum-exp of every query row of this (batch, head)
+    for (int r = threadIdx.x; r < nb * 128; r += 256) {
+      float d = 0.0f, l = INFINITY;
+      if (r < p.L) {
+        const uint4* o = reinterpret_cast<const uint4*>(p.ctx + ((long long)b * p.L + r) * p.ldc + hh * 64);
+        const uint4* g = reinterpret_cast<const uint4*>(p.dctx + ((long long)b * p.L + r) * p.ldc + hh * 64);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint4 ov = o[u], gv = g[u];
+          const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const float2 of = unpack_bf16(ow[w]), gf = unpack_bf16(gw[w]);
+            d = fmaf(of.x, gf.x, d);
+            d = fmaf(of.y, gf.y, d);
+          }
+        }
+        l = p.lse[((long long)b * p.h + hh) * p.L + r];
+      }
+      Dsm[r] = d;
+      Lsm[r] = l;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    if (elect_one_sync()) {
+      // ======================= TMA + MMA control thread =======================
+      constexpr uint32_t idesc_dp = make_idesc_bf16(128, 128, 0, 0);   // dP = dO . V^T       (A, B K-major)
+      constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);    // A K-major, B MN-major (dS.K, Z.band)
+      constexpr uint32_t idesc_mn = make_idesc_bf16(128, 64, 1, 1);    // A, B MN-major         (Pd^T.dO, dS^T.Q)
+      const uint32_t sQ = smem_u32(smem + B_OFF_Q), sDO = smem_u32(smem + B_OFF_DO), sK = smem_u32(smem + B_OFF_K),
+                     sV = smem_u32(smem + B_OFF_V), sPK = smem_u32(smem + B_OFF_PK), sPQ = smem_u32(smem + B_OFF_PQ),
+                     sS0 = smem_u32(s0);
+      auto load_qdo = [&](int I) {
+        mbar_arrive_expect_tx(bar_q, 16384);
+        tma_load_4d(smem + B_OFF_Q, &map_q, bar_q, 0, hh, I * 128, b);
+        mbar_arrive_expect_tx(bar_do, 16384);
+        tma_load_4d(smem + B_OFF_DO, &map_do, bar_do, 0, hh, I * 128, b);
+      };
+      auto load_kv = [&](int J) {
+        mbar_arrive_expect_tx(bar_k, 16384);
+        tma_load_4d(smem + B_OFF_K, &map_k, bar_k, 0, hh, J * 128, b);
+        mbar_arrive_expect_tx(bar_v, 16384);
+        tma_load_4d(smem + B_OFF_V, &map_v, bar_v, 0, hh, J * 128, b);
+      };
+      auto band_of = [&](int I, int J) { return (I - J) * 128 - 127 + p.rel_off; };
+      load_kv(0);
+      load_qdo(0);
+      if constexpr (REL) {
+        mbar_arrive_expect_tx(bar_pk, 32768);
+        tma_load_3d(smem + B_OFF_PK, &map_pk, bar_pk, 0, band_of(0, 0), hh);
+        mbar_arrive_expect_tx(bar_pq, 32768);
+        tma_load_3d(smem + B_OFF_PQ, &map_pq, bar_pq, 0, band_of(0, 0), hh);
+      }
+      for (int t = 0; t < npairs; ++t) {
+        const int J = t / nb, I = t - J * nb;
+        const uint32_t ph = t & 1, phJ = J & 1;
+        const bool has_next = (t + 1 < npairs);
+        const int Jn = (t + 1) / nb, In = (t + 1) - Jn * nb;
+        // ---- dP = dO_I . V_J^T
+        mbar_wait(bar_do, ph);
+        if (I == 0) mbar_wait(bar_v, phJ);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + TB_DP, make_smem_desc_sw128(sDO + k * 32, 16, 1024),
+                    make_smem_desc_sw128(sV + k * 32, 16, 1024), idesc_dp, k > 0);
+        umma_commit(bar_dp);
+        // ---- content terms: dV_J += Pd^T.dO_I ; dQ_I += dS.K_J ; dK_J += dS^T.Q_I
+        mbar_wait(bar_q, ph);
+        if (I == 0) mbar_wait(bar_k, phJ);
+        mbar_wait(bar_rdyA, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // A = Pd^T: MN-major (keys contiguous), two 64-key chunks 16 KB apart
+          umma_bf16(tmem + TB_DV, make_smem_desc_sw128(sS0 + k * 2048, 16384, 1024),
+                    make_smem_desc_sw128(sDO + k * 2048, 16, 1024), idesc_mn, (I > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // A = dS: K-major, keys [64 (k/4), +64) in the (k/4)-th 16 KB half
+          umma_bf16(tmem + TB_DQ + 64 * I, make_smem_desc_sw128(sS0 + 32768 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    make_smem_desc_sw128(sK + k * 2048, 16, 1024), idesc_kn, (J > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // A = dS^T: MN-major
+          umma_bf16(tmem + TB_DK, make_smem_desc_sw128(sS0 + 32768 + k * 2048, 16384, 1024),
+                    make_smem_desc_sw128(sQ + k * 2048, 16, 1024), idesc_mn, (I > 0 || k > 0) ? 1u : 0u);
+        umma_commit(bar_mmaA);
+        mbar_wait(bar_mmaA, ph);      // Q_I, dO_I (and K_J, V_J after the last query tile) are free again
+        if (has_next) {
+          load_qdo(In);
+          if (Jn != J) load_kv(Jn);
+        }
+        if constexpr (REL) {
+          // ---- c2p: dQ_I += Z1 . PKband   (K = 256 band rows: 4 chunks of 64, 4 k-steps each)
+          mbar_wait(bar_pk, ph);
+          mbar_wait(bar_rdyB, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            umma_bf16(tmem + TB_DQ + 64 * I, make_smem_desc_sw128(sS0 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                      make_smem_desc_sw128(sPK + k * 2048, 16, 1024), idesc_kn, 1u);
+          umma_commit(bar_mmaB);
+          mbar_wait(bar_mmaB, ph);
+          if (has_next) {
+            mbar_arrive_expect_tx(bar_pk, 32768);
+            tma_load_3d(smem + B_OFF_PK, &map_pk, bar_pk, 0, band_of(In, Jn), hh);
+          }
+          // ---- p2c: dK_J += Z2 . PQband
+          mbar_wait(bar_pq, ph);
+          mbar_wait(bar_rdyC, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            umma_bf16(tmem + TB_DK, make_smem_desc_sw128(sS0 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                      make_smem_desc_sw128(sPQ + k * 2048, 16, 1024), idesc_kn, 1u);
+          umma_commit(bar_mmaC);
+          mbar_wait(bar_mmaC, ph);
+          if (has_next) {
+            mbar_arrive_expect_tx(bar_pq, 32768);
+            tma_load_3d(smem + B_OFF_PQ, &map_pq, bar_pq, 0, band_of(In, Jn), hh);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 8) {
+    // ============ compute warpgroups: thread = tile row a, warpgroup g = columns [64g, 64g+64) ============
+    const int g = warp >> 2, wq = warp & 3;
+    const int a = wq * 32 + lane;
+    const int ctid = threadIdx.x;   // 0..255
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
+    uint64_t* bar_s0free = REL ? bar_mmaC : bar_mmaA;   // last MMA group that reads the staging region
+
+    for (int t = 0; t < npairs; ++t) {
+      const int J = t / nb, I = t - J * nb;
+      const uint32_t ph = t & 1;
+      const int i = I * 128 + a, j0 = J * 128;
+      const bool row_ok = i < p.L;
+      const long long srow = ((long long)b * p.h + hh) * p.L + i;
+      // ---- prefetch this thread's 64 saved scores (fp32, log2 domain; -inf where masked)
+      float4 sc[16];
+      if (row_ok) {
+        const float4* src = reinterpret_cast<const float4*>(p.s2 + srow * p.lp + j0 + 64 * g);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) sc[u] = __ldg(src + u);
+      }
+      const float lse = Lsm[i], D = Dsm[i];
+      const uint32_t rowid = static_cast<uint32_t>(srow);
+      if (t > 0) mbar_wait(bar_s0free, (t - 1) & 1);   // the previous pair's MMAs no longer read S0
+      mbar_wait(bar_dp, ph);
+      tc_fence_after();
+      uint32_t dsb[32];   // dS of this thread's 64 columns, bf16 pairs (kept for the Z1 / Z2 scatters)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        uint32_t v[32];
+        tmem_ld_32x32(lane_base + TB_DP + 64 * g + 32 * q, v);
+        tmem_ld_wait();
+        uint32_t pdb[16];
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+          uint32_t keep = 0xFFu;
+          if (p.drop.thresh16) keep = drop_keep8(p.drop, rowid, static_cast<uint32_t>(j0 + 64 * g + 32 * q + 8 * gg) >> 3);
+          float dsv[8], pdv[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int idx = 32 * q + 8 * gg + e;           // column inside this thread's 64
+            const float4 s4 = sc[idx >> 2];
+            const float s = (idx & 3) == 0 ? s4.x : (idx & 3) == 1 ? s4.y : (idx & 3) == 2 ? s4.z : s4.w;
+            const float pr = row_ok ? ex2_approx(s - lse) : 0.0f;   // s = -inf or lse = +inf -> 0
+            const float f = ((keep >> e) & 1u) ? p.drop.inv_keep : 0.0f;
+            pdv[e] = pr * f;
+            dsv[e] = (pr > 0.0f) ? pr * (__uint_as_float(v[8 * gg + e]) * f - D) * p.scale : 0.0f;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            dsb[16 * q + 4 * gg + e] = pack_bf16(dsv[2 * e], dsv[2 * e + 1]);
+            pdb[4 * gg + e] = pack_bf16(pdv[2 * e], pdv[2 * e + 1]);
+          }
+        }
+        // stage Pd and dS rows: K-major [row a][64 keys] chunks (one 16 KB chunk per warpgroup), 128B swizzle
+        uint8_t* prow = s0 + g * 16384 + a * 128;
+        uint8_t* drow = s0 + 32768 + g * 16384 + a * 128;
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+          const int unit = ((q * 4 + gg) ^ (a & 7)) << 4;
+          *reinterpret_cast<uint4*>(prow + unit) = make_uint4(pdb[4 * gg], pdb[4 * gg + 1], pdb[4 * gg + 2], pdb[4 * gg + 3]);
+          *reinterpret_cast<uint4*>(drow + unit) = make_uint4(dsb[16 * q + 4 * gg], dsb[16 * q + 4 * gg + 1],
+                                                               dsb[16 * q + 4 * gg + 2], dsb[16 * q + 4 * gg + 3]);
+        }
+      }
+      compute_arrive(bar_rdyA, lane);
+      if (p.ds_out != nullptr && row_ok) {
+        uint4* dst = reinterpret_cast<uint4*>(p.ds_out + srow * p.lp + j0 + 64 * g);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dst[u] = make_uint4(dsb[4 * u], dsb[4 * u + 1], dsb[4 * u + 2], dsb[4 * u + 3]);
+      }
+      if constexpr (REL) {
+        mbar_wait(bar_mmaA, ph);
+        zero_s0(s0, ctid);
+        named_bar_sync(1, 256);
+        scatter_z1(s0, a, g, dsb);
+        compute_arrive(bar_rdyB, lane);
+        mbar_wait(bar_mmaB, ph);
+        zero_s0(s0, ctid);
+        named_bar_sync(1, 256);
+        scatter_z2(s0, a, g, dsb);
+        compute_arrive(bar_rdyC, lane);
+      }
+      if (I == nb - 1) {
+        // ---- key block J is complete: dK_J, dV_J -> bf16 (thread = key row, warpgroup = 32-column half)
+        mbar_wait(bar_s0free, ph);
+        tc_fence_after();
+        const int j = j0 + a;
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          uint32_t v[32];
+          tmem_ld_32x32(lane_base + (w == 0 ? TB_DK : TB_DV) + 32 * g, v);
+          tmem_ld_wait();
+          if (j < p.L) {
+            __nv_bfloat16* base = (w == 0) ? p.dk + ((long long)b * p.L + j) * p.lddk : p.dv + ((long long)b * p.L + j) * p.lddv;
+            uint4* dst = reinterpret_cast<uint4*>(base + hh * 64 + 32 * g);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              dst[u] = make_uint4(pack_bf16(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
+                                  pack_bf16(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
+                                  pack_bf16(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
+                                  pack_bf16(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7])));
+          }
+        }
+        tc_fence_before();   // the next key block's first MMA overwrites dK / dV (ordered by bar_rdyA)
+      }
+    }
+    // ---- dQ of every query tile
+    mbar_wait(bar_s0free, (npairs - 1) & 1);
+    tc_fence_after();
+    for (int I = 0; I < nb; ++I) {
+      const int i = I * 128 + a;
+      uint32_t v[32];
+      tmem_ld_32x32(lane_base + TB_DQ + 64 * I + 32 * g, v);
+      tmem_ld_wait();
+      if (i < p.L) {
+        uint4* dst = reinterpret_cast<uint4*>(p.dq + ((long long)b * p.L + i) * p.lddq + hh * 64 + 32 * g);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          dst[u] = make_uint4(pack_bf16(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
+                              pack_bf16(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
+                              pack_bf16(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
+                              pack_bf16(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7])));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gradients of the per-relative-position tables:
+//   gpk[h, band0(d) + c, :] += sum_{b, pairs (I, J = I - d)} Z1^T . Q_I      (c2p, deberta.py:870-881)
+//   gpq[h, band0(d) + c, :] += sum_{b, pairs}               Z2^T . K_J      (p2c, deberta.py:884-918)
+// One CTA = (head, diagonal d, contiguous slice of the (pair, batch) units of that diagonal).
+// ---------------------------------------------------------------------------------------------
+static constexpr int AR_THREADS = 320;
+static constexpr uint32_t R_OFF_Q = 0, R_OFF_K = 16384, R_OFF_Z = 32768, R_OFF_BARS = R_OFF_Z + 65536,
+                          AR_SMEM = R_OFF_BARS + 128 + 1024;
+static constexpr uint32_t TR_PK = 0, TR_PQ = 128;   // two [256 x 64] accumulators, each two 128-lane halves of 64 columns
+
+struct AttnBwdRelParams {
+  int B, L, h, nb, lp, rel_rows, rel_off, units_per_cta;
+  const __nv_bfloat16* ds;
+  float* gpk; float* gpq;
+};
+
+__global__ void __launch_bounds__(AR_THREADS, 2)
+attn_bwd_rel_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ AttnBwdRelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + R_OFF_BARS);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_k = bars + 1;
+  uint64_t* bar_rdy1 = bars + 2;   // Z1 staged
+  uint64_t* bar_rdy2 = bars + 3;   // Z2 staged
+  uint64_t* bar_mma1 = bars + 4;
+  uint64_t* bar_mma2 = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint8_t* sz = smem + R_OFF_Z;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = p.nb;
+  const int hh = blockIdx.y;
+  // blockIdx.x -> (diagonal, slice): diagonals are laid out one after the other, each with ceil(units / units_per_cta) slices
+  int d = 0, slice = 0, nunits = 0;
+  {
+    int x = blockIdx.x;
+    for (int dd = -(nb - 1); dd <= nb - 1; ++dd) {
+      const int nu = (nb - (dd < 0 ? -dd : dd)) * p.B;
+      const int ns = (nu + p.units_per_cta - 1) / p.units_per_cta;
+      if (x < ns) { d = dd; slice = x; nunits = nu; break; }
+      x -= ns;
+    }
+  }
+  const int u_begin = slice * p.units_per_cta;
+  const int u_end = min(u_begin + p.units_per_cta, nunits);
+  const int I_first = d > 0 ? d : 0;
+  const int band0 = d * 128 - 127 + p.rel_off;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k);
+    mbar_init(bar_q, 1); mbar_init(bar_k, 1);
+    mbar_init(bar_rdy1, 8); mbar_init(bar_rdy2, 8);
+    mbar_init(bar_mma1, 1); mbar_init(bar_mma2, 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc_mn = make_idesc_bf16(128, 64, 1, 1);
+      const uint32_t sQ = smem_u32(smem + R_OFF_Q), sK = smem_u32(smem + R_OFF_K), sZ = smem_u32(sz);
+      auto load_qk = [&](int u) {
+        const int pair = u / p.B, bb = u - pair * p.B;
+        const int I = I_first + pair, J = I - d;
+        mbar_arrive_expect_tx(bar_q, 16384);
+        tma_load_4d(smem + R_OFF_Q, &map_q, bar_q, 0, hh, I * 128, bb);
+        mbar_arrive_expect_tx(bar_k, 16384);
+        tma_load_4d(smem + R_OFF_K, &map_k, bar_k, 0, hh, J * 128, bb);
+      };
+      if (u_begin < u_end) load_qk(u_begin);
+      for (int u = u_begin; u < u_end; ++u) {
+        const uint32_t ph = (u - u_begin) & 1;
+        const uint32_t acc = (u > u_begin) ? 1u : 0u;
+        // ---- gpk band += Z1^T . Q_I : M = band index c (two halves of 128 = 2 chunks of 64 each, 16 KB apart),
+        //      K = 128 query rows (16 rows = 2048 B per step)
+        mbar_wait(bar_q, ph);
+        mbar_wait(bar_rdy1, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem + TR_PK + 64 * mh, make_smem_desc_sw128(sZ + mh * 32768 + k * 2048, 16384, 1024),
+                      make_smem_desc_sw128(sQ + k * 2048, 16, 1024), idesc_mn, (acc || k > 0) ? 1u : 0u);
+        umma_commit(bar_mma1);
+        mbar_wait(bar_mma1, ph);
+        // ---- gpq band += Z2^T . K_J
+        mbar_wait(bar_k, ph);
+        mbar_wait(bar_rdy2, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem + TR_PQ + 64 * mh, make_smem_desc_sw128(sZ + mh * 32768 + k * 2048, 16384, 1024),
+                      make_smem_desc_sw128(sK + k * 2048, 16, 1024), idesc_mn, (acc || k > 0) ? 1u : 0u);
+        umma_commit(bar_mma2);
+        mbar_wait(bar_mma2, ph);
+        if (u + 1 < u_end) load_qk(u + 1);
+      }
+    }
+    __syncwarp();
+  } else if (warp < 8) {
+    const int g = warp >> 2, wq = warp & 3;
+    const int a = wq * 32 + lane;
+    const int ctid = threadIdx.x;
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
+    for (int u = u_begin; u < u_end; ++u) {
+      const uint32_t ph = (u - u_begin) & 1;
+      const int pair = u / p.B, bb = u - pair * p.B;
+      const int I = I_first + pair, J = I - d;
+      const int i = I * 128 + a;
+      uint32_t dsb[32];
+      if (i < p.L) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.ds + (((long long)bb * p.h + hh) * p.L + i) * p.lp + J * 128 + 64 * g);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint4 w = __ldg(src + q);
+          dsb[4 * q] = w.x; dsb[4 * q + 1] = w.y; dsb[4 * q + 2] = w.z; dsb[4 * q + 3] = w.w;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q) dsb[q] = 0u;
+      }
+      if (u > u_begin) mbar_wait(bar_mma2, ph ^ 1);   // previous unit's MMAs no longer read the staging region
+      zero_s0(sz, ctid);
+      named_bar_sync(1, 256);
+      scatter_z1(sz, a, g, dsb);
+      compute_arrive(bar_rdy1, lane);
+      mbar_wait(bar_mma1, ph);
+      zero_s0(sz, ctid);
+      named_bar_sync(1, 256);
+      scatter_z2(sz, a, g, dsb);
+      compute_arrive(bar_rdy2, lane);
+    }
+    // ---- flush the band accumulators (thread = band row c = 128 mh + a, warpgroup = 32-column half)
+    if (u_begin < u_end) {
+      mbar_wait(bar_mma2, (u_end - 1 - u_begin) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int w = 0; w < 4; ++w) {
+        const int mh = w & 1;
+        const int row = band0 + 128 * mh + a;
+        uint32_t v[32];
+        tmem_ld_32x32(lane_base + (w < 2 ? TR_PK : TR_PQ) + 64 * mh + 32 * g, v);
+        tmem_ld_wait();
+        if (row >= 0 && row < p.rel_rows) {
+          float* dst = (w < 2 ? p.gpk : p.gpq) + ((long long)hh * p.rel_rows + row) * 64 + 32 * g;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) atomicAdd(dst + e, __uint_as_float(v[e]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+static int make_rows_map(CUtensorMap* m, const void* ptr, long long ld, int B, int L, int h) {
+  const uint64_t dims[4] = {64, (uint64_t)h, (uint64_t)L, (uint64_t)B};
+  const uint64_t strides[3] = {64, (uint64_t)ld, (uint64_t)ld * L};
+  const uint32_t box[4] = {64, 1, 128, 1};
+  return make_tmap_bf16_nd(m, ptr, 4, dims, strides, box);
+}
+static int make_band_map(CUtensorMap* m, const void* ptr, int rel_rows, int h) {
+  const uint64_t dims[3] = {64, (uint64_t)rel_rows, (uint64_t)h};
+  const uint64_t strides[2] = {64, (uint64_t)rel_rows * 64};
+  const uint32_t box[3] = {64, 256, 1};
+  return make_tmap_bf16_nd(m, ptr, 3, dims, strides, box);
+}
+
+int attn_bwd(const fb_attn_bwd_args* a, cudaStream_t st) {
+  FB_REQUIRE(a && a->Q && a->K && a->V && a->dO && a->O && a->s2 && a->lse && a->dQ && a->dK && a->dV,
+             "fb_attn_bwd: null arg");
+  FB_REQUIRE(a->B > 0 && a->h > 0 && a->L > 0 && a->L <= 512, "fb_attn_bwd: need 0 < L <= 512 (got %d)", a->L);
+  const int lpad = (a->L + 127) / 128 * 128;
+  FB_REQUIRE(a->lp == lpad, "fb_attn_bwd: s2 row pitch must be L rounded up to 128 (got %d)", a->lp);
+  const bool rel = a->PKrel != nullptr;
+  FB_REQUIRE(!rel || a->PQrel, "fb_attn_bwd: PKrel and PQrel must be given together");
+  FB_REQUIRE(!rel || (a->rel_off >= lpad && a->rel_rows >= a->rel_off + lpad + 1),
+             "fb_attn_bwd: relative tables too small (rel_rows=%d rel_off=%d L=%d)", a->rel_rows, a->rel_off, a->L);
+  FB_REQUIRE(a->lddq % 8 == 0 && a->lddk % 8 == 0 && a->lddv % 8 == 0 && a->ldo % 8 == 0,
+             "fb_attn_bwd: row pitches must be multiples of 8 elements");
+  CUtensorMap mq, mk, mv, mdo, mpk, mpq;
+  int rc;
+  if ((rc = make_rows_map(&mq, a->Q, a->ldq, a->B, a->L, a->h))) return rc;
+  if ((rc = make_rows_map(&mk, a->K, a->ldk, a->B, a->L, a->h))) return rc;
+  if ((rc = make_rows_map(&mv, a->V, a->ldv, a->B, a->L, a->h))) return rc;
+  if ((rc = make_rows_map(&mdo, a->dO, a->ldo, a->B, a->L, a->h))) return rc;
+  if (rel) {
+    if ((rc = make_band_map(&mpk, a->PKrel, a->rel_rows, a->h))) return rc;
+    if ((rc = make_band_map(&mpq, a->PQrel, a->rel_rows, a->h))) return rc;
+  } else {
+    mpk = mk; mpq = mk;   // never dereferenced by the plain-attention instantiation
+  }
+  AttnBwdFusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = a->B; p.L = a->L; p.h = a->h; p.nb = lpad / 128; p.lp = lpad; p.rel_off = a->rel_off;
+  p.s2 = a->s2; p.lse = a->lse;
+  p.ctx = (const __nv_bfloat16*)a->O; p.dctx = (const __nv_bfloat16*)a->dO; p.ldc = a->ldo;
+  p.dq = (__nv_bfloat16*)a->dQ; p.lddq = a->lddq;
+  p.dk = (__nv_bfloat16*)a->dK; p.lddk = a->lddk;
+  p.dv = (__nv_bfloat16*)a->dV; p.lddv = a->lddv;
+  p.ds_out = (__nv_bfloat16*)a->ds_out;
+  p.scale = a->scale;
+  p.drop = make_drop(a->dropout_p, a->seed, a->offset);
+  static bool configured = false;
+  if (!configured) {
+    FB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    FB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+    configured = true;
+  }
+  dim3 grid(a->h, a->B);
+  if (rel)
+    attn_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, st>>>(mq, mk, mv, mdo, mpk, mpq, p);
+  else
+    attn_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, st>>>(mq, mk, mv, mdo, mpk, mpq, p);
+  count_launch();
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int attn_bwd_rel(const fb_attn_bwd_rel_args* a, cudaStream_t st) {
+  FB_REQUIRE(a && a->ds && a->Q && a->K && a->gpk && a->gpq, "fb_attn_bwd_rel: null arg");
+  FB_REQUIRE(a->B > 0 && a->h > 0 && a->L > 0 && a->L <= 512, "fb_attn_bwd_rel: need 0 < L <= 512 (got %d)", a->L);
+  const int lpad = (a->L + 127) / 128 * 128;
+  FB_REQUIRE(a->lp == lpad, "fb_attn_bwd_rel: ds row pitch must be L rounded up to 128 (got %d)", a->lp);
+  FB_REQUIRE(a->rel_off >= lpad && a->rel_rows >= a->rel_off + lpad + 1, "fb_attn_bwd_rel: relative tables too small");
+  CUtensorMap mq, mk;
+  int rc;
+  if ((rc = make_rows_map(&mq, a->Q, a->ldq, a->B, a->L, a->h))) return rc;
+  if ((rc = make_rows_map(&mk, a->K, a->ldk, a->B, a->L, a->h))) return rc;
+  AttnBwdRelParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = a->B; p.L = a->L; p.h = a->h; p.nb = lpad / 128; p.lp = lpad; p.rel_rows = a->rel_rows; p.rel_off = a->rel_off;
+  p.ds = (const __nv_bfloat16*)a->ds; p.gpk = a->gpk; p.gpq = a->gpq;
+  // slice the (pair, batch) units of every diagonal so that the grid is about two CTAs per SM
+  const int nb = p.nb;
+  const int total_units = nb * nb * a->B;
+  int upc = (total_units * a->h + 2 * num_sms() - 1) / (2 * num_sms());
+  if (upc < 1) upc = 1;
+  if (a->units_per_cta > 0) upc = a->units_per_cta;
+  p.units_per_cta = upc;
+  int nslices = 0;
+  for (int dd = -(nb - 1); dd <= nb - 1; ++dd) {
+    const int nu = (nb - (dd < 0 ? -dd : dd)) * a->B;
+    nslices += (nu + upc - 1) / upc;
+  }
+  FB_CHECK_CUDA(cudaMemsetAsync(a->gpk, 0, sizeof(float) * (size_t)a->h * a->rel_rows * 64, st));
+  FB_CHECK_CUDA(cudaMemsetAsync(a->gpq, 0, sizeof(float) * (size_t)a->h * a->rel_rows * 64, st));
+  static bool configured = false;
+  if (!configured) {
+    FB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_rel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM));
+    configured = true;
+  }
+  attn_bwd_rel_kernel<<<dim3(nslices, a->h), AR_THREADS, AR_SMEM, st>>>(mq, mk, p);
+  count_launch();
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace fb
+
+extern "C" {
+int fb_attn_bwd(const fb_attn_bwd_args* args, void* stream) {
+  return fb::attn_bwd(args, reinterpret_cast<cudaStream_t>(stream));
+}
+int fb_attn_bwd_rel(const fb_attn_bwd_rel_args* args, void* stream) {
+  return fb::attn_bwd_rel(args, reinterpret_cast<cudaStream_t>(stream));
+}
+}

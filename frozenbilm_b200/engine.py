@@ -15,6 +15,7 @@ Backward = hand-scheduled selective backward: dX through the frozen linears, dW 
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -76,6 +77,8 @@ class DebertaEngine:
         if cfg.head_dim != 64:
             raise NotImplementedError("the fused attention kernel is specialised for head_dim = 64")
         self.use_rel = True                                   # disentangled (c2p + p2c) attention
+        # attention backward: one fused kernel per pass (default) or the staged GEMM schedule (FB_ATTN_BWD=staged)
+        self.fused_attn_bwd = os.environ.get("FB_ATTN_BWD", "fused") != "staged"
         self.attn_scale = 1.0 / math.sqrt(3 * 64)             # deberta.py:769-777
         self.layer_prefix = "deberta.encoder.layer."
         if cfg.hidden_size % 128 != 0:
@@ -544,15 +547,55 @@ class DebertaEngine:
                                       SITE_HID1, slot)
         dctx16 = ws.get("bw.dctx16", (T, H), BF16)
         lib.gemm(du1, W[f"o.w.{i}"], dctx16, b_mn_major=True)
-        dqkv32 = self._attn_bwd(rec, dctx16)
         dqkv16 = ws.get(f"bw.dqkv16.{slot if emd else 0}", (T, 3 * H), BF16)
-        lib.cast_bf16(dqkv32, dqkv16)
+        if self.fused_attn_bwd:
+            self._attn_bwd_fused(rec, dctx16, dqkv16)
+        else:
+            dqkv32 = self._attn_bwd(rec, dctx16)
+            lib.cast_bf16(dqkv32, dqkv16)
         dxq = ws.get(f"bw.dxq.{slot}", (T, H), F32)
         if not emd:
             lib.gemm(dqkv16, W[f"qkv.w.{i}"], dxq, b_mn_major=True, resid=ds1)
             return dxq
         lib.gemm(dqkv16[:, :H], W[f"qkv.w.{i}"][:H], dxq, b_mn_major=True, resid=ds1)
         return dxq, dqkv16[:, H:]
+
+    def _attn_bwd_fused(self, rec, dctx16, dqkv16):
+        """Attention backward as one fused tcgen05 kernel per pass (fb_attn_bwd) + the band-gradient kernel of the
+        positional projections (fb_attn_bwd_rel); dQ | dK | dV land in ``dqkv16`` as bf16."""
+        cfg, W, ws = self.cfg, self.W, self.ws
+        B, L, F, Lt, T = self.dims
+        H, h = cfg.hidden_size, cfg.num_attention_heads
+        i, pass_id = rec["layer"], rec["pass_id"]
+        Q, K, V = rec["Q"], rec["K"], rec["V"]
+        lp = (L + 127) // 128 * 128
+        rel = self.use_rel
+        ds = ws.get("bw.ds", (B, h, L, lp), BF16) if rel else None
+        ad = self.drop(cfg.attention_probs_dropout_prob, pass_id * 8 + SITE_PROBS)
+        lib.attn_bwd(Q, K, V, rec["ctx"], dctx16, rec["s2"], rec["lse"], rec["pk"], rec["pq"],
+                     dqkv16[:, :H], dqkv16[:, H:2 * H], dqkv16[:, 2 * H:], ds_out=ds, B=B, L=L, h=h,
+                     scale=self.attn_scale, dropout_p=ad.p, seed=ad.seed, offset=ad.offset)
+        if not rel:
+            return
+        rel_rows, _ = lib.rel_table_geometry(L)
+        gpk = ws.get("bw.gpk", (h, rel_rows, 64), F32)
+        gpq = ws.get("bw.gpq", (h, rel_rows, 64), F32)
+        lib.attn_bwd_rel(ds, Q, K, gpk, gpq, B=B, L=L, h=h)
+        self._bwd_rel_tables(gpq, gpk, i, pass_id, L, h)
+
+    def _bwd_rel_tables(self, gpq, gpk, i, pass_id, L, h):
+        """d(per-relative-position tables) -> d(Linear_{q|k}(dropout(R))) -> accumulate dR (deberta.py:847-853)."""
+        cfg, W, ws = self.cfg, self.W, self.ws
+        H = cfg.hidden_size
+        S2 = 2 * cfg.position_buckets
+        dpqk32 = ws.get("bw.dpqk32", (S2, 2 * H), F32, zero=True)
+        lib.rel_to_bucket(gpq, gpk, self.bucket_of_rel, L, h, dpqk32)
+        dpqk16 = ws.get("bw.dpqk16", (S2, 2 * H), BF16)
+        lib.cast_bf16(dpqk32, dpqk16)
+        dRd32 = ws.get("bw.dRd32", (S2, H), F32)
+        lib.gemm(dpqk16, W[f"qkv.w.{i}"][:2 * H], dRd32, b_mn_major=True)
+        lib.dropout_apply(dRd32, self.drop(cfg.hidden_dropout_prob, pass_id * 8 + SITE_POS), out32=self._dR32,
+                          accumulate=True)
 
     def _attn_bwd(self, rec, dctx16):
         """Attention backward from GEMMs + the staging kernels of fb_attention.cu (see fb_attn_bwd_prep)."""
@@ -607,15 +650,7 @@ class DebertaEngine:
                  batch={"outer": (h, B * L * rel_rows, 64, rel_rows * 64)})
         lib.gemm(z2_2d, K, gpq.view(-1, 64), a_mn_major=True, b_mn_major=True, M=rel_rows, N=64, K=B * L,
                  batch={"outer": (h, B * L * rel_rows, 64, rel_rows * 64)})
-        S2 = 2 * cfg.position_buckets
-        dpqk32 = ws.get("bw.dpqk32", (S2, 2 * H), F32, zero=True)
-        lib.rel_to_bucket(gpq, gpk, self.bucket_of_rel, L, h, dpqk32)
-        dpqk16 = ws.get("bw.dpqk16", (S2, 2 * H), BF16)
-        lib.cast_bf16(dpqk32, dpqk16)
-        dRd32 = ws.get("bw.dRd32", (S2, H), F32)
-        lib.gemm(dpqk16, W[f"qkv.w.{i}"][:2 * H], dRd32, b_mn_major=True)
-        lib.dropout_apply(dRd32, self.drop(cfg.hidden_dropout_prob, pass_id * 8 + SITE_POS), out32=self._dR32,
-                          accumulate=True)
+        self._bwd_rel_tables(gpq, gpk, i, pass_id, L, h)
         return dqkv32
 
 

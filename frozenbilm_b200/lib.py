@@ -81,6 +81,35 @@ class AttnBwdPrepArgs(C.Structure):
     ]
 
 
+class AttnBwdArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("L", C.c_int), ("h", C.c_int), ("lp", C.c_int),
+        ("Q", C.c_void_p), ("ldq", C.c_longlong),
+        ("K", C.c_void_p), ("ldk", C.c_longlong),
+        ("V", C.c_void_p), ("ldv", C.c_longlong),
+        ("O", C.c_void_p), ("dO", C.c_void_p), ("ldo", C.c_longlong),
+        ("s2", C.c_void_p), ("lse", C.c_void_p),
+        ("PKrel", C.c_void_p), ("PQrel", C.c_void_p), ("rel_rows", C.c_int), ("rel_off", C.c_int),
+        ("dQ", C.c_void_p), ("lddq", C.c_longlong),
+        ("dK", C.c_void_p), ("lddk", C.c_longlong),
+        ("dV", C.c_void_p), ("lddv", C.c_longlong),
+        ("ds_out", C.c_void_p),
+        ("scale", C.c_float),
+        ("dropout_p", C.c_float), ("seed", C.c_ulonglong), ("offset", C.c_ulonglong),
+    ]
+
+
+class AttnBwdRelArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("L", C.c_int), ("h", C.c_int), ("lp", C.c_int), ("rel_rows", C.c_int), ("rel_off", C.c_int),
+        ("ds", C.c_void_p),
+        ("Q", C.c_void_p), ("ldq", C.c_longlong),
+        ("K", C.c_void_p), ("ldk", C.c_longlong),
+        ("gpk", C.c_void_p), ("gpq", C.c_void_p),
+        ("units_per_cta", C.c_int),
+    ]
+
+
 _lib = None
 
 
@@ -126,7 +155,7 @@ EXPORTS = [
     "fb_last_error", "fb_abi_version", "fb_launch_count", "fb_gemm", "fb_attn_fwd", "fb_build_rel_tables",
     "fb_layernorm_fwd", "fb_layernorm_bwd", "fb_move_rows", "fb_gelu_bwd", "fb_add_rowbcast", "fb_conv_im2col",
     "fb_conv_col2im", "fb_colsum_bf16", "fb_cross_entropy", "fb_dropout_apply", "fb_sumsq", "fb_adam_step",
-    "fb_cast_f32_bf16", "fb_attn_bwd_prep", "fb_rel_to_bucket",
+    "fb_cast_f32_bf16", "fb_attn_bwd_prep", "fb_rel_to_bucket", "fb_attn_bwd", "fb_attn_bwd_rel",
 ]
 
 
@@ -356,6 +385,44 @@ def attn_bwd_prep(s2, lse, dp, ctx, dctx, ds, pd, z1=None, z2=None, *, B, L, h, 
     a.scale = float(scale)
     a.dropout_p, a.seed, a.offset = float(dropout_p), int(seed), int(offset)
     check(load().fb_attn_bwd_prep(C.byref(a), stream_ptr()), "fb_attn_bwd_prep")
+
+
+def attn_bwd(Q, K, V, O, dO, s2, lse, PKrel, PQrel, dQ, dK, dV, ds_out=None, *, B, L, h, scale, dropout_p=0.0, seed=0,
+             offset=0):
+    """Fused attention backward (fb_attn_bwd).  Q/K/V/O/dO/dQ/dK/dV: bf16 2-D views [B*L, >= h*64]; s2: fp32
+    [B,h,L,lp]; lse: fp32 [B,h,L]; ds_out: optional bf16 [B,h,L,lp]."""
+    rel_rows, rel_off = rel_table_geometry(L)
+    assert s2.dtype == torch.float32 and lse.dtype == torch.float32
+    assert O.stride(0) == dO.stride(0)
+    a = AttnBwdArgs()
+    a.B, a.L, a.h, a.lp = B, L, h, s2.shape[-1]
+    a.Q, a.ldq = _ptr(Q), Q.stride(0)
+    a.K, a.ldk = _ptr(K), K.stride(0)
+    a.V, a.ldv = _ptr(V), V.stride(0)
+    a.O, a.dO, a.ldo = _ptr(O), _ptr(dO), O.stride(0)
+    a.s2, a.lse = _ptr(s2), _ptr(lse)
+    a.PKrel, a.PQrel, a.rel_rows, a.rel_off = _ptr(PKrel), _ptr(PQrel), rel_rows, rel_off
+    a.dQ, a.lddq = _ptr(dQ), dQ.stride(0)
+    a.dK, a.lddk = _ptr(dK), dK.stride(0)
+    a.dV, a.lddv = _ptr(dV), dV.stride(0)
+    a.ds_out = _ptr(ds_out)
+    a.scale = float(scale)
+    a.dropout_p, a.seed, a.offset = float(dropout_p), int(seed), int(offset)
+    check(load().fb_attn_bwd(C.byref(a), stream_ptr()), "fb_attn_bwd")
+
+
+def attn_bwd_rel(ds, Q, K, gpk, gpq, *, B, L, h, units_per_cta=0):
+    """gpk / gpq (fp32 [h, rel_rows, 64], overwritten) = gradients of the per-relative-position tables."""
+    rel_rows, rel_off = rel_table_geometry(L)
+    assert gpk.dtype == torch.float32 and gpq.dtype == torch.float32 and gpk.shape[1] == rel_rows
+    a = AttnBwdRelArgs()
+    a.B, a.L, a.h, a.lp, a.rel_rows, a.rel_off = B, L, h, ds.shape[-1], rel_rows, rel_off
+    a.ds = _ptr(ds)
+    a.Q, a.ldq = _ptr(Q), Q.stride(0)
+    a.K, a.ldk = _ptr(K), K.stride(0)
+    a.gpk, a.gpq = _ptr(gpk), _ptr(gpq)
+    a.units_per_cta = int(units_per_cta)
+    check(load().fb_attn_bwd_rel(C.byref(a), stream_ptr()), "fb_attn_bwd_rel")
 
 
 def rel_to_bucket(gpq, gpk, bucket_of_rel, L, h, out):

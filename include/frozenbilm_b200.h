@@ -125,6 +125,44 @@ int fb_attn_bwd_prep(const fb_attn_bwd_prep_args* args, void* stream);
 int fb_rel_to_bucket(const float* gpq, const float* gpk, int H, int h, const int* bucket_of_rel, int rel_rows,
                      int rel_off, int L, float* out, long long ldo, void* stream);
 
+/* Fused attention backward (same autograd, deberta.py:769-808 / 820-947 / XSoftmax :134-138 / XDropout :188-194),
+ * one tcgen05 kernel per layer pass instead of the staged schedule above: one CTA per (batch, head) recomputes
+ * P = exp2(s2 - lse) and dS tile by tile, keeps dQ / dK / dV in TMEM and writes them once as bf16:
+ *   dV = Pd^T.dO ; dQ = dS.K + Z1.PKrel ; dK = dS^T.Q + Z2.PQrel   (Z1/Z2 = dS regrouped by relative position
+ *   inside shared memory, never in HBM).  ds_out (optional, bf16 [B,h,L,lp]) feeds fb_attn_bwd_rel.
+ * PKrel = PQrel = NULL selects plain attention (BERT, bert.py:141-191).  O and dO share the row pitch ldo. */
+typedef struct fb_attn_bwd_args {
+  int B, L, h, lp;                           /* lp = L rounded up to 128 = row pitch of s2 / ds_out */
+  const void* Q; long long ldq;              /* bf16 [B*L, >= h*64] views, as in fb_attn_fwd */
+  const void* K; long long ldk;
+  const void* V; long long ldv;
+  const void* O; const void* dO; long long ldo;   /* bf16 context and its gradient */
+  const float* s2; const float* lse;         /* fp32 [B,h,L,lp] scores (log2 domain, -inf = masked), [B,h,L] */
+  const void* PKrel; const void* PQrel; int rel_rows, rel_off;
+  void* dQ; long long lddq;                  /* bf16 outputs */
+  void* dK; long long lddk;
+  void* dV; long long lddv;
+  void* ds_out;
+  float scale;
+  float dropout_p; unsigned long long seed; unsigned long long offset;   /* must equal the forward's */
+} fb_attn_bwd_args;
+int fb_attn_bwd(const fb_attn_bwd_args* args, void* stream);
+
+/* Gradients of the per-relative-position tables (fp32 [h, rel_rows, 64], OVERWRITTEN):
+ *   gpk[h, (i-j)+rel_off] = sum_{b,i,j} dS[b,h,i,j] Q[b,h,i]   (c2p, deberta.py:870-881)
+ *   gpq[h, (i-j)+rel_off] = sum_{b,i,j} dS[b,h,i,j] K[b,h,j]   (p2c, deberta.py:884-918)
+ * One CTA per (head, tile diagonal, batch slice) accumulates its 256-row band in TMEM and flushes once.
+ * units_per_cta = 0 picks about two CTAs per SM. */
+typedef struct fb_attn_bwd_rel_args {
+  int B, L, h, lp, rel_rows, rel_off;
+  const void* ds;                            /* bf16 [B,h,L,lp] from fb_attn_bwd */
+  const void* Q; long long ldq;
+  const void* K; long long ldk;
+  float* gpk; float* gpq;
+  int units_per_cta;
+} fb_attn_bwd_rel_args;
+int fb_attn_bwd_rel(const fb_attn_bwd_rel_args* args, void* stream);
+
 /* Expands pqk = Linear_{q|k}(rel_emb) ([2S, 2H] bf16: PQ in cols [0,H), PK in [H,2H); deberta.py:847-853)
  * into the per-relative-position tables used above: out[hh][row] = pqk[bucket_of_rel[row - rel_off + 511]].
  * bucket_of_rel: int32 [1023] = clamp(bucket(rel) + S, 0, 2S-1) for rel in [-511, 511]
