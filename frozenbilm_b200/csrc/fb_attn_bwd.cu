@@ -30,8 +30,13 @@
 
 namespace fb {
 
-static constexpr int AB_THREADS = 320;  // warps 0-7: two compute warpgroups (thread = tile row, warpgroup = 64-col
-                                        // half), warp 8 = TMA + MMA control, warp 9 = TMEM alloc
+// Compute warps: NG warpgroups; thread = tile row a (TMEM lane), warpgroup g = columns [CW g, CW g + CW) of the
+// 128-wide tile.  The kernels are bound by instruction issue of these warps (integer address math of the
+// regrouping stores, dropout hash, exp2), so NG = 4 (16 warps, 4 per scheduler) instead of 2 doubles the
+// latency hiding; warp 4 NG = TMA + MMA control, warp 4 NG + 1 = TMEM alloc.
+static constexpr int NG = 4, CW = 128 / NG, NCT = 128 * NG;   // column groups, columns per thread, compute threads
+static_assert(NG == 4, "the epilogues use 16-column TMEM loads (64 / NG)");
+static constexpr int AB_THREADS = NCT + 64;
 // shared memory map (bytes); every operand tile is 1024-aligned (128B swizzle atoms)
 static constexpr uint32_t B_OFF_Q = 0, B_OFF_DO = 16384, B_OFF_K = 32768, B_OFF_V = 49152, B_OFF_PK = 65536,
                           B_OFF_PQ = 98304, B_OFF_S0 = 131072,           // S0: 64 KB staging: [Pd | dS] or Z1 or Z2
@@ -57,34 +62,42 @@ __device__ __forceinline__ uint32_t sw_off(int row, int col /* element index ins
   return static_cast<uint32_t>(row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1)));
 }
 
-// zero the 64 KB staging region with all 256 compute threads (conflict-free 16-byte stores)
+// zero the 64 KB staging region with all NT compute threads (conflict-free 16-byte stores)
+template <int NT>
 __device__ __forceinline__ void zero_s0(uint8_t* s0, int ctid) {
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-  for (int k = 0; k < 16; ++k) *reinterpret_cast<uint4*>(s0 + k * 4096 + ctid * 16) = z;
+  for (int k = 0; k < 65536 / (NT * 16); ++k) *reinterpret_cast<uint4*>(s0 + k * (NT * 16) + ctid * 16) = z;
 }
 
-// Z1[a][c] = dS[a][jj], c = a - jj + 127, for this thread's 64 keys jj = 64 g + e (dsb = packed bf16 pairs)
-__device__ __forceinline__ void scatter_z1(uint8_t* s0, int a, int g, const uint32_t (&dsb)[32]) {
+// Z1[a][c] = dS[a][jj], c = a - jj + 127, for this thread's W keys jj = j_first + e (dsb = packed bf16 pairs).
+// Byte offset of (row r, column c) in the four 16 KB K-major chunks:
+//   (c >> 6) * 16384 + r * 128 + (((c ^ (r << 3)) & 63) << 1)        (the XOR is the 128B swizzle)
+template <int W>
+__device__ __forceinline__ void scatter_z1(uint8_t* s0, int a, int j_first, const uint32_t (&dsb)[W / 2]) {
+  const int c0 = a - j_first + 127;
+  const uint32_t rowb = static_cast<uint32_t>(a) << 7, x = static_cast<uint32_t>(a & 7) << 3;
 #pragma unroll
-  for (int e = 0; e < 64; ++e) {
-    const int c = a - (64 * g + e) + 127;
+  for (int e = 0; e < W; ++e) {
+    const uint32_t c = static_cast<uint32_t>(c0 - e);
     const uint16_t v = static_cast<uint16_t>((e & 1) ? (dsb[e >> 1] >> 16) : (dsb[e >> 1] & 0xFFFFu));
-    *reinterpret_cast<uint16_t*>(s0 + (c >> 6) * 16384 + sw_off(a, c & 63)) = v;
+    *reinterpret_cast<uint16_t*>(s0 + ((c & 0xC0u) << 8) + rowb + (((c ^ x) & 63u) << 1)) = v;
   }
 }
-// Z2[jj][c] = dS[a][jj], same c
-__device__ __forceinline__ void scatter_z2(uint8_t* s0, int a, int g, const uint32_t (&dsb)[32]) {
+// Z2[jj][c] = dS[a][jj], same c (the row is the key: constant per unrolled element)
+template <int W>
+__device__ __forceinline__ void scatter_z2(uint8_t* s0, int a, int j_first, const uint32_t (&dsb)[W / 2]) {
+  const int c0 = a - j_first + 127;
 #pragma unroll
-  for (int e = 0; e < 64; ++e) {
-    const int jj = 64 * g + e;
-    const int c = a - jj + 127;
+  for (int e = 0; e < W; ++e) {
+    const uint32_t c = static_cast<uint32_t>(c0 - e);
+    const uint32_t jj = static_cast<uint32_t>(j_first + e);   // j_first is a multiple of 8: (jj & 7) == (e & 7)
     const uint16_t v = static_cast<uint16_t>((e & 1) ? (dsb[e >> 1] >> 16) : (dsb[e >> 1] & 0xFFFFu));
-    *reinterpret_cast<uint16_t*>(s0 + (c >> 6) * 16384 + sw_off(jj, c & 63)) = v;
+    *reinterpret_cast<uint16_t*>(s0 + ((c & 0xC0u) << 8) + (jj << 7) + (((c ^ ((e & 7u) << 3)) & 63u) << 1)) = v;
   }
 }
 
-// signal "operands staged in shared memory" from the 8 compute warps to the MMA thread
+// signal "operands staged in shared memory" from the compute warps to the MMA thread
 __device__ __forceinline__ void compute_arrive(uint64_t* bar, int lane) {
   fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
   tc_fence_before();
@@ -124,21 +137,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   const int nb = p.nb;            // number of 128-row tiles (queries and keys)
   const int npairs = nb * nb;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 4 * NG && lane == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_do);
     if constexpr (REL) { tma_prefetch_desc(&map_pk); tma_prefetch_desc(&map_pq); }
     for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
-    mbar_init(bar_rdyA, 8); mbar_init(bar_rdyB, 8); mbar_init(bar_rdyC, 8);
+    mbar_init(bar_rdyA, 4 * NG); mbar_init(bar_rdyB, 4 * NG); mbar_init(bar_rdyC, 4 * NG);
     mbar_init(bar_mmaA, 1); mbar_init(bar_mmaB, 1); mbar_init(bar_mmaC, 1);
     fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == 4 * NG + 1) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
-  if (warp < 8) {
+  if (warp < 4 * NG) {
     // D = rowsum(dO * O) and the row log-sum-exp of every query row of this (batch, head)
-    for (int r = threadIdx.x; r < nb * 128; r += 256) {
+    for (int r = threadIdx.x; r < nb * 128; r += NCT) {
       float d = 0.0f, l = INFINITY;
       if (r < p.L) {
         const uint4* o = reinterpret_cast<const uint4*>(p.ctx + ((long long)b * p.L + r) * p.ldc + hh * 64);
@@ -165,7 +178,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == 4 * NG) {
     if (elect_one_sync()) {
       // ======================= TMA + MMA control thread =======================
       constexpr uint32_t idesc_dp = make_idesc_bf16(128, 128, 0, 0);   // dP = dO . V^T       (A, B K-major)
@@ -265,13 +278,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp < 8) {
-    // ============ compute warpgroups: thread = tile row a, warpgroup g = columns [64g, 64g+64) ============
+  } else if (warp < 4 * NG) {
+    // ============ compute warpgroups: thread = tile row a, warpgroup g = columns [CW g, CW g + CW) ============
     const int g = warp >> 2, wq = warp & 3;
     const int a = wq * 32 + lane;
-    const int ctid = threadIdx.x;   // 0..255
+    const int ctid = threadIdx.x;   // 0 .. NCT-1
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
     uint64_t* bar_s0free = REL ? bar_mmaC : bar_mmaA;   // last MMA group that reads the staging region
+    constexpr int OC = 64 / NG;                         // output columns per thread in the dQ / dK / dV epilogues
 
     for (int t = 0; t < npairs; ++t) {
       const int J = t / nb, I = t - J * nb;
@@ -279,33 +293,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const int i = I * 128 + a, j0 = J * 128;
       const bool row_ok = i < p.L;
       const long long srow = ((long long)b * p.h + hh) * p.L + i;
-      // ---- prefetch this thread's 64 saved scores (fp32, log2 domain; -inf where masked)
-      float4 sc[16];
+      // ---- prefetch this thread's CW saved scores (fp32, log2 domain; -inf where masked)
+      float4 sc[CW / 4];
       if (row_ok) {
-        const float4* src = reinterpret_cast<const float4*>(p.s2 + srow * p.lp + j0 + 64 * g);
+        const float4* src = reinterpret_cast<const float4*>(p.s2 + srow * p.lp + j0 + CW * g);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) sc[u] = __ldg(src + u);
+        for (int u = 0; u < CW / 4; ++u) sc[u] = __ldg(src + u);
       }
       const float lse = Lsm[i], D = Dsm[i];
       const uint32_t rowid = static_cast<uint32_t>(srow);
       if (t > 0) mbar_wait(bar_s0free, (t - 1) & 1);   // the previous pair's MMAs no longer read S0
       mbar_wait(bar_dp, ph);
       tc_fence_after();
-      uint32_t dsb[32];   // dS of this thread's 64 columns, bf16 pairs (kept for the Z1 / Z2 scatters)
+      uint32_t dsb[CW / 2];   // dS of this thread's CW columns, bf16 pairs (kept for the Z1 / Z2 scatters)
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
+      for (int q = 0; q < CW / 32; ++q) {
         uint32_t v[32];
-        tmem_ld_32x32(lane_base + TB_DP + 64 * g + 32 * q, v);
+        tmem_ld_32x32(lane_base + TB_DP + CW * g + 32 * q, v);
         tmem_ld_wait();
         uint32_t pdb[16];
 #pragma unroll
         for (int gg = 0; gg < 4; ++gg) {
           uint32_t keep = 0xFFu;
-          if (p.drop.thresh16) keep = drop_keep8(p.drop, rowid, static_cast<uint32_t>(j0 + 64 * g + 32 * q + 8 * gg) >> 3);
+          if (p.drop.thresh16) keep = drop_keep8(p.drop, rowid, static_cast<uint32_t>(j0 + CW * g + 32 * q + 8 * gg) >> 3);
           float dsv[8], pdv[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const int idx = 32 * q + 8 * gg + e;           // column inside this thread's 64
+            const int idx = 32 * q + 8 * gg + e;           // column inside this thread's CW
             const float4 s4 = sc[idx >> 2];
             const float s = (idx & 3) == 0 ? s4.x : (idx & 3) == 1 ? s4.y : (idx & 3) == 2 ? s4.z : s4.w;
             const float pr = row_ok ? ex2_approx(s - lse) : 0.0f;   // s = -inf or lse = +inf -> 0
@@ -319,12 +333,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             pdb[4 * gg + e] = pack_bf16(pdv[2 * e], pdv[2 * e + 1]);
           }
         }
-        // stage Pd and dS rows: K-major [row a][64 keys] chunks (one 16 KB chunk per warpgroup), 128B swizzle
-        uint8_t* prow = s0 + g * 16384 + a * 128;
-        uint8_t* drow = s0 + 32768 + g * 16384 + a * 128;
+        // stage Pd and dS rows: K-major [row a][64 keys] chunks of 16 KB, 128B swizzle; this thread's 32 columns
+        // are the four 16-byte units (col0 >> 3) .. +3 of chunk (col0 >> 6)
+        const int col0 = CW * g + 32 * q;
+        uint8_t* prow = s0 + (col0 >> 6) * 16384 + a * 128;
+        uint8_t* drow = prow + 32768;
 #pragma unroll
         for (int gg = 0; gg < 4; ++gg) {
-          const int unit = ((q * 4 + gg) ^ (a & 7)) << 4;
+          const int unit = ((((col0 & 63) >> 3) + gg) ^ (a & 7)) << 4;
           *reinterpret_cast<uint4*>(prow + unit) = make_uint4(pdb[4 * gg], pdb[4 * gg + 1], pdb[4 * gg + 2], pdb[4 * gg + 3]);
           *reinterpret_cast<uint4*>(drow + unit) = make_uint4(dsb[16 * q + 4 * gg], dsb[16 * q + 4 * gg + 1],
                                                                dsb[16 * q + 4 * gg + 2], dsb[16 * q + 4 * gg + 3]);
@@ -332,37 +348,37 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
       compute_arrive(bar_rdyA, lane);
       if (p.ds_out != nullptr && row_ok) {
-        uint4* dst = reinterpret_cast<uint4*>(p.ds_out + srow * p.lp + j0 + 64 * g);
+        uint4* dst = reinterpret_cast<uint4*>(p.ds_out + srow * p.lp + j0 + CW * g);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) dst[u] = make_uint4(dsb[4 * u], dsb[4 * u + 1], dsb[4 * u + 2], dsb[4 * u + 3]);
+        for (int u = 0; u < CW / 8; ++u) dst[u] = make_uint4(dsb[4 * u], dsb[4 * u + 1], dsb[4 * u + 2], dsb[4 * u + 3]);
       }
       if constexpr (REL) {
         mbar_wait(bar_mmaA, ph);
-        zero_s0(s0, ctid);
-        named_bar_sync(1, 256);
-        scatter_z1(s0, a, g, dsb);
+        zero_s0<NCT>(s0, ctid);
+        named_bar_sync(1, NCT);
+        scatter_z1<CW>(s0, a, CW * g, dsb);
         compute_arrive(bar_rdyB, lane);
         mbar_wait(bar_mmaB, ph);
-        zero_s0(s0, ctid);
-        named_bar_sync(1, 256);
-        scatter_z2(s0, a, g, dsb);
+        zero_s0<NCT>(s0, ctid);
+        named_bar_sync(1, NCT);
+        scatter_z2<CW>(s0, a, CW * g, dsb);
         compute_arrive(bar_rdyC, lane);
       }
       if (I == nb - 1) {
-        // ---- key block J is complete: dK_J, dV_J -> bf16 (thread = key row, warpgroup = 32-column half)
+        // ---- key block J is complete: dK_J, dV_J -> bf16 (thread = key row, warpgroup = OC-column slice)
         mbar_wait(bar_s0free, ph);
         tc_fence_after();
         const int j = j0 + a;
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
-          uint32_t v[32];
-          tmem_ld_32x32(lane_base + (w == 0 ? TB_DK : TB_DV) + 32 * g, v);
+          uint32_t v[16];
+          tmem_ld_32x16(lane_base + (w == 0 ? TB_DK : TB_DV) + OC * g, v);
           tmem_ld_wait();
           if (j < p.L) {
             __nv_bfloat16* base = (w == 0) ? p.dk + ((long long)b * p.L + j) * p.lddk : p.dv + ((long long)b * p.L + j) * p.lddv;
-            uint4* dst = reinterpret_cast<uint4*>(base + hh * 64 + 32 * g);
+            uint4* dst = reinterpret_cast<uint4*>(base + hh * 64 + OC * g);
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < OC / 8; ++u)
               dst[u] = make_uint4(pack_bf16(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
                                   pack_bf16(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
                                   pack_bf16(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
@@ -377,13 +393,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     tc_fence_after();
     for (int I = 0; I < nb; ++I) {
       const int i = I * 128 + a;
-      uint32_t v[32];
-      tmem_ld_32x32(lane_base + TB_DQ + 64 * I + 32 * g, v);
+      uint32_t v[16];
+      tmem_ld_32x16(lane_base + TB_DQ + 64 * I + OC * g, v);
       tmem_ld_wait();
       if (i < p.L) {
-        uint4* dst = reinterpret_cast<uint4*>(p.dq + ((long long)b * p.L + i) * p.lddq + hh * 64 + 32 * g);
+        uint4* dst = reinterpret_cast<uint4*>(p.dq + ((long long)b * p.L + i) * p.lddq + hh * 64 + OC * g);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < OC / 8; ++u)
           dst[u] = make_uint4(pack_bf16(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
                               pack_bf16(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
                               pack_bf16(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
@@ -394,7 +410,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 4 * NG + 1) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -535,14 +551,14 @@ attn_bwd_rel_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int q = 0; q < 32; ++q) dsb[q] = 0u;
       }
       if (u > u_begin) mbar_wait(bar_mma2, ph ^ 1);   // previous unit's MMAs no longer read the staging region
-      zero_s0(sz, ctid);
+      zero_s0<256>(sz, ctid);
       named_bar_sync(1, 256);
-      scatter_z1(sz, a, g, dsb);
+      scatter_z1<64>(sz, a, 64 * g, dsb);
       compute_arrive(bar_rdy1, lane);
       mbar_wait(bar_mma1, ph);
-      zero_s0(sz, ctid);
+      zero_s0<256>(sz, ctid);
       named_bar_sync(1, 256);
-      scatter_z2(sz, a, g, dsb);
+      scatter_z2<64>(sz, a, 64 * g, dsb);
       compute_arrive(bar_rdy2, lane);
     }
     // ---- flush the band accumulators (thread = band row c = 128 mh + a, warpgroup = 32-column half)
@@ -651,10 +667,13 @@ int attn_bwd_rel(const fb_attn_bwd_rel_args* a, cudaStream_t st) {
   memset(&p, 0, sizeof(p));
   p.B = a->B; p.L = a->L; p.h = a->h; p.nb = lpad / 128; p.lp = lpad; p.rel_rows = a->rel_rows; p.rel_off = a->rel_off;
   p.ds = (const __nv_bfloat16*)a->ds; p.gpk = a->gpk; p.gpq = a->gpq;
-  // slice the (pair, batch) units of every diagonal so that the grid is about two CTAs per SM
+  // Slice the (pair, batch) units of every diagonal.  Two CTAs are resident per SM; slices of at most 8 units keep
+  // the tail short (the diagonals hold different numbers of units, so "one slice per CTA slot" leaves a second,
+  // nearly empty wave) while one flush of the band accumulators (128 KB of fp32 atomics) per 8 units stays cheap.
   const int nb = p.nb;
   const int total_units = nb * nb * a->B;
   int upc = (total_units * a->h + 2 * num_sms() - 1) / (2 * num_sms());
+  if (upc > 8) upc = 8;
   if (upc < 1) upc = 1;
   if (a->units_per_cta > 0) upc = a->units_per_cta;
   p.units_per_cta = upc;

@@ -110,6 +110,18 @@ class AttnBwdRelArgs(C.Structure):
     ]
 
 
+class UmmaProbeArgs(C.Structure):
+    _fields_ = [
+        ("a_image", C.c_void_p), ("a_bytes", C.c_int),
+        ("b_image", C.c_void_p), ("b_bytes", C.c_int),
+        ("n_mma", C.c_int), ("a_off", C.POINTER(C.c_int)), ("b_off", C.POINTER(C.c_int)),
+        ("a_desc", C.c_ulonglong), ("b_desc", C.c_ulonglong),
+        ("idesc", C.c_uint),
+        ("N", C.c_int),
+        ("out", C.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -156,6 +168,7 @@ EXPORTS = [
     "fb_layernorm_fwd", "fb_layernorm_bwd", "fb_move_rows", "fb_gelu_bwd", "fb_add_rowbcast", "fb_conv_im2col",
     "fb_conv_col2im", "fb_colsum_bf16", "fb_cross_entropy", "fb_dropout_apply", "fb_sumsq", "fb_adam_step",
     "fb_cast_f32_bf16", "fb_attn_bwd_prep", "fb_rel_to_bucket", "fb_attn_bwd", "fb_attn_bwd_rel",
+    "fb_umma_probe",
 ]
 
 
@@ -423,6 +436,23 @@ def attn_bwd_rel(ds, Q, K, gpk, gpq, *, B, L, h, units_per_cta=0):
     a.gpk, a.gpq = _ptr(gpk), _ptr(gpq)
     a.units_per_cta = int(units_per_cta)
     check(load().fb_attn_bwd_rel(C.byref(a), stream_ptr()), "fb_attn_bwd_rel")
+
+
+def umma_probe(a_image, b_image, a_off, b_off, a_desc, b_desc, idesc, N):
+    """Hardware test bench (fb_umma_probe): a_image / b_image are uint8 CUDA tensors (raw shared-memory images);
+    returns the fp32 [128, N] accumulator."""
+    out = torch.zeros(128, N, device=a_image.device, dtype=torch.float32)
+    n = len(a_off)
+    a = UmmaProbeArgs()
+    a.a_image, a.a_bytes = _ptr(a_image), a_image.numel()
+    a.b_image, a.b_bytes = _ptr(b_image), b_image.numel()
+    a.n_mma = n
+    ao, bo = (C.c_int * n)(*a_off), (C.c_int * n)(*b_off)
+    a.a_off, a.b_off = ao, bo
+    a.a_desc, a.b_desc, a.idesc, a.N = int(a_desc), int(b_desc), int(idesc), int(N)
+    a.out = _ptr(out)
+    check(load().fb_umma_probe(C.byref(a), stream_ptr()), "fb_umma_probe")
+    return out
 
 
 def rel_to_bucket(gpq, gpk, bucket_of_rel, L, h, out):

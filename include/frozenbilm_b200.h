@@ -217,6 +217,23 @@ int fb_adam_step(float* p, const float* g, float* m, float* v, long long n, floa
                  void* stream);
 int fb_cast_f32_bf16(const float* x, long long n, void* out, void* stream);
 
+
+/* Hardware test bench (tests/ and scripts/ only, not on the training path): runs n_mma tcgen05.mma instructions of
+ * one CTA on caller-supplied raw shared-memory images of A and B, with caller-supplied descriptor templates
+ * (a_desc / b_desc: every field except the start address) and per-instruction start offsets, and returns the TMEM
+ * accumulator as fp32 [128, N].  Used to pin operand-layout semantics (SWIZZLE_NONE strides, skewed SBO) on a B200
+ * before a kernel depends on them. */
+typedef struct fb_umma_probe_args {
+  const void* a_image; int a_bytes;          /* device pointers; sizes are multiples of 16, <= 128 KB / 64 KB */
+  const void* b_image; int b_bytes;
+  int n_mma; const int* a_off; const int* b_off;   /* host arrays [n_mma], byte offsets of the descriptor start */
+  unsigned long long a_desc, b_desc;
+  unsigned int idesc;
+  int N;
+  float* out;                                /* device fp32 [128, N] */
+} fb_umma_probe_args;
+int fb_umma_probe(const fb_umma_probe_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
