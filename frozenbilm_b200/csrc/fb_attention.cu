@@ -172,6 +172,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
     const uint32_t rowid = static_cast<uint32_t>((b * p.h + hh) * p.L + i);
     const bool do_drop = p.drop_thresh16 != 0;
+    const uint32_t rowkey = drop_row_key_raw(rowid, p.seed_lo, p.seed_hi, p.off_lo, p.off_hi);
     float m_run = -INFINITY, l_run = 0.0f;
     float o[64];
 #pragma unroll
@@ -308,10 +309,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (do_drop) {
 #pragma unroll
           for (int gg = 0; gg < 4; ++gg) {
-            const uint32_t keep = dropout_keep8(rowid, (j0 + c0 + 8 * gg) >> 3, p.drop_thresh16, p.seed_lo,
-                                                p.seed_hi, p.off_lo, p.off_hi);
+            float f[8];
+            drop_factors8(rowkey, static_cast<uint32_t>(j0 + c0 + 8 * gg) >> 3, p.drop_thresh16, p.inv_keep, f);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) pr[8 * gg + e] = ((keep >> e) & 1) ? pr[8 * gg + e] * p.inv_keep : 0.0f;
+            for (int e = 0; e < 8; ++e) pr[8 * gg + e] *= f[e];
           }
         }
         uint8_t* prow = smem + OFF_P + g * 16384 + a * 128;

@@ -55,7 +55,12 @@ struct AttnBwdFusedParams {
   __nv_bfloat16* dv; long long lddv;
   __nv_bfloat16* ds_out;
   float scale; DropSpec drop;
+  long long* dbg;   // optional [pairs][32] clock64 stamps of CTA (0,0): events 0-15 control thread, 16-31 compute warp 0
 };
+#define FB_STAMP(ev)                                                                         \
+  do {                                                                                       \
+    if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[t * 32 + (ev)] = clock64(); \
+  } while (0)
 
 // 16-byte units of one 128-byte row of a 128B-swizzled K-major tile: unit u of row r lives at (u ^ (r & 7)).
 __device__ __forceinline__ uint32_t sw_off(int row, int col /* element index inside the 64-wide chunk */) {
@@ -213,6 +218,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const uint32_t ph = t & 1, phJ = J & 1;
         const bool has_next = (t + 1 < npairs);
         const int Jn = (t + 1) / nb, In = (t + 1) - Jn * nb;
+        FB_STAMP(0);
         // ---- dP = dO_I . V_J^T
         mbar_wait(bar_do, ph);
         if (I == 0) mbar_wait(bar_v, phJ);
@@ -222,11 +228,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           umma_bf16(tmem + TB_DP, make_smem_desc_sw128(sDO + k * 32, 16, 1024),
                     make_smem_desc_sw128(sV + k * 32, 16, 1024), idesc_dp, k > 0);
         umma_commit(bar_dp);
+        FB_STAMP(1);
         // ---- content terms: dV_J += Pd^T.dO_I ; dQ_I += dS.K_J ; dK_J += dS^T.Q_I
         mbar_wait(bar_q, ph);
         if (I == 0) mbar_wait(bar_k, phJ);
         mbar_wait(bar_rdyA, ph);
         tc_fence_after();
+        FB_STAMP(2);
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // A = Pd^T: MN-major (keys contiguous), two 64-key chunks 16 KB apart
           umma_bf16(tmem + TB_DV, make_smem_desc_sw128(sS0 + k * 2048, 16384, 1024),
@@ -240,7 +248,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           umma_bf16(tmem + TB_DK, make_smem_desc_sw128(sS0 + 32768 + k * 2048, 16384, 1024),
                     make_smem_desc_sw128(sQ + k * 2048, 16, 1024), idesc_mn, (I > 0 || k > 0) ? 1u : 0u);
         umma_commit(bar_mmaA);
+        FB_STAMP(3);
         mbar_wait(bar_mmaA, ph);      // Q_I, dO_I (and K_J, V_J after the last query tile) are free again
+        FB_STAMP(4);
         if (has_next) {
           load_qdo(In);
           if (Jn != J) load_kv(Jn);
@@ -248,28 +258,36 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if constexpr (REL) {
           // ---- c2p: dQ_I += Z1 . PKband   (K = 256 band rows: 4 chunks of 64, 4 k-steps each)
           mbar_wait(bar_pk, ph);
+          FB_STAMP(5);
           mbar_wait(bar_rdyB, ph);
           tc_fence_after();
+          FB_STAMP(6);
 #pragma unroll
           for (int k = 0; k < 16; ++k)
             umma_bf16(tmem + TB_DQ + 64 * I, make_smem_desc_sw128(sS0 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
                       make_smem_desc_sw128(sPK + k * 2048, 16, 1024), idesc_kn, 1u);
           umma_commit(bar_mmaB);
+          FB_STAMP(7);
           mbar_wait(bar_mmaB, ph);
+          FB_STAMP(8);
           if (has_next) {
             mbar_arrive_expect_tx(bar_pk, 32768);
             tma_load_3d(smem + B_OFF_PK, &map_pk, bar_pk, 0, band_of(In, Jn), hh);
           }
           // ---- p2c: dK_J += Z2 . PQband
           mbar_wait(bar_pq, ph);
+          FB_STAMP(9);
           mbar_wait(bar_rdyC, ph);
           tc_fence_after();
+          FB_STAMP(10);
 #pragma unroll
           for (int k = 0; k < 16; ++k)
             umma_bf16(tmem + TB_DK, make_smem_desc_sw128(sS0 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
                       make_smem_desc_sw128(sPQ + k * 2048, 16, 1024), idesc_kn, 1u);
           umma_commit(bar_mmaC);
+          FB_STAMP(11);
           mbar_wait(bar_mmaC, ph);
+          FB_STAMP(12);
           if (has_next) {
             mbar_arrive_expect_tx(bar_pq, 32768);
             tma_load_3d(smem + B_OFF_PQ, &map_pq, bar_pq, 0, band_of(In, Jn), hh);
@@ -302,9 +320,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
       const float lse = Lsm[i], D = Dsm[i];
       const uint32_t rowid = static_cast<uint32_t>(srow);
+      const bool stamp = (threadIdx.x == 0);
+      if (stamp) FB_STAMP(16);
       if (t > 0) mbar_wait(bar_s0free, (t - 1) & 1);   // the previous pair's MMAs no longer read S0
+      if (stamp) FB_STAMP(17);
       mbar_wait(bar_dp, ph);
       tc_fence_after();
+      if (stamp) FB_STAMP(18);
       uint32_t dsb[CW / 2];   // dS of this thread's CW columns, bf16 pairs (kept for the Z1 / Z2 scatters)
 #pragma unroll
       for (int q = 0; q < CW / 32; ++q) {
@@ -346,6 +368,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                                                                dsb[16 * q + 4 * gg + 2], dsb[16 * q + 4 * gg + 3]);
         }
       }
+      if (stamp) FB_STAMP(19);
       compute_arrive(bar_rdyA, lane);
       if (p.ds_out != nullptr && row_ok) {
         uint4* dst = reinterpret_cast<uint4*>(p.ds_out + srow * p.lp + j0 + CW * g);
@@ -353,15 +376,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         for (int u = 0; u < CW / 8; ++u) dst[u] = make_uint4(dsb[4 * u], dsb[4 * u + 1], dsb[4 * u + 2], dsb[4 * u + 3]);
       }
       if constexpr (REL) {
+        if (stamp) FB_STAMP(20);
         mbar_wait(bar_mmaA, ph);
+        if (stamp) FB_STAMP(21);
         zero_s0<NCT>(s0, ctid);
+        if (stamp) FB_STAMP(22);
         named_bar_sync(1, NCT);
+        if (stamp) FB_STAMP(23);
         scatter_z1<CW>(s0, a, CW * g, dsb);
+        if (stamp) FB_STAMP(24);
         compute_arrive(bar_rdyB, lane);
         mbar_wait(bar_mmaB, ph);
+        if (stamp) FB_STAMP(25);
         zero_s0<NCT>(s0, ctid);
         named_bar_sync(1, NCT);
+        if (stamp) FB_STAMP(26);
         scatter_z2<CW>(s0, a, CW * g, dsb);
+        if (stamp) FB_STAMP(27);
         compute_arrive(bar_rdyC, lane);
       }
       if (I == nb - 1) {
@@ -387,6 +418,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         tc_fence_before();   // the next key block's first MMA overwrites dK / dV (ordered by bar_rdyA)
       }
+      if (stamp) FB_STAMP(28);
     }
     // ---- dQ of every query tile
     mbar_wait(bar_s0free, (npairs - 1) & 1);
@@ -602,6 +634,8 @@ static int make_band_map(CUtensorMap* m, const void* ptr, int rel_rows, int h) {
   return make_tmap_bf16_nd(m, ptr, 3, dims, strides, box);
 }
 
+static long long* g_attn_bwd_dbg = nullptr;   // set by fb_attn_bwd_set_debug (profiling aid, normally null)
+
 int attn_bwd(const fb_attn_bwd_args* a, cudaStream_t st) {
   FB_REQUIRE(a && a->Q && a->K && a->V && a->dO && a->O && a->s2 && a->lse && a->dQ && a->dK && a->dV,
              "fb_attn_bwd: null arg");
@@ -637,6 +671,7 @@ int attn_bwd(const fb_attn_bwd_args* a, cudaStream_t st) {
   p.ds_out = (__nv_bfloat16*)a->ds_out;
   p.scale = a->scale;
   p.drop = make_drop(a->dropout_p, a->seed, a->offset);
+  p.dbg = g_attn_bwd_dbg;
   static bool configured = false;
   if (!configured) {
     FB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
@@ -700,6 +735,10 @@ int attn_bwd_rel(const fb_attn_bwd_rel_args* a, cudaStream_t st) {
 extern "C" {
 int fb_attn_bwd(const fb_attn_bwd_args* args, void* stream) {
   return fb::attn_bwd(args, reinterpret_cast<cudaStream_t>(stream));
+}
+int fb_attn_bwd_set_debug(long long* stamps) {
+  fb::g_attn_bwd_dbg = stamps;
+  return 0;
 }
 int fb_attn_bwd_rel(const fb_attn_bwd_rel_args* args, void* stream) {
   return fb::attn_bwd_rel(args, reinterpret_cast<cudaStream_t>(stream));

@@ -343,30 +343,56 @@ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c
   return make_uint4(c0, c1, c2, c3);
 }
 
-// 8 Bernoulli(keep) decisions (bit e = keep element 8*group+e of row `rowid`), 16-bit resolution:
-// keep iff rnd16 >= thresh16 with thresh16 = round(p * 65536).  Counter-based: a 32-bit avalanche hash
-// (two multiply-xorshift rounds, "lowbias32" constants) of (seed, offset, row, group) expanded to four words.
-// Any (seed, offset, row, group) regenerates the same mask, so the backward never stores dropout masks; the
-// generator costs ~5 integer ops per element (Philox4x32-10 was ~12 and dominated the softmax epilogues).
+// Counter-based dropout RNG.  Element (row, col) is kept iff its 16-bit field >= thresh16 = round(p * 65536).
+// Any (seed, offset, row, col) regenerates the same decision, so the backward never stores dropout masks.
+//   rowkey = mix32(row * c + k0(seed, offset)) ^ k1          hoisted out of the column loops by the callers
+//   gh     = mix(rowkey ^ group * c')                        one strong 32-bit hash per 8 consecutive columns
+//   w_i    = gh * M_i ; w_i ^= w_i >> 16   (i = 0..3)        fields: element 2i = low half, 2i+1 = high half
+// ~2.5 integer instructions per element plus one compare + select (the first version spent five full
+// mix32 rounds per 8 elements and assembled a bit mask: ~10 per element, which showed up as the largest single
+// item of the softmax / dS epilogues).
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
   return x;
 }
+__device__ __forceinline__ uint32_t drop_row_key_raw(uint32_t rowid, uint32_t seed_lo, uint32_t seed_hi, uint32_t off_lo,
+                                                     uint32_t off_hi) {
+  const uint32_t k0 = seed_lo ^ (off_lo * 0x9E3779B1u) ^ (off_hi * 0x85EBCA77u);   // loop-invariant
+  const uint32_t k1 = (seed_hi ^ 0xC2B2AE3Du) + off_lo * 0x27D4EB2Fu;
+  return mix32(rowid * 0x9E3779B1u + k0) ^ k1;
+}
+__device__ __forceinline__ void drop_words4(uint32_t rowkey, uint32_t group, uint32_t (&w)[4]) {
+  uint32_t g = rowkey ^ (group * 0x85EBCA6Bu);
+  g *= 0x7FEB352Du; g ^= g >> 15; g *= 0x846CA68Bu; g ^= g >> 16;
+  w[0] = g * 0x9E3779B1u; w[1] = g * 0xC2B2AE3Du; w[2] = g * 0x27D4EB2Fu; w[3] = g * 0x165667B1u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w[i] ^= w[i] >> 16;
+}
+// f[e] = keep(element 8*group + e) ? on : 0
+__device__ __forceinline__ void drop_factors8(uint32_t rowkey, uint32_t group, uint32_t thresh16, float on, float (&f)[8]) {
+  uint32_t w[4];
+  drop_words4(rowkey, group, w);
+  const uint32_t th = thresh16 << 16;   // thresh16 <= 65535 for p < 1
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = ((w[i] << 16) >= th) ? on : 0.0f;
+    f[2 * i + 1] = (w[i] >= th) ? on : 0.0f;
+  }
+}
+// 8 decisions as a bit mask (bit e = keep element 8*group + e)
 __device__ __forceinline__ uint32_t dropout_keep8(uint32_t rowid, uint32_t group, uint32_t thresh16,
                                                   uint32_t seed_lo, uint32_t seed_hi, uint32_t off_lo,
                                                   uint32_t off_hi) {
-  const uint32_t k0 = seed_lo ^ (off_lo * 0x9E3779B1u) ^ (off_hi * 0x85EBCA77u);   // loop-invariant
-  const uint32_t k1 = (seed_hi ^ 0xC2B2AE3Du) + off_lo * 0x27D4EB2Fu;
-  const uint32_t a = mix32((rowid * 0x9E3779B1u) ^ (group * 0x85EBCA6Bu + k0)) ^ k1;
-  const uint32_t th2 = thresh16 * 0x00010001u;
-  // __vsetgeu2: per 16-bit half 1 if r >= th else 0
-  const uint32_t c0 = __vsetgeu2(mix32(a), th2);
-  const uint32_t c1 = __vsetgeu2(mix32(a + 0x9E3779B9u), th2);
-  const uint32_t c2 = __vsetgeu2(mix32(a + 0x3C6EF372u), th2);
-  const uint32_t c3 = __vsetgeu2(mix32(a + 0xDAA66D2Bu), th2);
-  // halves -> bits 0..7
-  return (c0 & 1u) | ((c0 >> 15) & 2u) | ((c1 & 1u) << 2) | ((c1 >> 13) & 8u) | ((c2 & 1u) << 4) |
-         ((c2 >> 11) & 32u) | ((c3 & 1u) << 6) | ((c3 >> 9) & 128u);
+  uint32_t w[4];
+  drop_words4(drop_row_key_raw(rowid, seed_lo, seed_hi, off_lo, off_hi), group, w);
+  const uint32_t th = thresh16 << 16;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bits |= (((w[i] << 16) >= th) ? 1u : 0u) << (2 * i);
+    bits |= ((w[i] >= th) ? 1u : 0u) << (2 * i + 1);
+  }
+  return bits;
 }
 
 // Host-side description of one dropout site (plain data, passed by value into kernels).
@@ -378,6 +404,7 @@ struct DropSpec {
 inline DropSpec make_drop(float p, unsigned long long seed, unsigned long long offset) {
   DropSpec d;
   d.thresh16 = (p > 0.0f) ? (uint32_t)(p * 65536.0f + 0.5f) : 0u;
+  if (d.thresh16 > 65535u) d.thresh16 = 65535u;
   d.inv_keep = (p > 0.0f) ? 1.0f / (1.0f - p) : 1.0f;
   d.seed_lo = (uint32_t)seed; d.seed_hi = (uint32_t)(seed >> 32);
   d.off_lo = (uint32_t)offset; d.off_hi = (uint32_t)(offset >> 32);
@@ -385,6 +412,9 @@ inline DropSpec make_drop(float p, unsigned long long seed, unsigned long long o
 }
 __device__ __forceinline__ uint32_t drop_keep8(const DropSpec& d, uint32_t rowid, uint32_t group) {
   return dropout_keep8(rowid, group, d.thresh16, d.seed_lo, d.seed_hi, d.off_lo, d.off_hi);
+}
+__device__ __forceinline__ uint32_t drop_row_key(const DropSpec& d, uint32_t rowid) {
+  return drop_row_key_raw(rowid, d.seed_lo, d.seed_hi, d.off_lo, d.off_hi);
 }
 
 }  // namespace fb

@@ -21,6 +21,7 @@ struct ProbeParams {
   uint32_t idesc;
   int N;
   float* out;
+  long long* cycles;   // optional [2]: clock64 from the first MMA issue to (all issued, all complete)
 };
 
 __global__ void __launch_bounds__(160, 1) umma_probe_kernel(const __grid_constant__ ProbeParams p) {
@@ -43,12 +44,17 @@ __global__ void __launch_bounds__(160, 1) umma_probe_kernel(const __grid_constan
   if (warp == 4) {
     if (elect_one_sync()) {
       const uint32_t sa = smem_u32(smem), sb = smem_u32(smem + PR_A_BYTES);
+      const long long c0 = clock64();
       for (int i = 0; i < p.n_mma; ++i) {
         const uint64_t ad = p.a_desc | static_cast<uint64_t>(((sa + p.a_off[i]) & 0x3FFFF) >> 4);
         const uint64_t bd = p.b_desc | static_cast<uint64_t>(((sb + p.b_off[i]) & 0x3FFFF) >> 4);
         umma_bf16(tmem, ad, bd, p.idesc, i > 0 ? 1u : 0u);
       }
       umma_commit(bar);
+      const long long c1 = clock64();
+      mbar_wait(bar, 0);
+      const long long c2 = clock64();
+      if (p.cycles) { p.cycles[0] = c1 - c0; p.cycles[1] = c2 - c0; }
     }
     __syncwarp();
   } else {
@@ -82,6 +88,7 @@ int umma_probe(const fb_umma_probe_args* a, cudaStream_t st) {
   p.n_mma = a->n_mma;
   for (int i = 0; i < a->n_mma; ++i) { p.a_off[i] = a->a_off[i]; p.b_off[i] = a->b_off[i]; }
   p.a_desc = a->a_desc; p.b_desc = a->b_desc; p.idesc = a->idesc; p.N = a->N; p.out = a->out;
+  p.cycles = a->cycles;
   static bool configured = false;
   if (!configured) {
     FB_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PR_SMEM));

@@ -119,6 +119,7 @@ class UmmaProbeArgs(C.Structure):
         ("idesc", C.c_uint),
         ("N", C.c_int),
         ("out", C.c_void_p),
+        ("cycles", C.c_void_p),
     ]
 
 
@@ -168,7 +169,7 @@ EXPORTS = [
     "fb_layernorm_fwd", "fb_layernorm_bwd", "fb_move_rows", "fb_gelu_bwd", "fb_add_rowbcast", "fb_conv_im2col",
     "fb_conv_col2im", "fb_colsum_bf16", "fb_cross_entropy", "fb_dropout_apply", "fb_sumsq", "fb_adam_step",
     "fb_cast_f32_bf16", "fb_attn_bwd_prep", "fb_rel_to_bucket", "fb_attn_bwd", "fb_attn_bwd_rel",
-    "fb_umma_probe",
+    "fb_umma_probe", "fb_attn_bwd_set_debug",
 ]
 
 
@@ -438,7 +439,7 @@ def attn_bwd_rel(ds, Q, K, gpk, gpq, *, B, L, h, units_per_cta=0):
     check(load().fb_attn_bwd_rel(C.byref(a), stream_ptr()), "fb_attn_bwd_rel")
 
 
-def umma_probe(a_image, b_image, a_off, b_off, a_desc, b_desc, idesc, N):
+def umma_probe(a_image, b_image, a_off, b_off, a_desc, b_desc, idesc, N, cycles=None):
     """Hardware test bench (fb_umma_probe): a_image / b_image are uint8 CUDA tensors (raw shared-memory images);
     returns the fp32 [128, N] accumulator."""
     out = torch.zeros(128, N, device=a_image.device, dtype=torch.float32)
@@ -451,6 +452,7 @@ def umma_probe(a_image, b_image, a_off, b_off, a_desc, b_desc, idesc, N):
     a.a_off, a.b_off = ao, bo
     a.a_desc, a.b_desc, a.idesc, a.N = int(a_desc), int(b_desc), int(idesc), int(N)
     a.out = _ptr(out)
+    a.cycles = _ptr(cycles)
     check(load().fb_umma_probe(C.byref(a), stream_ptr()), "fb_umma_probe")
     return out
 

@@ -147,6 +147,9 @@ typedef struct fb_attn_bwd_args {
   float dropout_p; unsigned long long seed; unsigned long long offset;   /* must equal the forward's */
 } fb_attn_bwd_args;
 int fb_attn_bwd(const fb_attn_bwd_args* args, void* stream);
+/* Profiling aid: when non-NULL (device int64 [pairs * 32]), CTA (0,0) of every following fb_attn_bwd launch records
+ * clock64() stamps of its phases (see FB_STAMP in fb_attn_bwd.cu).  NULL (the default) disables it. */
+int fb_attn_bwd_set_debug(long long* stamps);
 
 /* Gradients of the per-relative-position tables (fp32 [h, rel_rows, 64], OVERWRITTEN):
  *   gpk[h, (i-j)+rel_off] = sum_{b,i,j} dS[b,h,i,j] Q[b,h,i]   (c2p, deberta.py:870-881)
@@ -231,6 +234,7 @@ typedef struct fb_umma_probe_args {
   unsigned int idesc;
   int N;
   float* out;                                /* device fp32 [128, N] */
+  long long* cycles;                         /* optional device int64 [2]: SM cycles (all issued, all complete) */
 } fb_umma_probe_args;
 int fb_umma_probe(const fb_umma_probe_args* args, void* stream);
 
