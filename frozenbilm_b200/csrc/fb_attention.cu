@@ -387,7 +387,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 // where PQK = Linear_{q|k}(dropout(LayerNorm(rel_embeddings)))  [2S, 2H]  (deberta.py:847-853).
 __global__ void build_rel_tables_kernel(const __nv_bfloat16* __restrict__ pqk, long long ld, int H, int h,
                                         const int* __restrict__ bucket_of_rel, int rel_rows, int rel_off, int L,
-                                        __nv_bfloat16* __restrict__ out_pq, __nv_bfloat16* __restrict__ out_pk) {
+                                        __nv_bfloat16* __restrict__ out_pq, __nv_bfloat16* __restrict__ out_pk,
+                                        __nv_bfloat16* __restrict__ out_pk_rev) {
   const int row = blockIdx.x, hh = blockIdx.y, t = blockIdx.z;
   const int rel = row - rel_off;
   uint32_t val = 0;
@@ -397,6 +398,8 @@ __global__ void build_rel_tables_kernel(const __nv_bfloat16* __restrict__ pqk, l
   }
   __nv_bfloat16* out = (t == 0 ? out_pq : out_pk) + ((long long)hh * rel_rows + row) * 64;
   *reinterpret_cast<uint32_t*>(out + threadIdx.x * 2) = val;
+  if (t == 1 && out_pk_rev != nullptr)   // row-reversed copy of PKrel for the fused backward (fb_attn_bwd)
+    *reinterpret_cast<uint32_t*>(out_pk_rev + ((long long)hh * rel_rows + (rel_rows - 1 - row)) * 64 + threadIdx.x * 2) = val;
 }
 
 
@@ -561,6 +564,7 @@ int attn_fwd(const fb_attn_args* a, cudaStream_t st) {
   if (a->dropout_p > 0.0f) {
     FB_REQUIRE(a->dropout_p < 1.0f, "fb_attn_fwd: dropout_p must be < 1");
     p.drop_thresh16 = (uint32_t)(a->dropout_p * 65536.0f + 0.5f);
+    if (p.drop_thresh16 > 65535u) p.drop_thresh16 = 65535u;
     p.inv_keep = 1.0f / (1.0f - a->dropout_p);
   } else {
     p.drop_thresh16 = 0; p.inv_keep = 1.0f;
@@ -584,13 +588,14 @@ int attn_fwd(const fb_attn_args* a, cudaStream_t st) {
 }
 
 int build_rel_tables(const void* pqk, long long ld, int H, int h, const int* bucket_of_rel, int rel_rows,
-                     int rel_off, int L, void* out_pq, void* out_pk, cudaStream_t st) {
+                     int rel_off, int L, void* out_pq, void* out_pk, void* out_pk_rev, cudaStream_t st) {
   FB_REQUIRE(pqk && bucket_of_rel && out_pq && out_pk, "fb_build_rel_tables: null arg");
   FB_REQUIRE(H == h * 64, "fb_build_rel_tables: head_dim must be 64");
   dim3 grid(rel_rows, h, 2);
   build_rel_tables_kernel<<<grid, 32, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(pqk), ld, H, h, bucket_of_rel,
                                                rel_rows, rel_off, L, reinterpret_cast<__nv_bfloat16*>(out_pq),
-                                               reinterpret_cast<__nv_bfloat16*>(out_pk));
+                                               reinterpret_cast<__nv_bfloat16*>(out_pk),
+                                               reinterpret_cast<__nv_bfloat16*>(out_pk_rev));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -643,8 +648,8 @@ int fb_rel_to_bucket(const float* gpq, const float* gpk, int H, int h, const int
 }
 int fb_attn_fwd(const fb_attn_args* args, void* stream) { return fb::attn_fwd(args, reinterpret_cast<cudaStream_t>(stream)); }
 int fb_build_rel_tables(const void* pqk, long long ld, int H, int h, const int* bucket_of_rel, int rel_rows,
-                        int rel_off, int L, void* out_pq, void* out_pk, void* stream) {
-  return fb::build_rel_tables(pqk, ld, H, h, bucket_of_rel, rel_rows, rel_off, L, out_pq, out_pk,
+                        int rel_off, int L, void* out_pq, void* out_pk, void* out_pk_rev, void* stream) {
+  return fb::build_rel_tables(pqk, ld, H, h, bucket_of_rel, rel_rows, rel_off, L, out_pq, out_pk, out_pk_rev,
                               reinterpret_cast<cudaStream_t>(stream));
 }
 }

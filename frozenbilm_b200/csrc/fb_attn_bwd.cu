@@ -6,20 +6,36 @@
 // O = Pd.V  and the saved masked scores s2 (log2 domain) / row log-sum-exp of fb_attn_fwd:
 //
 //   dP   = dO . V^T                                   tcgen05.mma 128x128x64
-//   dS   = P * (dropout_bwd(dP) - rowsum(dO*O)) * scale      (registers, thread = query row)
-//   dV_J += Pd^T . dO_I        dQ_I += dS . K_J        dK_J += dS^T . Q_I         (128x64x128 each)
-//   dQ_I += Z1 . PKband        dK_J += Z2 . PQband                                 (128x64x256 each)
-//   dPKrel[band] += Z1^T . Q_I ,  dPQrel[band] += Z2^T . K_J                        (fb_attn_bwd_rel)
+//   dS'  = P * (dropout_bwd(dP) - rowsum(dO*O))       (registers, thread = query row; dS = scale * dS')
+//   dV_J += Pd^T . dO_I        dQ_I += dS' . K_J       dK_J += dS'^T . Q_I        (128x64x128 each)
+//   dQ_I += Z1 . PKrev-band    dK_J += Z2 . PQ-band                               (128x64x256 each)
+//   dPKrel[band] += Z1^T . Q_I ,  dPQrel[band] += Z2^T . K_J                       (fb_attn_bwd_rel)
+//   (scale is applied once, when the accumulators leave TMEM)
 //
-// Z1[a][c] = dS[a][b] and Z2[b][c] = dS[a][b] with c = a - b + 127 are the score gradients regrouped by
-// RELATIVE POSITION inside a (128-query, 128-key) tile pair: the band of 256 table rows such a pair
-// touches is contiguous (row = (i-j) + rel_off), so the positional terms become plain MMAs against
-// one TMA box of the per-relative-position tables (same convention as the forward kernel).
+// Z1 / Z2 are dS' regrouped by RELATIVE POSITION inside a (128-query a, 128-key b) tile pair:
+//   Z1[a][k] = dS'[a][b],  k = b - a + 127   (row = query;  PKrev-band[k] = PKrel row of relative position 127 - k)
+//   Z2[b][k] = dS'[a][b],  k = a - b + 127   (row = key;    PQ-band[k]    = PQrel row of relative position k - 127)
+// so that the positional terms are plain MMAs against one TMA box of a per-relative-position table (the band of
+// a tile pair is contiguous; PKrel is read through a row-reversed copy so that both Z's are "row r shifted right
+// by 127 - r").
+//
+// How the shift is made (the expensive part of a naive implementation: a scattered 2-byte store with a swizzled
+// address per element, plus re-zeroing 64 KB per tile pair):
+//   * 127 - r = 8 (15 - G) + (7 - rho) with G = r >> 3, rho = r & 7.  Z lives in shared memory in the SWIZZLE_NONE
+//     K-major core-matrix layout (8 rows x 16 bytes, K-adjacent core matrices LBO = 128 B apart).  Row group G is
+//     STORED as a 17-unit window (its 128 values shifted by the fine part 7 - rho, zero elsewhere) at group stride
+//     SP; the MMA descriptor is given SBO = SP + LBO, so the tensor core sees group G displaced by G more units:
+//     the coarse part 8 (15 - G) of the shift costs nothing.  (Semantics of SWIZZLE_NONE strides and of a skewed
+//     SBO, also for the MN-major view Z^T used by fb_attn_bwd_rel, are pinned on hardware by
+//     scripts/gpu_umma_probe.py through fb_umma_probe.)
+//   * the zero padding between windows is written once per CTA: every tile pair overwrites exactly the same data
+//     positions of every row (for Z1 and for Z2), so nothing is re-zeroed and no barrier is needed.
+//   * per element the store address is (one of 8 per-thread offsets) + immediate.
 //
 // fb_attn_bwd:      one CTA per (batch, head); all key blocks x query tiles; dQ (per query tile), dK and dV
 //                   (per key block) accumulate in TMEM, so there are no atomics and dQ/dK/dV are written
 //                   once, as bf16, straight into the operand buffer of the following dX GEMM.
-//                   dS is also written (bf16 [B,h,L,lp]) for fb_attn_bwd_rel.
+//                   dS' is also written (bf16 [B,h,L,lp]) for fb_attn_bwd_rel.
 // fb_attn_bwd_rel:  gradients of the positional projections.  They are sums over batch AND over all tile
 //                   pairs of one diagonal, so a CTA owns (head, diagonal, slice of the batch), keeps the two
 //                   [256 x 64] fp32 band accumulators in TMEM across its whole slice and flushes once.
@@ -30,24 +46,94 @@
 
 namespace fb {
 
+// ---- skewed SWIZZLE_NONE staging buffer for Z1 / Z2 (bytes) ----
+static constexpr uint32_t Z_LBO = 128;              // K-adjacent core matrices (8 k-elements each)
+static constexpr uint32_t Z_SP = 4000;              // storage stride of a row group: 31.25 units; not a multiple of
+                                                    // 128 so that the four row groups of a warp hit different banks
+static constexpr uint32_t Z_SBO = Z_SP + Z_LBO;     // group stride the tensor core is told (skew of one unit per group)
+static constexpr uint32_t Z_PRE = 15 * Z_LBO;       // zero units in front of group 0
+static constexpr uint32_t Z_BYTES = 66048;          // >= Z_PRE + 15 * Z_SP + 32 * Z_LBO = 66016
+
+__device__ __forceinline__ uint64_t make_smem_desc_none(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;   // layout type 0 = SWIZZLE_NONE
+}
+
+// Z1 rows are queries: this thread owns row a and W of its values, keys b = j_first + e (j_first % 8 == 0).
+// Window position of key b: y = b + 7 - rho.
+template <int W>
+__device__ __forceinline__ void build_z1(uint8_t* z, int a, int j_first, const uint32_t (&dsb)[W / 2]) {
+  const int G = a >> 3, rho = a & 7;
+  uint8_t* rowbase = z + Z_PRE + G * Z_SP + rho * 16 + (j_first >> 3) * Z_LBO;
+  uint8_t* off[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int t = 7 - rho + r;
+    off[r] = rowbase + (t >> 3) * Z_LBO + (t & 7) * 2;
+  }
+#pragma unroll
+  for (int e = 0; e < W; ++e) {
+    const uint32_t w = dsb[e >> 1];
+    *reinterpret_cast<uint16_t*>(off[e & 7] + (e >> 3) * Z_LBO) = static_cast<uint16_t>((e & 1) ? (w >> 16) : w);
+  }
+}
+// Z2 rows are keys: this thread (query a) contributes one value to each of the rows b = j_first + e, at window
+// position y = a + 7 - (b & 7).
+template <int W>
+__device__ __forceinline__ void build_z2(uint8_t* z, int a, int j_first, const uint32_t (&dsb)[W / 2]) {
+  uint8_t* base = z + Z_PRE + (j_first >> 3) * Z_SP;
+  uint8_t* off[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int y = a + 7 - r;
+    off[r] = base + r * 16 + (y >> 3) * Z_LBO + (y & 7) * 2;
+  }
+#pragma unroll
+  for (int e = 0; e < W; ++e) {
+    const uint32_t w = dsb[e >> 1];
+    *reinterpret_cast<uint16_t*>(off[e & 7] + (e >> 3) * Z_SP) = static_cast<uint16_t>((e & 1) ? (w >> 16) : w);
+  }
+}
+
+// signal "operands staged in shared memory" from the compute warps to the MMA thread
+__device__ __forceinline__ void compute_arrive(uint64_t* bar, int lane) {
+  fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+__device__ __forceinline__ uint4 pack8_scaled(const uint32_t* v, float sc) {
+  return make_uint4(pack_bf16(__uint_as_float(v[0]) * sc, __uint_as_float(v[1]) * sc),
+                    pack_bf16(__uint_as_float(v[2]) * sc, __uint_as_float(v[3]) * sc),
+                    pack_bf16(__uint_as_float(v[4]) * sc, __uint_as_float(v[5]) * sc),
+                    pack_bf16(__uint_as_float(v[6]) * sc, __uint_as_float(v[7]) * sc));
+}
+
 // Compute warps: NG warpgroups; thread = tile row a (TMEM lane), warpgroup g = columns [CW g, CW g + CW) of the
-// 128-wide tile.  The kernels are bound by instruction issue of these warps (integer address math of the
-// regrouping stores, dropout hash, exp2), so NG = 4 (16 warps, 4 per scheduler) instead of 2 doubles the
-// latency hiding; warp 4 NG = TMA + MMA control, warp 4 NG + 1 = TMEM alloc.
+// 128-wide tile; warp 4 NG = TMA + MMA control, warp 4 NG + 1 = TMEM alloc.
 static constexpr int NG = 4, CW = 128 / NG, NCT = 128 * NG;   // column groups, columns per thread, compute threads
 static_assert(NG == 4, "the epilogues use 16-column TMEM loads (64 / NG)");
 static constexpr int AB_THREADS = NCT + 64;
-// shared memory map (bytes); every operand tile is 1024-aligned (128B swizzle atoms)
-static constexpr uint32_t B_OFF_Q = 0, B_OFF_DO = 16384, B_OFF_K = 32768, B_OFF_V = 49152, B_OFF_PK = 65536,
-                          B_OFF_PQ = 98304, B_OFF_S0 = 131072,           // S0: 64 KB staging: [Pd | dS] or Z1 or Z2
-                          B_OFF_D = B_OFF_S0 + 65536,                    // D[512] fp32 = rowsum(dO * O)
-                          B_OFF_LSE = B_OFF_D + 2048,                    // lse[512] fp32
-                          B_OFF_BARS = B_OFF_LSE + 2048, AB_SMEM = B_OFF_BARS + 256 + 1024;
+// shared memory map (bytes); every swizzled operand tile is 1024-aligned (128B swizzle atoms)
+static constexpr uint32_t B_OFF_Q = 0, B_OFF_DO = 16384, B_OFF_K = 32768, B_OFF_V = 49152,
+                          B_OFF_PK = 65536,                              // PKrev band (32 KB)
+                          B_OFF_S0 = 98304,                              // [Pd | dS'] (64 KB); first 32 KB double as
+                                                                         // the PQ band once the content MMAs are done
+                          B_OFF_Z = B_OFF_S0 + 65536,                    // Z1 / Z2
+                          B_OFF_BARS = B_OFF_Z + Z_BYTES,
+                          B_OFF_I16 = B_OFF_BARS + 256,                  // 16 x 16 bf16 identity (512 B, SWIZZLE_NONE)
+                          AB_SMEM = B_OFF_I16 + 512 + 1024;
+static_assert(AB_SMEM <= 232448, "shared memory budget");
 // TMEM columns: dP tile, 4 dQ accumulators (L <= 512), dK, dV
 static constexpr uint32_t TB_DP = 0, TB_DQ = 128, TB_DK = 384, TB_DV = 448;
 
 struct AttnBwdFusedParams {
-  int B, L, h, nb, lp, rel_off;
+  int B, L, h, nb, lp, rel_off, rel_rows;
   const float* s2; const float* lse;
   const __nv_bfloat16* ctx; const __nv_bfloat16* dctx; long long ldc;
   __nv_bfloat16* dq; long long lddq;
@@ -62,54 +148,6 @@ struct AttnBwdFusedParams {
     if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[t * 32 + (ev)] = clock64(); \
   } while (0)
 
-// 16-byte units of one 128-byte row of a 128B-swizzled K-major tile: unit u of row r lives at (u ^ (r & 7)).
-__device__ __forceinline__ uint32_t sw_off(int row, int col /* element index inside the 64-wide chunk */) {
-  return static_cast<uint32_t>(row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1)));
-}
-
-// zero the 64 KB staging region with all NT compute threads (conflict-free 16-byte stores)
-template <int NT>
-__device__ __forceinline__ void zero_s0(uint8_t* s0, int ctid) {
-  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-  for (int k = 0; k < 65536 / (NT * 16); ++k) *reinterpret_cast<uint4*>(s0 + k * (NT * 16) + ctid * 16) = z;
-}
-
-// Z1[a][c] = dS[a][jj], c = a - jj + 127, for this thread's W keys jj = j_first + e (dsb = packed bf16 pairs).
-// Byte offset of (row r, column c) in the four 16 KB K-major chunks:
-//   (c >> 6) * 16384 + r * 128 + (((c ^ (r << 3)) & 63) << 1)        (the XOR is the 128B swizzle)
-template <int W>
-__device__ __forceinline__ void scatter_z1(uint8_t* s0, int a, int j_first, const uint32_t (&dsb)[W / 2]) {
-  const int c0 = a - j_first + 127;
-  const uint32_t rowb = static_cast<uint32_t>(a) << 7, x = static_cast<uint32_t>(a & 7) << 3;
-#pragma unroll
-  for (int e = 0; e < W; ++e) {
-    const uint32_t c = static_cast<uint32_t>(c0 - e);
-    const uint16_t v = static_cast<uint16_t>((e & 1) ? (dsb[e >> 1] >> 16) : (dsb[e >> 1] & 0xFFFFu));
-    *reinterpret_cast<uint16_t*>(s0 + ((c & 0xC0u) << 8) + rowb + (((c ^ x) & 63u) << 1)) = v;
-  }
-}
-// Z2[jj][c] = dS[a][jj], same c (the row is the key: constant per unrolled element)
-template <int W>
-__device__ __forceinline__ void scatter_z2(uint8_t* s0, int a, int j_first, const uint32_t (&dsb)[W / 2]) {
-  const int c0 = a - j_first + 127;
-#pragma unroll
-  for (int e = 0; e < W; ++e) {
-    const uint32_t c = static_cast<uint32_t>(c0 - e);
-    const uint32_t jj = static_cast<uint32_t>(j_first + e);   // j_first is a multiple of 8: (jj & 7) == (e & 7)
-    const uint16_t v = static_cast<uint16_t>((e & 1) ? (dsb[e >> 1] >> 16) : (dsb[e >> 1] & 0xFFFFu));
-    *reinterpret_cast<uint16_t*>(s0 + ((c & 0xC0u) << 8) + (jj << 7) + (((c ^ ((e & 7u) << 3)) & 63u) << 1)) = v;
-  }
-}
-
-// signal "operands staged in shared memory" from the compute warps to the MMA thread
-__device__ __forceinline__ void compute_arrive(uint64_t* bar, int lane) {
-  fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(bar);
-}
-
 template <bool REL>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -123,19 +161,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint64_t* bar_do = bars + 1;   // TMA: dO_I
   uint64_t* bar_k = bars + 2;    // TMA: K_J
   uint64_t* bar_v = bars + 3;    // TMA: V_J
-  uint64_t* bar_pk = bars + 4;   // TMA: PKband
-  uint64_t* bar_pq = bars + 5;   // TMA: PQband
+  uint64_t* bar_pk = bars + 4;   // TMA: PKrev band
+  uint64_t* bar_pq = bars + 5;   // TMA: PQ band
   uint64_t* bar_dp = bars + 6;   // MMA: dP complete
-  uint64_t* bar_rdyA = bars + 7;   // compute -> MMA: Pd | dS staged
+  uint64_t* bar_rdyA = bars + 7;   // compute -> MMA: Pd | dS' staged
   uint64_t* bar_rdyB = bars + 8;   // compute -> MMA: Z1 staged
   uint64_t* bar_rdyC = bars + 9;   // compute -> MMA: Z2 staged
   uint64_t* bar_mmaA = bars + 10;  // MMA: dV, dQ, dK (content terms) complete
-  uint64_t* bar_mmaB = bars + 11;  // MMA: dQ += Z1.PK complete
+  uint64_t* bar_mmaB = bars + 11;  // MMA: dQ += Z1.PKrev complete
   uint64_t* bar_mmaC = bars + 12;  // MMA: dK += Z2.PQ complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-  float* Dsm = reinterpret_cast<float*>(smem + B_OFF_D);
-  float* Lsm = reinterpret_cast<float*>(smem + B_OFF_LSE);
   uint8_t* s0 = smem + B_OFF_S0;
+  uint8_t* zb = smem + B_OFF_Z;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hh = blockIdx.x, b = blockIdx.y;
@@ -154,16 +191,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  // per-thread row statistics for the query rows I * 128 + a: D = rowsum(dO * O), lse
+  float Dr[4] = {0.f, 0.f, 0.f, 0.f}, Lr[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
   if (warp < 4 * NG) {
-    // D = rowsum(dO * O) and the row log-sum-exp of every query row of this (batch, head)
-    for (int r = threadIdx.x; r < nb * 128; r += NCT) {
-      float d = 0.0f, l = INFINITY;
-      if (r < p.L) {
+    if constexpr (REL) {
+      // zero the Z staging buffer once: the padding between the row-group windows is never written again
+      const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+      for (uint32_t o = threadIdx.x * 16; o < Z_BYTES; o += NCT * 16) *reinterpret_cast<uint4*>(zb + o) = z4;
+      if (threadIdx.x < 256) {
+        // I16[n][k] as a K-major SWIZZLE_NONE B operand: core matrices (n >> 3, k >> 3), LBO (K) = 128, SBO (N) = 256
+        const int n = threadIdx.x >> 4, k = threadIdx.x & 15;
+        *reinterpret_cast<uint16_t*>(smem + B_OFF_I16 + (n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) =
+            (n == k) ? static_cast<uint16_t>(0x3F80) : static_cast<uint16_t>(0);
+      }
+    }
+    const int a = (warp & 3) * 32 + lane;
+#pragma unroll
+    for (int I = 0; I < 4; ++I) {
+      const int r = I * 128 + a;
+      float d = 0.0f;
+      if (I < nb && r < p.L) {
         const uint4* o = reinterpret_cast<const uint4*>(p.ctx + ((long long)b * p.L + r) * p.ldc + hh * 64);
         const uint4* g = reinterpret_cast<const uint4*>(p.dctx + ((long long)b * p.L + r) * p.ldc + hh * 64);
-#pragma unroll
+#pragma unroll 1
         for (int u = 0; u < 8; ++u) {
-          const uint4 ov = o[u], gv = g[u];
+          const uint4 ov = __ldg(o + u), gv = __ldg(g + u);
           const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
@@ -172,10 +224,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             d = fmaf(of.y, gf.y, d);
           }
         }
-        l = p.lse[((long long)b * p.h + hh) * p.L + r];
+        Dr[I] = d;
+        Lr[I] = p.lse[((long long)b * p.h + hh) * p.L + r];
       }
-      Dsm[r] = d;
-      Lsm[r] = l;
     }
   }
   tc_fence_before();
@@ -190,8 +241,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);    // A K-major, B MN-major (dS.K, Z.band)
       constexpr uint32_t idesc_mn = make_idesc_bf16(128, 64, 1, 1);    // A, B MN-major         (Pd^T.dO, dS^T.Q)
       const uint32_t sQ = smem_u32(smem + B_OFF_Q), sDO = smem_u32(smem + B_OFF_DO), sK = smem_u32(smem + B_OFF_K),
-                     sV = smem_u32(smem + B_OFF_V), sPK = smem_u32(smem + B_OFF_PK), sPQ = smem_u32(smem + B_OFF_PQ),
-                     sS0 = smem_u32(s0);
+                     sV = smem_u32(smem + B_OFF_V), sPK = smem_u32(smem + B_OFF_PK), sS0 = smem_u32(s0),
+                     sZ = smem_u32(zb);
       auto load_qdo = [&](int I) {
         mbar_arrive_expect_tx(bar_q, 16384);
         tma_load_4d(smem + B_OFF_Q, &map_q, bar_q, 0, hh, I * 128, b);
@@ -204,14 +255,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         mbar_arrive_expect_tx(bar_v, 16384);
         tma_load_4d(smem + B_OFF_V, &map_v, bar_v, 0, hh, J * 128, b);
       };
-      auto band_of = [&](int I, int J) { return (I - J) * 128 - 127 + p.rel_off; };
+      // PQ band: table row of k = (i - j) + rel_off with i - j = (I - J) 128 + k - 127
+      auto pq_band = [&](int I, int J) { return (I - J) * 128 - 127 + p.rel_off; };
+      // PKrev band: reversed table row of k = rel_rows - 1 - ((I - J) 128 + 127 - k + rel_off)
+      auto pk_band = [&](int I, int J) { return p.rel_rows - 128 - p.rel_off - (I - J) * 128; };
       load_kv(0);
       load_qdo(0);
       if constexpr (REL) {
         mbar_arrive_expect_tx(bar_pk, 32768);
-        tma_load_3d(smem + B_OFF_PK, &map_pk, bar_pk, 0, band_of(0, 0), hh);
-        mbar_arrive_expect_tx(bar_pq, 32768);
-        tma_load_3d(smem + B_OFF_PQ, &map_pq, bar_pq, 0, band_of(0, 0), hh);
+        tma_load_3d(smem + B_OFF_PK, &map_pk, bar_pk, 0, pk_band(0, 0), hh);
       }
       for (int t = 0; t < npairs; ++t) {
         const int J = t / nb, I = t - J * nb;
@@ -229,7 +281,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     make_smem_desc_sw128(sV + k * 32, 16, 1024), idesc_dp, k > 0);
         umma_commit(bar_dp);
         FB_STAMP(1);
-        // ---- content terms: dV_J += Pd^T.dO_I ; dQ_I += dS.K_J ; dK_J += dS^T.Q_I
+        // ---- content terms: dV_J += Pd^T.dO_I ; dQ_I += dS'.K_J ; dK_J += dS'^T.Q_I
         mbar_wait(bar_q, ph);
         if (I == 0) mbar_wait(bar_k, phJ);
         mbar_wait(bar_rdyA, ph);
@@ -240,58 +292,66 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           umma_bf16(tmem + TB_DV, make_smem_desc_sw128(sS0 + k * 2048, 16384, 1024),
                     make_smem_desc_sw128(sDO + k * 2048, 16, 1024), idesc_mn, (I > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // A = dS: K-major, keys [64 (k/4), +64) in the (k/4)-th 16 KB half
+        for (int k = 0; k < 8; ++k)   // A = dS': K-major, keys [64 (k/4), +64) in the (k/4)-th 16 KB half
           umma_bf16(tmem + TB_DQ + 64 * I, make_smem_desc_sw128(sS0 + 32768 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
                     make_smem_desc_sw128(sK + k * 2048, 16, 1024), idesc_kn, (J > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // A = dS^T: MN-major
+        for (int k = 0; k < 8; ++k)   // A = dS'^T: MN-major
           umma_bf16(tmem + TB_DK, make_smem_desc_sw128(sS0 + 32768 + k * 2048, 16384, 1024),
                     make_smem_desc_sw128(sQ + k * 2048, 16, 1024), idesc_mn, (I > 0 || k > 0) ? 1u : 0u);
         umma_commit(bar_mmaA);
         FB_STAMP(3);
-        mbar_wait(bar_mmaA, ph);      // Q_I, dO_I (and K_J, V_J after the last query tile) are free again
-        FB_STAMP(4);
+        if constexpr (REL) {
+          // ---- dS'^T through the tensor core (exact: bf16 x 1.0): D[key][16 j + n] = sum_q dS'[16 j + q][key] I[q][n],
+          //      into the dP columns (already consumed); the compute threads read it back with lane = key for Z2
+          constexpr uint32_t idesc_t = make_idesc_bf16(128, 16, 1, 0);
+          const uint64_t idb = make_smem_desc_none(smem_u32(smem + B_OFF_I16), 128, 256);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            umma_bf16(tmem + TB_DP + 16 * j, make_smem_desc_sw128(sS0 + 32768 + j * 2048, 16384, 1024), idb, idesc_t, 0u);
+          // ---- c2p: dQ_I += Z1 . PKrev-band   (K = 256: 16 k-steps of two core matrices)
+          mbar_wait(bar_pk, ph);
+          mbar_wait(bar_rdyB, ph);
+          tc_fence_after();
+          FB_STAMP(4);
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            umma_bf16(tmem + TB_DQ + 64 * I, make_smem_desc_none(sZ + k * 2 * Z_LBO, Z_LBO, Z_SBO),
+                      make_smem_desc_sw128(sPK + k * 2048, 16, 1024), idesc_kn, 1u);
+          umma_commit(bar_mmaB);
+          FB_STAMP(5);
+        }
+        mbar_wait(bar_mmaA, ph);      // Q_I, dO_I, [Pd | dS'] (and K_J, V_J after the last query tile) are free
+        FB_STAMP(6);
+        if constexpr (REL) {
+          mbar_arrive_expect_tx(bar_pq, 32768);
+          tma_load_3d(s0, &map_pq, bar_pq, 0, pq_band(I, J), hh);
+        }
         if (has_next) {
           load_qdo(In);
           if (Jn != J) load_kv(Jn);
         }
         if constexpr (REL) {
-          // ---- c2p: dQ_I += Z1 . PKband   (K = 256 band rows: 4 chunks of 64, 4 k-steps each)
-          mbar_wait(bar_pk, ph);
-          FB_STAMP(5);
-          mbar_wait(bar_rdyB, ph);
-          tc_fence_after();
-          FB_STAMP(6);
-#pragma unroll
-          for (int k = 0; k < 16; ++k)
-            umma_bf16(tmem + TB_DQ + 64 * I, make_smem_desc_sw128(sS0 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                      make_smem_desc_sw128(sPK + k * 2048, 16, 1024), idesc_kn, 1u);
-          umma_commit(bar_mmaB);
+          mbar_wait(bar_mmaB, ph);    // the PKrev band and Z1 are free
           FB_STAMP(7);
-          mbar_wait(bar_mmaB, ph);
-          FB_STAMP(8);
           if (has_next) {
             mbar_arrive_expect_tx(bar_pk, 32768);
-            tma_load_3d(smem + B_OFF_PK, &map_pk, bar_pk, 0, band_of(In, Jn), hh);
+            tma_load_3d(smem + B_OFF_PK, &map_pk, bar_pk, 0, pk_band(In, Jn), hh);
           }
-          // ---- p2c: dK_J += Z2 . PQband
+          // ---- p2c: dK_J += Z2 . PQ-band
           mbar_wait(bar_pq, ph);
-          FB_STAMP(9);
+          FB_STAMP(8);
           mbar_wait(bar_rdyC, ph);
           tc_fence_after();
-          FB_STAMP(10);
+          FB_STAMP(9);
 #pragma unroll
           for (int k = 0; k < 16; ++k)
-            umma_bf16(tmem + TB_DK, make_smem_desc_sw128(sS0 + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                      make_smem_desc_sw128(sPQ + k * 2048, 16, 1024), idesc_kn, 1u);
+            umma_bf16(tmem + TB_DK, make_smem_desc_none(sZ + k * 2 * Z_LBO, Z_LBO, Z_SBO),
+                      make_smem_desc_sw128(sS0 + k * 2048, 16, 1024), idesc_kn, 1u);
           umma_commit(bar_mmaC);
-          FB_STAMP(11);
+          FB_STAMP(10);
           mbar_wait(bar_mmaC, ph);
-          FB_STAMP(12);
-          if (has_next) {
-            mbar_arrive_expect_tx(bar_pq, 32768);
-            tma_load_3d(smem + B_OFF_PQ, &map_pq, bar_pq, 0, band_of(In, Jn), hh);
-          }
+          FB_STAMP(11);
         }
       }
     }
@@ -300,10 +360,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // ============ compute warpgroups: thread = tile row a, warpgroup g = columns [CW g, CW g + CW) ============
     const int g = warp >> 2, wq = warp & 3;
     const int a = wq * 32 + lane;
-    const int ctid = threadIdx.x;   // 0 .. NCT-1
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
-    uint64_t* bar_s0free = REL ? bar_mmaC : bar_mmaA;   // last MMA group that reads the staging region
-    constexpr int OC = 64 / NG;                         // output columns per thread in the dQ / dK / dV epilogues
+    uint64_t* bar_last = REL ? bar_mmaC : bar_mmaA;   // last MMA group of a pair
+    constexpr int OC = 64 / NG;                       // output columns per thread in the dQ / dK / dV epilogues
+    const bool do_drop = p.drop.thresh16 != 0;
+
+    // This thread's CW saved scores of a pair (fp32, log2 domain; -inf where masked or padded).  HBM latency under
+    // this access pattern is several microseconds, so the segment of pair t+1 is hinted into L2 at the start of
+    // pair t and loaded into registers while the last MMA group of pair t runs.
+    float4 sc[CW / 4];
+    auto score_ptr = [&](int tt) -> const float4* {
+      const int Jt = tt / nb, It = tt - Jt * nb;
+      const int it = It * 128 + a;
+      if (tt >= npairs || it >= p.L) return nullptr;
+      return reinterpret_cast<const float4*>(p.s2 + (((long long)b * p.h + hh) * p.L + it) * p.lp + Jt * 128 + CW * g);
+    };
+    auto load_scores = [&](int tt) {
+      const float4* src = score_ptr(tt);
+      if (src != nullptr) {
+#pragma unroll
+        for (int u = 0; u < CW / 4; ++u) sc[u] = __ldg(src + u);
+      } else {
+#pragma unroll
+        for (int u = 0; u < CW / 4; ++u) sc[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+    };
+    load_scores(0);
 
     for (int t = 0; t < npairs; ++t) {
       const int J = t / nb, I = t - J * nb;
@@ -311,93 +393,108 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const int i = I * 128 + a, j0 = J * 128;
       const bool row_ok = i < p.L;
       const long long srow = ((long long)b * p.h + hh) * p.L + i;
-      // ---- prefetch this thread's CW saved scores (fp32, log2 domain; -inf where masked)
-      float4 sc[CW / 4];
-      if (row_ok) {
-        const float4* src = reinterpret_cast<const float4*>(p.s2 + srow * p.lp + j0 + CW * g);
-#pragma unroll
-        for (int u = 0; u < CW / 4; ++u) sc[u] = __ldg(src + u);
-      }
-      const float lse = Lsm[i], D = Dsm[i];
-      const uint32_t rowid = static_cast<uint32_t>(srow);
       const bool stamp = (threadIdx.x == 0);
       if (stamp) FB_STAMP(16);
-      if (t > 0) mbar_wait(bar_s0free, (t - 1) & 1);   // the previous pair's MMAs no longer read S0
-      if (stamp) FB_STAMP(17);
+      {
+        const float4* nxt = score_ptr(t + 1);
+        if (nxt != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+      }
+      float lse = Lr[0], D = Dr[0];
+#pragma unroll
+      for (int ii = 1; ii < 4; ++ii)
+        if (ii == I) { lse = Lr[ii]; D = Dr[ii]; }
+      const uint32_t rowkey = drop_row_key(p.drop, static_cast<uint32_t>(srow));
       mbar_wait(bar_dp, ph);
       tc_fence_after();
-      if (stamp) FB_STAMP(18);
-      uint32_t dsb[CW / 2];   // dS of this thread's CW columns, bf16 pairs (kept for the Z1 / Z2 scatters)
-#pragma unroll
-      for (int q = 0; q < CW / 32; ++q) {
+      if (stamp) FB_STAMP(17);
+      uint32_t dsb[CW / 2], pdb[CW / 2];   // dS' and Pd of this thread's CW columns, bf16 pairs
+      {
         uint32_t v[32];
-        tmem_ld_32x32(lane_base + TB_DP + CW * g + 32 * q, v);
+        tmem_ld_32x32(lane_base + TB_DP + CW * g, v);
         tmem_ld_wait();
-        uint32_t pdb[16];
 #pragma unroll
         for (int gg = 0; gg < 4; ++gg) {
-          uint32_t keep = 0xFFu;
-          if (p.drop.thresh16) keep = drop_keep8(p.drop, rowid, static_cast<uint32_t>(j0 + CW * g + 32 * q + 8 * gg) >> 3);
+          float fk[8];
+          if (do_drop) {
+            drop_factors8(rowkey, static_cast<uint32_t>(j0 + CW * g + 8 * gg) >> 3, p.drop.thresh16, p.drop.inv_keep, fk);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) fk[e] = 1.0f;
+          }
           float dsv[8], pdv[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const int idx = 32 * q + 8 * gg + e;           // column inside this thread's CW
+            const int idx = 8 * gg + e;           // column inside this thread's CW
             const float4 s4 = sc[idx >> 2];
             const float s = (idx & 3) == 0 ? s4.x : (idx & 3) == 1 ? s4.y : (idx & 3) == 2 ? s4.z : s4.w;
-            const float pr = row_ok ? ex2_approx(s - lse) : 0.0f;   // s = -inf or lse = +inf -> 0
-            const float f = ((keep >> e) & 1u) ? p.drop.inv_keep : 0.0f;
-            pdv[e] = pr * f;
-            dsv[e] = (pr > 0.0f) ? pr * (__uint_as_float(v[8 * gg + e]) * f - D) * p.scale : 0.0f;
+            const float pr = ex2_approx(s - lse);   // s = -inf (masked / padded row) or lse = +inf (dead row) -> 0
+            pdv[e] = pr * fk[e];
+            dsv[e] = pr * fmaf(__uint_as_float(v[idx]), fk[e], -D);
           }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            dsb[16 * q + 4 * gg + e] = pack_bf16(dsv[2 * e], dsv[2 * e + 1]);
+            dsb[4 * gg + e] = pack_bf16(dsv[2 * e], dsv[2 * e + 1]);
             pdb[4 * gg + e] = pack_bf16(pdv[2 * e], pdv[2 * e + 1]);
           }
         }
-        // stage Pd and dS rows: K-major [row a][64 keys] chunks of 16 KB, 128B swizzle; this thread's 32 columns
+      }
+      if (stamp) FB_STAMP(18);
+      // [Pd | dS'] and Z are free once the previous pair's last MMA group has completed
+      if (t > 0) mbar_wait(bar_last, (t - 1) & 1);
+      if (stamp) FB_STAMP(19);
+      {
+        // stage Pd and dS' rows: K-major [row a][64 keys] chunks of 16 KB, 128B swizzle; this thread's 32 columns
         // are the four 16-byte units (col0 >> 3) .. +3 of chunk (col0 >> 6)
-        const int col0 = CW * g + 32 * q;
+        const int col0 = CW * g;
         uint8_t* prow = s0 + (col0 >> 6) * 16384 + a * 128;
         uint8_t* drow = prow + 32768;
 #pragma unroll
         for (int gg = 0; gg < 4; ++gg) {
           const int unit = ((((col0 & 63) >> 3) + gg) ^ (a & 7)) << 4;
           *reinterpret_cast<uint4*>(prow + unit) = make_uint4(pdb[4 * gg], pdb[4 * gg + 1], pdb[4 * gg + 2], pdb[4 * gg + 3]);
-          *reinterpret_cast<uint4*>(drow + unit) = make_uint4(dsb[16 * q + 4 * gg], dsb[16 * q + 4 * gg + 1],
-                                                               dsb[16 * q + 4 * gg + 2], dsb[16 * q + 4 * gg + 3]);
+          *reinterpret_cast<uint4*>(drow + unit) = make_uint4(dsb[4 * gg], dsb[4 * gg + 1], dsb[4 * gg + 2], dsb[4 * gg + 3]);
         }
       }
-      if (stamp) FB_STAMP(19);
-      compute_arrive(bar_rdyA, lane);
+      if constexpr (REL) {
+        // Z1 is built BEFORE the content MMAs are released: shared-memory stores that run while the tensor core
+        // streams operands are several times slower (measured), and the MMAs then issue back to back
+        build_z1<CW>(zb, a, CW * g, dsb);
+        if (stamp) FB_STAMP(20);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(bar_rdyA); mbar_arrive(bar_rdyB); }
+        if (stamp) FB_STAMP(21);
+      } else {
+        compute_arrive(bar_rdyA, lane);
+      }
       if (p.ds_out != nullptr && row_ok) {
         uint4* dst = reinterpret_cast<uint4*>(p.ds_out + srow * p.lp + j0 + CW * g);
 #pragma unroll
         for (int u = 0; u < CW / 8; ++u) dst[u] = make_uint4(dsb[4 * u], dsb[4 * u + 1], dsb[4 * u + 2], dsb[4 * u + 3]);
       }
       if constexpr (REL) {
-        if (stamp) FB_STAMP(20);
-        mbar_wait(bar_mmaA, ph);
-        if (stamp) FB_STAMP(21);
-        zero_s0<NCT>(s0, ctid);
         if (stamp) FB_STAMP(22);
-        named_bar_sync(1, NCT);
+        mbar_wait(bar_mmaB, ph);      // the tensor core no longer reads Z1; dS'^T is in the dP columns
+        tc_fence_after();
         if (stamp) FB_STAMP(23);
-        scatter_z1<CW>(s0, a, CW * g, dsb);
-        if (stamp) FB_STAMP(24);
-        compute_arrive(bar_rdyB, lane);
-        mbar_wait(bar_mmaB, ph);
-        if (stamp) FB_STAMP(25);
-        zero_s0<NCT>(s0, ctid);
-        named_bar_sync(1, NCT);
-        if (stamp) FB_STAMP(26);
-        scatter_z2<CW>(s0, a, CW * g, dsb);
-        if (stamp) FB_STAMP(27);
+        {
+          // this thread now owns KEY row a: Z2[a][k] = dS'^T[a][q], k = q - a + 127: the Z1 construction on the transpose
+          uint32_t v[32];
+          tmem_ld_32x32(lane_base + TB_DP + CW * g, v);
+          tmem_ld_wait();
+          uint32_t dst[CW / 2];
+#pragma unroll
+          for (int e = 0; e < CW / 2; ++e) dst[e] = pack_bf16(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+          build_z1<CW>(zb, a, CW * g, dst);
+        }
+        tc_fence_before();
         compute_arrive(bar_rdyC, lane);
+        if (stamp) FB_STAMP(24);
       }
       if (I == nb - 1) {
-        // ---- key block J is complete: dK_J, dV_J -> bf16 (thread = key row, warpgroup = OC-column slice)
-        mbar_wait(bar_s0free, ph);
+        // ---- key block J is complete: dK_J (x scale), dV_J -> bf16 (thread = key row, warpgroup = OC-column slice)
+        mbar_wait(bar_last, ph);
         tc_fence_after();
         const int j = j0 + a;
 #pragma unroll
@@ -408,20 +505,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           if (j < p.L) {
             __nv_bfloat16* base = (w == 0) ? p.dk + ((long long)b * p.L + j) * p.lddk : p.dv + ((long long)b * p.L + j) * p.lddv;
             uint4* dst = reinterpret_cast<uint4*>(base + hh * 64 + OC * g);
+            const float sc_out = (w == 0) ? p.scale : 1.0f;
 #pragma unroll
-            for (int u = 0; u < OC / 8; ++u)
-              dst[u] = make_uint4(pack_bf16(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
-                                  pack_bf16(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
-                                  pack_bf16(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
-                                  pack_bf16(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7])));
+            for (int u = 0; u < OC / 8; ++u) dst[u] = pack8_scaled(v + 8 * u, sc_out);
           }
         }
         tc_fence_before();   // the next key block's first MMA overwrites dK / dV (ordered by bar_rdyA)
       }
-      if (stamp) FB_STAMP(28);
+      if (stamp) FB_STAMP(25);
+      if (t + 1 < npairs) {
+        // next pair's scores into registers while the last MMA group runs, then park on its barrier (busy compute
+        // warps measurably slow the control thread's MMA issue)
+        load_scores(t + 1);
+        mbar_wait(bar_last, ph);
+      }
+      if (stamp) FB_STAMP(26);
     }
-    // ---- dQ of every query tile
-    mbar_wait(bar_s0free, (npairs - 1) & 1);
+    // ---- dQ of every query tile (x scale)
+    mbar_wait(bar_last, (npairs - 1) & 1);
     tc_fence_after();
     for (int I = 0; I < nb; ++I) {
       const int i = I * 128 + a;
@@ -431,11 +532,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       if (i < p.L) {
         uint4* dst = reinterpret_cast<uint4*>(p.dq + ((long long)b * p.L + i) * p.lddq + hh * 64 + OC * g);
 #pragma unroll
-        for (int u = 0; u < OC / 8; ++u)
-          dst[u] = make_uint4(pack_bf16(__uint_as_float(v[8 * u]), __uint_as_float(v[8 * u + 1])),
-                              pack_bf16(__uint_as_float(v[8 * u + 2]), __uint_as_float(v[8 * u + 3])),
-                              pack_bf16(__uint_as_float(v[8 * u + 4]), __uint_as_float(v[8 * u + 5])),
-                              pack_bf16(__uint_as_float(v[8 * u + 6]), __uint_as_float(v[8 * u + 7])));
+        for (int u = 0; u < OC / 8; ++u) dst[u] = pack8_scaled(v + 8 * u, p.scale);
       }
     }
   }
@@ -449,13 +546,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------
-// Gradients of the per-relative-position tables:
-//   gpk[h, band0(d) + c, :] += sum_{b, pairs (I, J = I - d)} Z1^T . Q_I      (c2p, deberta.py:870-881)
-//   gpq[h, band0(d) + c, :] += sum_{b, pairs}               Z2^T . K_J      (p2c, deberta.py:884-918)
-// One CTA = (head, diagonal d, contiguous slice of the (pair, batch) units of that diagonal).
+// Gradients of the per-relative-position tables (scale applied at the flush):
+//   gpk[h, rel_off + d 128 + 127 - k, :] += sum_{b, pairs (I, J = I - d)} Z1^T . Q_I     (c2p, deberta.py:870-881)
+//   gpq[h, rel_off + d 128 - 127 + k, :] += sum_{b, pairs}               Z2^T . K_J     (p2c, deberta.py:884-918)
+// One CTA = (head, diagonal d, contiguous slice of the (pair, batch) units of that diagonal).  Z1 / Z2 are built
+// exactly as in fb_attn_bwd and read by the tensor core through the MN-major (transposed) view of the same buffer.
 // ---------------------------------------------------------------------------------------------
-static constexpr int AR_THREADS = 320;
-static constexpr uint32_t R_OFF_Q = 0, R_OFF_K = 16384, R_OFF_Z = 32768, R_OFF_BARS = R_OFF_Z + 65536,
+static constexpr int AR_THREADS = 320;   // warps 0-7 compute (thread = row, warpgroup = 64-column half), 8 control, 9 TMEM
+static constexpr uint32_t R_OFF_Q = 0, R_OFF_K = 16384, R_OFF_Z = 32768, R_OFF_BARS = R_OFF_Z + Z_BYTES,
                           AR_SMEM = R_OFF_BARS + 128 + 1024;
 static constexpr uint32_t TR_PK = 0, TR_PQ = 128;   // two [256 x 64] accumulators, each two 128-lane halves of 64 columns
 
@@ -463,6 +561,7 @@ struct AttnBwdRelParams {
   int B, L, h, nb, lp, rel_rows, rel_off, units_per_cta;
   const __nv_bfloat16* ds;
   float* gpk; float* gpq;
+  float scale;
 };
 
 __global__ void __launch_bounds__(AR_THREADS, 2)
@@ -497,7 +596,6 @@ attn_bwd_rel_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   const int u_begin = slice * p.units_per_cta;
   const int u_end = min(u_begin + p.units_per_cta, nunits);
   const int I_first = d > 0 ? d : 0;
-  const int band0 = d * 128 - 127 + p.rel_off;
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k);
@@ -509,6 +607,10 @@ attn_bwd_rel_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   if (warp == 9) {
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
+  }
+  if (warp < 8) {
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t o = threadIdx.x * 16; o < Z_BYTES; o += 256 * 16) *reinterpret_cast<uint4*>(sz + o) = z4;
   }
   tc_fence_before();
   __syncthreads();
@@ -531,8 +633,9 @@ attn_bwd_rel_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       for (int u = u_begin; u < u_end; ++u) {
         const uint32_t ph = (u - u_begin) & 1;
         const uint32_t acc = (u > u_begin) ? 1u : 0u;
-        // ---- gpk band += Z1^T . Q_I : M = band index c (two halves of 128 = 2 chunks of 64 each, 16 KB apart),
-        //      K = 128 query rows (16 rows = 2048 B per step)
+        // ---- band of gpk += Z1^T . Q_I.  A = Z^T: MN-major SWIZZLE_NONE view of the skewed buffer: M = band index k
+        //      (8-element groups Z_LBO apart -> SBO field), K = the 128 rows (8-row groups Z_SBO apart -> LBO field);
+        //      two M halves of 128 (16 groups each), 8 k-steps of 16 rows
         mbar_wait(bar_q, ph);
         mbar_wait(bar_rdy1, ph);
         tc_fence_after();
@@ -540,11 +643,11 @@ attn_bwd_rel_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int mh = 0; mh < 2; ++mh)
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_bf16(tmem + TR_PK + 64 * mh, make_smem_desc_sw128(sZ + mh * 32768 + k * 2048, 16384, 1024),
+            umma_bf16(tmem + TR_PK + 64 * mh, make_smem_desc_none(sZ + mh * 16 * Z_LBO + k * 2 * Z_SBO, Z_SBO, Z_LBO),
                       make_smem_desc_sw128(sQ + k * 2048, 16, 1024), idesc_mn, (acc || k > 0) ? 1u : 0u);
         umma_commit(bar_mma1);
         mbar_wait(bar_mma1, ph);
-        // ---- gpq band += Z2^T . K_J
+        // ---- band of gpq += Z2^T . K_J
         mbar_wait(bar_k, ph);
         mbar_wait(bar_rdy2, ph);
         tc_fence_after();
@@ -552,7 +655,7 @@ attn_bwd_rel_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int mh = 0; mh < 2; ++mh)
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_bf16(tmem + TR_PQ + 64 * mh, make_smem_desc_sw128(sZ + mh * 32768 + k * 2048, 16384, 1024),
+            umma_bf16(tmem + TR_PQ + 64 * mh, make_smem_desc_none(sZ + mh * 16 * Z_LBO + k * 2 * Z_SBO, Z_SBO, Z_LBO),
                       make_smem_desc_sw128(sK + k * 2048, 16, 1024), idesc_mn, (acc || k > 0) ? 1u : 0u);
         umma_commit(bar_mma2);
         mbar_wait(bar_mma2, ph);
@@ -563,7 +666,6 @@ attn_bwd_rel_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   } else if (warp < 8) {
     const int g = warp >> 2, wq = warp & 3;
     const int a = wq * 32 + lane;
-    const int ctid = threadIdx.x;
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
     for (int u = u_begin; u < u_end; ++u) {
       const uint32_t ph = (u - u_begin) & 1;
@@ -582,32 +684,30 @@ attn_bwd_rel_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
         for (int q = 0; q < 32; ++q) dsb[q] = 0u;
       }
-      if (u > u_begin) mbar_wait(bar_mma2, ph ^ 1);   // previous unit's MMAs no longer read the staging region
-      zero_s0<256>(sz, ctid);
-      named_bar_sync(1, 256);
-      scatter_z1<64>(sz, a, 64 * g, dsb);
+      if (u > u_begin) mbar_wait(bar_mma2, ph ^ 1);   // previous unit's MMAs no longer read the staging buffer
+      build_z1<64>(sz, a, 64 * g, dsb);
       compute_arrive(bar_rdy1, lane);
       mbar_wait(bar_mma1, ph);
-      zero_s0<256>(sz, ctid);
-      named_bar_sync(1, 256);
-      scatter_z2<64>(sz, a, 64 * g, dsb);
+      build_z2<64>(sz, a, 64 * g, dsb);
       compute_arrive(bar_rdy2, lane);
     }
-    // ---- flush the band accumulators (thread = band row c = 128 mh + a, warpgroup = 32-column half)
+    // ---- flush the band accumulators (thread = band index k = 128 mh + a, warpgroup = 32-column half)
     if (u_begin < u_end) {
       mbar_wait(bar_mma2, (u_end - 1 - u_begin) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int w = 0; w < 4; ++w) {
         const int mh = w & 1;
-        const int row = band0 + 128 * mh + a;
+        const int k = 128 * mh + a;
+        // relative position of band index k: Z1 (reversed table) 127 - k, Z2 k - 127
+        const int row = p.rel_off + d * 128 + (w < 2 ? 127 - k : k - 127);
         uint32_t v[32];
         tmem_ld_32x32(lane_base + (w < 2 ? TR_PK : TR_PQ) + 64 * mh + 32 * g, v);
         tmem_ld_wait();
-        if (row >= 0 && row < p.rel_rows) {
+        if (k < 255 && row >= 0 && row < p.rel_rows) {
           float* dst = (w < 2 ? p.gpk : p.gpq) + ((long long)hh * p.rel_rows + row) * 64 + 32 * g;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) atomicAdd(dst + e, __uint_as_float(v[e]));
+          for (int e = 0; e < 32; ++e) atomicAdd(dst + e, __uint_as_float(v[e]) * p.scale);
         }
       }
     }
@@ -642,8 +742,8 @@ int attn_bwd(const fb_attn_bwd_args* a, cudaStream_t st) {
   FB_REQUIRE(a->B > 0 && a->h > 0 && a->L > 0 && a->L <= 512, "fb_attn_bwd: need 0 < L <= 512 (got %d)", a->L);
   const int lpad = (a->L + 127) / 128 * 128;
   FB_REQUIRE(a->lp == lpad, "fb_attn_bwd: s2 row pitch must be L rounded up to 128 (got %d)", a->lp);
-  const bool rel = a->PKrel != nullptr;
-  FB_REQUIRE(!rel || a->PQrel, "fb_attn_bwd: PKrel and PQrel must be given together");
+  const bool rel = a->PKrev != nullptr;
+  FB_REQUIRE(!rel || a->PQrel, "fb_attn_bwd: PKrev and PQrel must be given together");
   FB_REQUIRE(!rel || (a->rel_off >= lpad && a->rel_rows >= a->rel_off + lpad + 1),
              "fb_attn_bwd: relative tables too small (rel_rows=%d rel_off=%d L=%d)", a->rel_rows, a->rel_off, a->L);
   FB_REQUIRE(a->lddq % 8 == 0 && a->lddk % 8 == 0 && a->lddv % 8 == 0 && a->ldo % 8 == 0,
@@ -655,14 +755,14 @@ int attn_bwd(const fb_attn_bwd_args* a, cudaStream_t st) {
   if ((rc = make_rows_map(&mv, a->V, a->ldv, a->B, a->L, a->h))) return rc;
   if ((rc = make_rows_map(&mdo, a->dO, a->ldo, a->B, a->L, a->h))) return rc;
   if (rel) {
-    if ((rc = make_band_map(&mpk, a->PKrel, a->rel_rows, a->h))) return rc;
+    if ((rc = make_band_map(&mpk, a->PKrev, a->rel_rows, a->h))) return rc;
     if ((rc = make_band_map(&mpq, a->PQrel, a->rel_rows, a->h))) return rc;
   } else {
     mpk = mk; mpq = mk;   // never dereferenced by the plain-attention instantiation
   }
   AttnBwdFusedParams p;
   memset(&p, 0, sizeof(p));
-  p.B = a->B; p.L = a->L; p.h = a->h; p.nb = lpad / 128; p.lp = lpad; p.rel_off = a->rel_off;
+  p.B = a->B; p.L = a->L; p.h = a->h; p.nb = lpad / 128; p.lp = lpad; p.rel_off = a->rel_off; p.rel_rows = a->rel_rows;
   p.s2 = a->s2; p.lse = a->lse;
   p.ctx = (const __nv_bfloat16*)a->O; p.dctx = (const __nv_bfloat16*)a->dO; p.ldc = a->ldo;
   p.dq = (__nv_bfloat16*)a->dQ; p.lddq = a->lddq;
@@ -702,6 +802,7 @@ int attn_bwd_rel(const fb_attn_bwd_rel_args* a, cudaStream_t st) {
   memset(&p, 0, sizeof(p));
   p.B = a->B; p.L = a->L; p.h = a->h; p.nb = lpad / 128; p.lp = lpad; p.rel_rows = a->rel_rows; p.rel_off = a->rel_off;
   p.ds = (const __nv_bfloat16*)a->ds; p.gpk = a->gpk; p.gpq = a->gpq;
+  p.scale = a->scale;
   // Slice the (pair, batch) units of every diagonal.  Two CTAs are resident per SM; slices of at most 8 units keep
   // the tail short (the diagonals hold different numbers of units, so "one slice per CTA slot" leaves a second,
   // nearly empty wave) while one flush of the band accumulators (128 KB of fp32 atomics) per 8 units stays cheap.

@@ -281,10 +281,11 @@ class DebertaEngine:
         rel_rows, _ = lib.rel_table_geometry(L)
         pq = ws.get("PQrel" + tagk, (h, rel_rows, 64), BF16)
         pk = ws.get("PKrel" + tagk, (h, rel_rows, 64), BF16)
-        lib.build_rel_tables(pqk, self.bucket_of_rel, L, h, out_pq=pq, out_pk=pk)
+        pkr = ws.get("PKrev" + tagk, (h, rel_rows, 64), BF16) if (self.training and self.fused_attn_bwd) else None
+        lib.build_rel_tables(pqk, self.bucket_of_rel, L, h, out_pq=pq, out_pk=pk, out_pk_rev=pkr)
         if key is not None:
-            self._rel_tables_cache[key] = (pq, pk)
-        return pq, pk
+            self._rel_tables_cache[key] = (pq, pk, pkr)
+        return pq, pk, pkr
 
     def _sublayer_out(self, name, i, pass_id, u_in16, W_dense, b_dense, ad_prefix, ln_prefix, resid32, site_ad,
                       site_hid, training, tag):
@@ -325,7 +326,7 @@ class DebertaEngine:
         tag = tag if tag is not None else str(pass_id)
         sfx = f".{tag}" if training else ""
         p = f"{self.layer_prefix}{i}."
-        pq, pk = self._rel_tables(i, pass_id, L) if self.use_rel else (None, None)
+        pq, pk, pkr = self._rel_tables(i, pass_id, L) if self.use_rel else (None, None, None)
         ctx16 = ws.get("ctx" + sfx, (T, H), BF16)
         lse = ws.get("lse" + sfx, (B, h, L), F32)
         att_drop = self.drop(cfg.attention_probs_dropout_prob, pass_id * 8 + SITE_PROBS)
@@ -344,8 +345,8 @@ class DebertaEngine:
                                             training, tag)
         rec = None
         if training:
-            rec = dict(layer=i, pass_id=pass_id, Q=Q, K=K, V=V, pq=pq, pk=pk, ctx=ctx16, lse=lse, att=rec1, ffn=rec2,
-                       h1=h1, s2=s2)
+            rec = dict(layer=i, pass_id=pass_id, Q=Q, K=K, V=V, pq=pq, pk=pk, pkr=pkr, ctx=ctx16, lse=lse, att=rec1,
+                       ffn=rec2, h1=h1, s2=s2)
         return y32, y16, rec
 
     # ------------------------------------------------------------------ head
@@ -572,7 +573,7 @@ class DebertaEngine:
         rel = self.use_rel
         ds = ws.get("bw.ds", (B, h, L, lp), BF16) if rel else None
         ad = self.drop(cfg.attention_probs_dropout_prob, pass_id * 8 + SITE_PROBS)
-        lib.attn_bwd(Q, K, V, rec["ctx"], dctx16, rec["s2"], rec["lse"], rec["pk"], rec["pq"],
+        lib.attn_bwd(Q, K, V, rec["ctx"], dctx16, rec["s2"], rec["lse"], rec["pkr"], rec["pq"],
                      dqkv16[:, :H], dqkv16[:, H:2 * H], dqkv16[:, 2 * H:], ds_out=ds, B=B, L=L, h=h,
                      scale=self.attn_scale, dropout_p=ad.p, seed=ad.seed, offset=ad.offset)
         if not rel:
@@ -580,7 +581,7 @@ class DebertaEngine:
         rel_rows, _ = lib.rel_table_geometry(L)
         gpk = ws.get("bw.gpk", (h, rel_rows, 64), F32)
         gpq = ws.get("bw.gpq", (h, rel_rows, 64), F32)
-        lib.attn_bwd_rel(ds, Q, K, gpk, gpq, B=B, L=L, h=h)
+        lib.attn_bwd_rel(ds, Q, K, gpk, gpq, B=B, L=L, h=h, scale=self.attn_scale)
         self._bwd_rel_tables(gpq, gpk, i, pass_id, L, h)
 
     def _bwd_rel_tables(self, gpq, gpk, i, pass_id, L, h):

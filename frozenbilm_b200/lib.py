@@ -89,7 +89,7 @@ class AttnBwdArgs(C.Structure):
         ("V", C.c_void_p), ("ldv", C.c_longlong),
         ("O", C.c_void_p), ("dO", C.c_void_p), ("ldo", C.c_longlong),
         ("s2", C.c_void_p), ("lse", C.c_void_p),
-        ("PKrel", C.c_void_p), ("PQrel", C.c_void_p), ("rel_rows", C.c_int), ("rel_off", C.c_int),
+        ("PKrev", C.c_void_p), ("PQrel", C.c_void_p), ("rel_rows", C.c_int), ("rel_off", C.c_int),
         ("dQ", C.c_void_p), ("lddq", C.c_longlong),
         ("dK", C.c_void_p), ("lddk", C.c_longlong),
         ("dV", C.c_void_p), ("lddv", C.c_longlong),
@@ -107,6 +107,7 @@ class AttnBwdRelArgs(C.Structure):
         ("K", C.c_void_p), ("ldk", C.c_longlong),
         ("gpk", C.c_void_p), ("gpq", C.c_void_p),
         ("units_per_cta", C.c_int),
+        ("scale", C.c_float),
     ]
 
 
@@ -157,7 +158,7 @@ def load() -> C.CDLL:
     lib.fb_sumsq.argtypes = [vp, ll, vp, vp]
     lib.fb_adam_step.argtypes = [vp, vp, vp, vp, ll, f, f, f, f, i, vp, f, f, vp, vp]
     lib.fb_cast_f32_bf16.argtypes = [vp, ll, vp, vp]
-    lib.fb_build_rel_tables.argtypes = [vp, ll, i, i, vp, i, i, i, vp, vp, vp]
+    lib.fb_build_rel_tables.argtypes = [vp, ll, i, i, vp, i, i, i, vp, vp, vp, vp]
     lib.fb_rel_to_bucket.argtypes = [vp, vp, i, i, vp, i, i, i, vp, ll, vp]
     _lib = lib
     return lib
@@ -265,8 +266,10 @@ def rel_table_geometry(L: int):
     return 2 * lpad + 8, lpad
 
 
-def build_rel_tables(pqk: torch.Tensor, bucket_of_rel: torch.Tensor, L: int, h: int, out_pq=None, out_pk=None):
-    """pqk: bf16 [2S, 2H] (PQ | PK).  Returns (PQrel, PKrel) bf16 [h, rel_rows, 64]."""
+def build_rel_tables(pqk: torch.Tensor, bucket_of_rel: torch.Tensor, L: int, h: int, out_pq=None, out_pk=None,
+                     out_pk_rev=None):
+    """pqk: bf16 [2S, 2H] (PQ | PK).  Returns (PQrel, PKrel) bf16 [h, rel_rows, 64]; ``out_pk_rev`` (optional, same
+    shape) receives PKrel with its rows reversed (the operand of the fused backward)."""
     H = pqk.shape[1] // 2
     rel_rows, rel_off = rel_table_geometry(L)
     if out_pq is None:
@@ -275,7 +278,8 @@ def build_rel_tables(pqk: torch.Tensor, bucket_of_rel: torch.Tensor, L: int, h: 
         out_pk = torch.empty(h, rel_rows, 64, device=pqk.device, dtype=torch.bfloat16)
     assert bucket_of_rel.dtype == torch.int32 and bucket_of_rel.numel() == 1023
     check(load().fb_build_rel_tables(_ptr(pqk), C.c_longlong(pqk.stride(0)), H, h, _ptr(bucket_of_rel), rel_rows,
-                                     rel_off, L, _ptr(out_pq), _ptr(out_pk), stream_ptr()), "fb_build_rel_tables")
+                                     rel_off, L, _ptr(out_pq), _ptr(out_pk), _ptr(out_pk_rev), stream_ptr()),
+          "fb_build_rel_tables")
     return out_pq, out_pk
 
 
@@ -401,10 +405,11 @@ def attn_bwd_prep(s2, lse, dp, ctx, dctx, ds, pd, z1=None, z2=None, *, B, L, h, 
     check(load().fb_attn_bwd_prep(C.byref(a), stream_ptr()), "fb_attn_bwd_prep")
 
 
-def attn_bwd(Q, K, V, O, dO, s2, lse, PKrel, PQrel, dQ, dK, dV, ds_out=None, *, B, L, h, scale, dropout_p=0.0, seed=0,
+def attn_bwd(Q, K, V, O, dO, s2, lse, PKrev, PQrel, dQ, dK, dV, ds_out=None, *, B, L, h, scale, dropout_p=0.0, seed=0,
              offset=0):
     """Fused attention backward (fb_attn_bwd).  Q/K/V/O/dO/dQ/dK/dV: bf16 2-D views [B*L, >= h*64]; s2: fp32
-    [B,h,L,lp]; lse: fp32 [B,h,L]; ds_out: optional bf16 [B,h,L,lp]."""
+    [B,h,L,lp]; lse: fp32 [B,h,L]; PKrev: row-reversed PKrel (build_rel_tables(out_pk_rev=...)); ds_out: optional
+    bf16 [B,h,L,lp], receives the UNSCALED dS'."""
     rel_rows, rel_off = rel_table_geometry(L)
     assert s2.dtype == torch.float32 and lse.dtype == torch.float32
     assert O.stride(0) == dO.stride(0)
@@ -415,7 +420,7 @@ def attn_bwd(Q, K, V, O, dO, s2, lse, PKrel, PQrel, dQ, dK, dV, ds_out=None, *, 
     a.V, a.ldv = _ptr(V), V.stride(0)
     a.O, a.dO, a.ldo = _ptr(O), _ptr(dO), O.stride(0)
     a.s2, a.lse = _ptr(s2), _ptr(lse)
-    a.PKrel, a.PQrel, a.rel_rows, a.rel_off = _ptr(PKrel), _ptr(PQrel), rel_rows, rel_off
+    a.PKrev, a.PQrel, a.rel_rows, a.rel_off = _ptr(PKrev), _ptr(PQrel), rel_rows, rel_off
     a.dQ, a.lddq = _ptr(dQ), dQ.stride(0)
     a.dK, a.lddk = _ptr(dK), dK.stride(0)
     a.dV, a.lddv = _ptr(dV), dV.stride(0)
@@ -425,7 +430,7 @@ def attn_bwd(Q, K, V, O, dO, s2, lse, PKrel, PQrel, dQ, dK, dV, ds_out=None, *, 
     check(load().fb_attn_bwd(C.byref(a), stream_ptr()), "fb_attn_bwd")
 
 
-def attn_bwd_rel(ds, Q, K, gpk, gpq, *, B, L, h, units_per_cta=0):
+def attn_bwd_rel(ds, Q, K, gpk, gpq, *, B, L, h, scale, units_per_cta=0):
     """gpk / gpq (fp32 [h, rel_rows, 64], overwritten) = gradients of the per-relative-position tables."""
     rel_rows, rel_off = rel_table_geometry(L)
     assert gpk.dtype == torch.float32 and gpq.dtype == torch.float32 and gpk.shape[1] == rel_rows
@@ -436,6 +441,7 @@ def attn_bwd_rel(ds, Q, K, gpk, gpq, *, B, L, h, units_per_cta=0):
     a.K, a.ldk = _ptr(K), K.stride(0)
     a.gpk, a.gpq = _ptr(gpk), _ptr(gpq)
     a.units_per_cta = int(units_per_cta)
+    a.scale = float(scale)
     check(load().fb_attn_bwd_rel(C.byref(a), stream_ptr()), "fb_attn_bwd_rel")
 
 

@@ -127,10 +127,12 @@ int fb_rel_to_bucket(const float* gpq, const float* gpk, int H, int h, const int
 
 /* Fused attention backward (same autograd, deberta.py:769-808 / 820-947 / XSoftmax :134-138 / XDropout :188-194),
  * one tcgen05 kernel per layer pass instead of the staged schedule above: one CTA per (batch, head) recomputes
- * P = exp2(s2 - lse) and dS tile by tile, keeps dQ / dK / dV in TMEM and writes them once as bf16:
- *   dV = Pd^T.dO ; dQ = dS.K + Z1.PKrel ; dK = dS^T.Q + Z2.PQrel   (Z1/Z2 = dS regrouped by relative position
- *   inside shared memory, never in HBM).  ds_out (optional, bf16 [B,h,L,lp]) feeds fb_attn_bwd_rel.
- * PKrel = PQrel = NULL selects plain attention (BERT, bert.py:141-191).  O and dO share the row pitch ldo. */
+ * P = exp2(s2 - lse) and dS' = P * (dropout_bwd(dP) - rowsum(dO*O)) tile by tile, keeps dQ / dK / dV in TMEM and
+ * writes them once as bf16:
+ *   dV = Pd^T.dO ; dQ = scale (dS'.K + Z1.PKrel) ; dK = scale (dS'^T.Q + Z2.PQrel)   (Z1/Z2 = dS' regrouped by
+ *   relative position inside shared memory, never in HBM).  ds_out (optional, bf16 [B,h,L,lp]) receives the
+ *   UNSCALED dS' and feeds fb_attn_bwd_rel.  PKrev is the row-reversed PKrel table of fb_build_rel_tables.
+ * PKrev = PQrel = NULL selects plain attention (BERT, bert.py:141-191).  O and dO share the row pitch ldo. */
 typedef struct fb_attn_bwd_args {
   int B, L, h, lp;                           /* lp = L rounded up to 128 = row pitch of s2 / ds_out */
   const void* Q; long long ldq;              /* bf16 [B*L, >= h*64] views, as in fb_attn_fwd */
@@ -138,7 +140,7 @@ typedef struct fb_attn_bwd_args {
   const void* V; long long ldv;
   const void* O; const void* dO; long long ldo;   /* bf16 context and its gradient */
   const float* s2; const float* lse;         /* fp32 [B,h,L,lp] scores (log2 domain, -inf = masked), [B,h,L] */
-  const void* PKrel; const void* PQrel; int rel_rows, rel_off;
+  const void* PKrev; const void* PQrel; int rel_rows, rel_off;
   void* dQ; long long lddq;                  /* bf16 outputs */
   void* dK; long long lddk;
   void* dV; long long lddv;
@@ -152,26 +154,28 @@ int fb_attn_bwd(const fb_attn_bwd_args* args, void* stream);
 int fb_attn_bwd_set_debug(long long* stamps);
 
 /* Gradients of the per-relative-position tables (fp32 [h, rel_rows, 64], OVERWRITTEN):
- *   gpk[h, (i-j)+rel_off] = sum_{b,i,j} dS[b,h,i,j] Q[b,h,i]   (c2p, deberta.py:870-881)
- *   gpq[h, (i-j)+rel_off] = sum_{b,i,j} dS[b,h,i,j] K[b,h,j]   (p2c, deberta.py:884-918)
+ *   gpk[h, (i-j)+rel_off] = scale sum_{b,i,j} dS'[b,h,i,j] Q[b,h,i]   (c2p, deberta.py:870-881)
+ *   gpq[h, (i-j)+rel_off] = scale sum_{b,i,j} dS'[b,h,i,j] K[b,h,j]   (p2c, deberta.py:884-918)
  * One CTA per (head, tile diagonal, batch slice) accumulates its 256-row band in TMEM and flushes once.
- * units_per_cta = 0 picks about two CTAs per SM. */
+ * units_per_cta = 0 picks the slice size. */
 typedef struct fb_attn_bwd_rel_args {
   int B, L, h, lp, rel_rows, rel_off;
-  const void* ds;                            /* bf16 [B,h,L,lp] from fb_attn_bwd */
+  const void* ds;                            /* bf16 [B,h,L,lp]: dS' from fb_attn_bwd (unscaled) */
   const void* Q; long long ldq;
   const void* K; long long ldk;
   float* gpk; float* gpq;
   int units_per_cta;
+  float scale;
 } fb_attn_bwd_rel_args;
 int fb_attn_bwd_rel(const fb_attn_bwd_rel_args* args, void* stream);
 
 /* Expands pqk = Linear_{q|k}(rel_emb) ([2S, 2H] bf16: PQ in cols [0,H), PK in [H,2H); deberta.py:847-853)
  * into the per-relative-position tables used above: out[hh][row] = pqk[bucket_of_rel[row - rel_off + 511]].
  * bucket_of_rel: int32 [1023] = clamp(bucket(rel) + S, 0, 2S-1) for rel in [-511, 511]
- * (make_log_bucket_position, deberta.py:578-589).  Rows with |rel| >= L are zero. */
+ * (make_log_bucket_position, deberta.py:578-589).  Rows with |rel| >= L are zero.  out_pk_rev (nullable) receives
+ * out_pk with its rows reversed (row r <-> rel_rows - 1 - r): the operand fb_attn_bwd wants. */
 int fb_build_rel_tables(const void* pqk, long long ld, int H, int h, const int* bucket_of_rel, int rel_rows,
-                        int rel_off, int L, void* out_pq, void* out_pk, void* stream);
+                        int rel_off, int L, void* out_pq, void* out_pk, void* out_pk_rev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * HBM-bound row kernels (fb_elementwise.cu).  All matrices are dense row-major [M, H].

@@ -22,7 +22,8 @@ mask = torch.ones(B, L, dtype=torch.uint8, device=dev)
 bor = torch.from_numpy(bucket_of_rel(256, 512)).to(dev)
 lp = 384
 scale = 1.0 / math.sqrt(192)
-PQrel, PKrel = lib.build_rel_tables(pqk, bor, L, h)
+PKrev = torch.empty(h, 2 * 384 + 8, 64, device=dev, dtype=torch.bfloat16)
+PQrel, PKrel = lib.build_rel_tables(pqk, bor, L, h, out_pk_rev=PKrev)
 Q, K, V = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
 ctx = torch.zeros(B * L, H, device=dev, dtype=torch.bfloat16)
 lse = torch.empty(B, h, L, device=dev)
@@ -33,7 +34,7 @@ ds = torch.empty(B, h, L, lp, device=dev, dtype=torch.bfloat16)
 
 
 def bwd():
-    lib.attn_bwd(Q, K, V, ctx, dO, s2, lse, PKrel, PQrel, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], ds_out=ds,
+    lib.attn_bwd(Q, K, V, ctx, dO, s2, lse, PKrev, PQrel, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], ds_out=ds,
                  B=B, L=L, h=h, scale=scale, dropout_p=0.1, seed=3, offset=5)
 
 
@@ -55,23 +56,16 @@ bwd()
 torch.cuda.synchronize()
 fn(C.c_void_p(0))
 st = stamps.cpu().view(16, 32)
-names_c = ["start", "dP issued", "rdyA seen", "A issued", "mmaA done", "pk landed", "rdyB seen", "B issued", "mmaB done",
-           "pq landed", "rdyC seen", "C issued", "mmaC done"]
-names_w = {16: "start", 17: "S0 free", 18: "dP ready", 19: "elementwise+stage done", 20: "ds stored", 21: "mmaA seen",
-           22: "zeroed", 23: "barrier", 24: "Z1 scattered", 25: "mmaB seen", 26: "zero+barrier", 27: "Z2 scattered",
-           28: "pair end"}
-t0 = int(st[0, 0])
+names_c = ["start", "dP issued", "rdyA seen", "A issued", "rdyB seen", "B issued", "mmaA done", "mmaB done", "pq landed",
+           "rdyC seen", "C issued", "mmaC done"]
+names_w = ["start", "dP ready", "elementwise done", "S0/Z free", "staged + Z1 built", "arrived (rdyA, rdyB)", "ds stored",
+           "mmaB seen", "Z2 built (rdyC)", "epilogue done", "scores loaded + parked until mmaC"]
+tot = 0
 for t in range(9):
-    row = st[t]
-    print(f"pair {t}: control thread (cycles since kernel start / delta)")
-    prev = int(row[0])
-    for e, n in enumerate(names_c):
-        v = int(row[e])
-        print(f"    {n:24s} {v - t0:9d}  +{v - prev:6d}")
-        prev = v
-    print("         compute warp 0")
-    prev = int(row[16])
-    for e in range(16, 29):
-        v = int(row[e])
-        print(f"    {names_w[e]:24s} {v - t0:9d}  +{v - prev:6d}")
-        prev = v
+    c = [int(x) for x in st[t, :12]]
+    w = [int(x) for x in st[t, 16:27]]
+    print(f"pair {t}: total {c[11] - c[0]} cycles")
+    print("  ctrl: " + "  ".join(f"{n} +{v - pv}" for n, v, pv in zip(names_c[1:], c[1:], c[:-1])))
+    print("  warp: " + "  ".join(f"{n} +{v - pv}" for n, v, pv in zip(names_w[1:], w[1:], w[:-1])))
+    tot += c[11] - c[0]
+print("sum of pairs", tot, "cycles")

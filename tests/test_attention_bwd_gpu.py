@@ -53,9 +53,12 @@ def run_case(B, L, h, rel, dropout_p=0.0, seed=0):
     bor = torch.from_numpy(bucket_of_rel(256, 512)).to(dev)
     lp = (L + 127) // 128 * 128
     scale = 1.0 / math.sqrt(64 * 3) if rel else 1.0 / 8.0
-    PQrel = PKrel = None
+    PQrel = PKrel = PKrev = None
     if rel:
-        PQrel, PKrel = lib.build_rel_tables(pqk, bor, L, h)
+        rel_rows, _ = lib.rel_table_geometry(L)
+        PKrev = torch.empty(h, rel_rows, 64, device=dev, dtype=torch.bfloat16)
+        PQrel, PKrel = lib.build_rel_tables(pqk, bor, L, h, out_pk_rev=PKrev)
+        assert torch.equal(PKrev, PKrel.flip(1))
     Q, K, V = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
     ctx = torch.zeros(B * L, H, device=dev, dtype=torch.bfloat16)
     lse = torch.empty(B, h, L, device=dev)
@@ -64,14 +67,14 @@ def run_case(B, L, h, rel, dropout_p=0.0, seed=0):
                  offset=5, s_out=s2, key_mask_only=not rel)
     dqkv = torch.full((B * L, 3 * H), float("nan"), device=dev, dtype=torch.bfloat16)
     ds = torch.zeros(B, h, L, lp, device=dev, dtype=torch.bfloat16)
-    lib.attn_bwd(Q, K, V, ctx, dO, s2, lse, PKrel, PQrel, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], ds_out=ds,
+    lib.attn_bwd(Q, K, V, ctx, dO, s2, lse, PKrev, PQrel, dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], ds_out=ds,
                  B=B, L=L, h=h, scale=scale, dropout_p=dropout_p, seed=seed, offset=5)
     out = dict(dq=dqkv[:, :H].float(), dk=dqkv[:, H:2 * H].float(), dv=dqkv[:, 2 * H:].float(), ds=ds.float())
     if rel:
         rel_rows, _ = lib.rel_table_geometry(L)
         gpk = torch.full((h, rel_rows, 64), float("nan"), device=dev)
         gpq = torch.full((h, rel_rows, 64), float("nan"), device=dev)
-        lib.attn_bwd_rel(ds, Q, K, gpk, gpq, B=B, L=L, h=h)
+        lib.attn_bwd_rel(ds, Q, K, gpk, gpq, B=B, L=L, h=h, scale=scale)
         dpqk = torch.zeros(512, 2 * H, device=dev)
         lib.rel_to_bucket(gpq, gpk, bor, L, h, dpqk)
         out["dpqk"] = dpqk
@@ -148,7 +151,7 @@ def test_attention_backward_dropout_matches_staged():
     lib.attn_bwd_prep(ins["s2"], ins["lse"], dp, ins["ctx"], dO, ds, pd, None, None, B=B, L=L, h=h, scale=ins["scale"],
                       dropout_p=0.1, seed=11, offset=5)
     torch.cuda.synchronize()
-    a, b = out["ds"][..., :L], ds.float()[..., :L]
+    a, b = out["ds"][..., :L] * ins["scale"], ds.float()[..., :L]   # the fused kernel exports the unscaled dS'
     # the staged path rounds dP to bf16 before the softmax backward; the fused one keeps it in fp32
     assert (a - b).abs().max().item() <= 2e-2 * b.abs().max().item()
     assert ((a == 0) == (b == 0)).float().mean().item() > 0.999
