@@ -27,6 +27,9 @@ import torch.distributed as dist  # noqa: E402
 from frozenbilm_b200.config import CONFIG_XL  # noqa: E402
 from frozenbilm_b200.synth import synth_batch, synth_params, is_trainable  # noqa: E402
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one FFN up-projection launch at B = 32 (ncu --set full capture,
+# profiles/r1_ncu_full_summary.md: 55.9 MB read + 228.4 MB written)
+NCU_FFN1_DRAM_BYTES = 284.3e6
 METRIC = "samples/sec DeBERTa-XL+adapters seq352 bf16 train step (fwd+bwd+allreduce+clip+Adam)"
 B_PER_GPU, N_FRAMES, N_TEXT = 32, 10, 342
 
@@ -244,41 +247,54 @@ def main():
         torch.cuda.profiler.stop()
         return
 
-    # ---- per-kernel roofline probe: the dominant kernel is the FFN up-projection GEMM
-    #      (M = B*L tokens, N = 4H, K = H), timed live with CUDA events around each of its launches
-    probe = {"ms": 0.0, "n": 0, "events": []}
+    # ---- per-kernel roofline probes, timed live with CUDA events around each launch inside the timed region:
+    #      the FFN up-projection GEMM (M = B*L tokens, N = 4H, K = H; fb::gemm_kernel is the dominant kernel family,
+    #      ~46 % of the step) and the three attention kernels (the rest of the tensor-core work)
     eng = model._engine_obj
     T = B * (N_FRAMES + N_TEXT)
     H, I = cfg.hidden_size, cfg.intermediate_size
-    orig_gemm = lib.gemm
-
-    def probed_gemm(A, Bm, D, **kw):
-        is_ffn1 = (kw.get("act") == lib.FB_ACT_GELU and Bm.shape[0] == I and A.shape[0] == T)
-        if not is_ffn1 or not probe.get("on"):
-            return orig_gemm(A, Bm, D, **kw)
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        r = orig_gemm(A, Bm, D, **kw)
-        e.record()
-        probe["events"].append((s, e))
-        return r
-
     import frozenbilm_b200.engine as engmod
-    engmod.lib.gemm = probed_gemm
+    probes = {k: {"events": [], "ms": 0.0, "n": 0} for k in ("ffn1", "attn_fwd", "attn_bwd", "attn_bwd_rel")}
+    probe_on = {"on": False}
+    originals = {}
+
+    def wrap(name, key, select=None):
+        orig = getattr(lib, name)
+        originals[name] = orig
+
+        def f(*a, **kw):
+            if not probe_on["on"] or (select is not None and not select(a, kw)):
+                return orig(*a, **kw)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = orig(*a, **kw)
+            e.record()
+            probes[key]["events"].append((s, e))
+            return r
+
+        setattr(engmod.lib, name, f)
+
+    wrap("gemm", "ffn1", lambda a, kw: kw.get("act") == lib.FB_ACT_GELU and a[1].shape[0] == I and a[0].shape[0] == T)
+    wrap("attn_fwd", "attn_fwd")
+    wrap("attn_bwd", "attn_bwd")
+    wrap("attn_bwd_rel", "attn_bwd_rel")
 
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    probe["on"] = True
+    probe_on["on"] = True
     l0 = lib.launch_count()
     ms = timed(step_resident, args.steps)
     launches = lib.launch_count() - l0
-    probe["on"] = False
+    probe_on["on"] = False
     clk = clocks.stop() if rank == 0 else None
-    for s, e in probe["events"]:
-        probe["ms"] += s.elapsed_time(e)
-        probe["n"] += 1
-    engmod.lib.gemm = orig_gemm
+    for pr in probes.values():
+        for s, e in pr["events"]:
+            pr["ms"] += s.elapsed_time(e)
+            pr["n"] += 1
+    for name, orig in originals.items():
+        setattr(engmod.lib, name, orig)
+    probe = probes["ffn1"]
 
     # ---- end-to-end arm through the public API with host buffers
     for i in range(2):
@@ -303,6 +319,20 @@ def main():
     per_pass = L * H * (51 * H + 12 * L + 24 * S)
     n_lab = max(1, round(0.15 * N_TEXT))
     flops_sample = n_pass * per_pass + 12 * L * H * H + 4 * L * H * H + 4 * n_lab * H * cfg.vocab_size
+    # attention share of the tensor-core work (L*H*(4L + 8S) forward, x3 with the backward), per launch
+    attn_fwd_flops = float(B) * L * H * (4 * L + 8 * S)
+    attn_roof = {"bound": "tensor", "unit": "TFLOP/s", "peak": peak_tf,
+                 "note": "algorithmic FLOPs (SURVEY 8d) / live CUDA-event time per launch; these kernels are bound by "
+                         "the softmax / relative-position regrouping on the CUDA cores, not by the tensor pipe"}
+    # backward = 2x forward: dP, dV, dQ, dK content terms (8L) + positional terms of dQ / dK (8S) in fb_attn_bwd,
+    # gradients of the two positional projections (8S) in fb_attn_bwd_rel
+    for key, fl in (("attn_fwd", attn_fwd_flops), ("attn_bwd", float(B) * L * H * (8 * L + 8 * S)),
+                    ("attn_bwd_rel", float(B) * L * H * 8 * S)):
+        pr = probes[key]
+        if pr["n"]:
+            us = 1e3 * pr["ms"] / pr["n"]
+            attn_roof[key] = {"us_per_launch": us, "achieved": fl / us / 1e6, "frac": fl / us / 1e6 / peak_tf,
+                              "launches_timed": pr["n"]}
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -320,8 +350,13 @@ def main():
         "clocks": clk,
         "roofline": {"bound": "tensor", "kernel": "fb::gemm_kernel<256> FFN up-projection 11264x6144x1536 (+bias+GELU)",
                      "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": (ach / peak_tf) if ach else None,
-                     "traffic": None, "peak_source": peak_src + " (bf16_tflops_sustained)",
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel (ncu --set full, per launch)
+                     "traffic": NCU_FFN1_DRAM_BYTES if B == B_PER_GPU else None,
+                     "traffic_unit": "bytes/launch", "traffic_source": "profiles/r1_ncu_full_summary.md",
+                     "algorithmic_bytes": 2.0 * (T * H + I * H + 2 * T * I),
+                     "peak_source": peak_src + " (bf16_tflops_sustained)",
                      "launches_timed": probe["n"]},
+        "roofline_attention": attn_roof,
     }
     if not args.no_cpu_baseline and world == 1:
         try:

@@ -24,8 +24,10 @@
 
 namespace fb {
 
-static constexpr int AT_THREADS = 320;   // warps 0-7: two softmax warpgroups (thread = query row, warpgroup =
-                                         // half of the keys), warp 8 = TMA+MMA control, warp 9 = TMEM alloc
+static constexpr int AT_THREADS = 384;   // warps 0-7: two softmax warpgroups (thread = query row, warpgroup =
+                                         // half of the keys), warp 8 = TMA+MMA control, warp 9 = TMEM alloc,
+                                         // warps 10-11 idle (they complete the third warpgroup for setmaxnreg)
+static constexpr int AT_REGS_SOFTMAX = 224, AT_REGS_CONTROL = 56;   // 2*128*224 + 128*56 = 64512 <= 65536
 static constexpr int T_PITCH = 136;      // halves per staging row: 272 B -> conflict-free LDS.128
 static constexpr uint32_t OFF_Q = 0, OFF_K = 16384, OFF_V = 32768, OFF_PK = 49152, OFF_PQ = 81920,
                           OFF_P = 114688, OFF_T1 = 147456, OFF_T2 = OFF_T1 + 128 * T_PITCH * 2,
@@ -45,6 +47,35 @@ struct AttnParams {
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
 };
 
+// Staging stores of the Toeplitz skew (one 32-column TMEM chunk of this thread's lane).
+//   MODE 0: elements e >= thr   MODE 1: every element   MODE 2: elements e < thr
+// p2c: element e -> dst[e * T_PITCH]     c2p: element e -> dst[-e]
+template <int MODE>
+__device__ __forceinline__ void stage_p2c(__half* dst, const uint32_t (&v)[32], int thr) {
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    const __half hv = __float2half_rn(__uint_as_float(v[e]));
+    if (MODE == 1 || (MODE == 0 && e >= thr) || (MODE == 2 && e < thr)) dst[e * T_PITCH] = hv;
+  }
+}
+template <int MODE>
+__device__ __forceinline__ void stage_c2p(__half* dst, const uint32_t (&v)[32], int thr) {
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    const __half hv = __float2half_rn(__uint_as_float(v[e]));
+    if (MODE == 1 || (MODE == 0 && e >= thr) || (MODE == 2 && e < thr)) dst[-e] = hv;
+  }
+}
+
+// Pipeline (per 128-key block kb; the tensor core and the softmax warps overlap across blocks):
+//   control thread                                   softmax warps (8 warps, thread = query row)
+//   wait mma1(kb)   -> TMA K/PQ(kb+1)                wait mma1(kb): p2c staging of X2 -> arrive xfree
+//   wait xfree(kb)  -> X1(kb) MMA -> commit mma2     O += P.V of block kb-1 (deferred, in the shadow of X1)
+//   wait mma2(kb)   -> TMA PK(kb+1)                  wait mma2(kb): c2p staging of X1 -> bar.sync
+//   wait sfree(kb)  -> S/X2(kb+1) MMA -> commit mma1 combine + mask + max in REGISTERS -> arrive sfree
+//   wait pready(kb) -> P.V(kb) MMA -> commit mma3    exp2 / dropout / P -> smem -> arrive pready
+// so the next block's S and X2 are computed while the current block is exponentiated, and the P.V result is
+// consumed one block later; only the X1 MMA (which shares TMEM columns with X2) is waited for in place.
 template <bool REL>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -56,14 +87,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
   uint64_t* bar_q = bars + 0;
-  uint64_t* bar_k = bars + 1;
+  uint64_t* bar_k = bars + 1;        // TMA: K block + PQ band (operands of S and X2)
   uint64_t* bar_v = bars + 2;
-  uint64_t* bar_mma1 = bars + 3;
-  uint64_t* bar_xfree = bars + 4;
-  uint64_t* bar_mma2 = bars + 5;
+  uint64_t* bar_mma1 = bars + 3;     // S, X2 complete
+  uint64_t* bar_xfree = bars + 4;    // X2 staged by all 8 warps
+  uint64_t* bar_mma2 = bars + 5;     // X1 complete
   uint64_t* bar_pready = bars + 6;   // [2], one per softmax warpgroup
   uint64_t* bar_mma3 = bars + 8;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* bar_pk = bars + 10;      // TMA: PK band (operand of X1)
+  uint64_t* bar_sfree = bars + 11;   // S / X1 / staging buffers consumed by all 8 warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   __half* T1 = reinterpret_cast<__half*>(smem + OFF_T1);
   __half* T2 = reinterpret_cast<__half*>(smem + OFF_T2);
   uint8_t* kmask = smem + OFF_KMASK;
@@ -78,6 +111,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     mbar_init(bar_mma1, 1); mbar_init(bar_xfree, 8); mbar_init(bar_mma2, 1);
     mbar_init(&bar_pready[0], 4); mbar_init(&bar_pready[1], 4);
     mbar_init(&bar_mma3[0], 1); mbar_init(&bar_mma3[1], 1);
+    mbar_init(bar_pk, 1); mbar_init(bar_sfree, 8);
     fence_barrier_init();
   }
   if (warp == 9) {
@@ -89,8 +123,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
-    if (elect_one_sync()) {
+  // register reallocation between the warpgroups: the softmax threads keep 64 output accumulators AND the 64
+  // scores of a block in registers (no TMEM round trip between the max and the exponentiation)
+  if (warp >= 8) {
+    // the whole third warpgroup (warps 8-11) releases registers at the same instruction
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AT_REGS_CONTROL));
+    if (warp == 8 && elect_one_sync()) {
       // ======================= TMA + MMA control thread =======================
       constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_band = make_idesc_bf16(128, 256, 0, 0);
@@ -99,27 +137,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                      sPK = smem_u32(smem + OFF_PK), sPQ = smem_u32(smem + OFF_PQ), sP = smem_u32(smem + OFF_P);
       auto load_k = [&](int kb) {
         const int j0 = kb * 128;
-        mbar_arrive_expect_tx(bar_k, REL ? 16384 + 2 * 32768 : 16384);
+        mbar_arrive_expect_tx(bar_k, REL ? 16384 + 32768 : 16384);
         tma_load_4d(smem + OFF_K, &map_k, bar_k, 0, hh, j0, b);
+        if constexpr (REL) tma_load_3d(smem + OFF_PQ, &map_pq, bar_k, 0, i0 - j0 - 127 + p.rel_off, hh);
+      };
+      auto load_pk = [&](int kb) {
         if constexpr (REL) {
-          const int band0 = i0 - j0 - 127 + p.rel_off;
-          tma_load_3d(smem + OFF_PK, &map_pk, bar_k, 0, band0, hh);
-          tma_load_3d(smem + OFF_PQ, &map_pq, bar_k, 0, band0, hh);
+          mbar_arrive_expect_tx(bar_pk, 32768);
+          tma_load_3d(smem + OFF_PK, &map_pk, bar_pk, 0, i0 - kb * 128 - 127 + p.rel_off, hh);
         }
       };
       auto load_v = [&](int kb) {
         mbar_arrive_expect_tx(bar_v, 16384);
         tma_load_4d(smem + OFF_V, &map_v, bar_v, 0, hh, kb * 128, b);
       };
-      mbar_arrive_expect_tx(bar_q, 16384);
-      tma_load_4d(smem + OFF_Q, &map_q, bar_q, 0, hh, i0, b);
-      load_k(0);
-      load_v(0);
-      mbar_wait(bar_q, 0);
-      for (int kb = 0; kb < p.nkb; ++kb) {
-        const uint32_t ph = kb & 1;
-        mbar_wait(bar_k, ph);
-        tc_fence_after();
+      auto issue_mma1 = [&]() {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tmem + TM_S, make_smem_desc_sw128(sQ + k * 32, 16, 1024),
@@ -131,13 +163,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                       make_smem_desc_sw128(sPQ + k * 32, 16, 1024), idesc_band, k > 0);
         }
         umma_commit(bar_mma1);
+      };
+      mbar_arrive_expect_tx(bar_q, 16384);
+      tma_load_4d(smem + OFF_Q, &map_q, bar_q, 0, hh, i0, b);
+      load_k(0);
+      load_pk(0);
+      load_v(0);
+      mbar_wait(bar_q, 0);
+      mbar_wait(bar_k, 0);
+      tc_fence_after();
+      issue_mma1();
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        const uint32_t ph = kb & 1;
+        const bool has_next = kb + 1 < p.nkb;
+        mbar_wait(bar_mma1, ph);      // S / X2 of this block are complete: the K and PQ tiles are free
+        if (has_next) load_k(kb + 1);
         if (kb > 0) {
           // the previous block's P.V (both halves) must retire before its V tile is overwritten
           mbar_wait(&bar_mma3[0], (kb - 1) & 1);
           mbar_wait(&bar_mma3[1], (kb - 1) & 1);
           load_v(kb);
         }
-        mbar_wait(bar_xfree, ph);
+        if constexpr (REL) mbar_wait(bar_pk, ph);
+        mbar_wait(bar_xfree, ph);     // X2 has been staged: its TMEM columns take X1
         tc_fence_after();
         if constexpr (REL) {
 #pragma unroll
@@ -146,8 +194,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                       make_smem_desc_sw128(sPK + k * 32, 16, 1024), idesc_band, k > 0);
         }
         umma_commit(bar_mma2);
-        mbar_wait(bar_mma2, ph);  // K / PK / PQ tiles are free again
-        if (kb + 1 < p.nkb) load_k(kb + 1);
+        if (has_next) {
+          if constexpr (REL) {
+            mbar_wait(bar_mma2, ph);  // the PK tile is free
+            load_pk(kb + 1);
+          }
+          // next block's S / X2 as soon as every warp has pulled this block's S and X1 out of TMEM
+          mbar_wait(bar_sfree, ph);
+          mbar_wait(bar_k, (kb + 1) & 1);
+          tc_fence_after();
+          issue_mma1();
+        }
         mbar_wait(bar_v, ph);
 #pragma unroll 1
         for (int g = 0; g < 2; ++g) {
@@ -163,8 +220,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp < 8) {
+  } else {
     // ============ softmax warpgroups: thread = query row, warpgroup g = key columns [64g, 64g+64) ============
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AT_REGS_SOFTMAX));
     const int g = warp >> 2, wq = warp & 3;
     const int a = wq * 32 + lane;        // row in tile == TMEM lane
     const int i = i0 + a;
@@ -173,10 +231,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     const uint32_t rowid = static_cast<uint32_t>((b * p.h + hh) * p.L + i);
     const bool do_drop = p.drop_thresh16 != 0;
     const uint32_t rowkey = drop_row_key_raw(rowid, p.seed_lo, p.seed_hi, p.off_lo, p.off_hi);
-    float m_run = -INFINITY, l_run = 0.0f;
+    float m_run = -INFINITY, l_run = 0.0f, alpha_pend = 1.0f;
     float o[64];
 #pragma unroll
     for (int k = 0; k < 64; ++k) o[k] = 0.0f;
+    // o = o * alpha + (P.V of block kb): issued one block late so that the MMA never has to be waited for
+    auto accumulate_o = [&](int kb) {
+      mbar_wait(&bar_mma3[g], kb & 1);
+      tc_fence_after();
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(lane_base + TM_O + 64 * g, va);
+      tmem_ld_32x32(lane_base + TM_O + 64 * g + 32, vb);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        o[e] = fmaf(o[e], alpha_pend, __uint_as_float(va[e]));
+        o[32 + e] = fmaf(o[32 + e], alpha_pend, __uint_as_float(vb[e]));
+      }
+      tc_fence_before();
+    };
 
     for (int kb = 0; kb < p.nkb; ++kb) {
       const uint32_t ph = kb & 1;
@@ -193,67 +266,67 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       // ---- p2c: lane = KEY row a of X2; scatter its 160-column window into T2[query][key].
       //      Window offset t = 32q + e is valid for 31 - lane <= t < 159 - lane: chunk 0 needs e >= 31 - lane,
       //      chunks 1-3 are valid for every lane, chunk 4 needs e < 31 - lane.  (g = 0: chunks 0-2, g = 1: 3-4.)
+      //      The TMEM load of the next chunk is in flight while the current one is stored.
       if constexpr (REL) {
-#pragma unroll 1
-        for (int q = (g == 0 ? 0 : 3); q < (g == 0 ? 3 : 5); ++q) {
-          uint32_t v[32];
-          tmem_ld_32x32(lane_base + TM_X + (96 - 32 * wq + 32 * q), v);
+        uint32_t va[32], vb[32];
+        const uint32_t xbase = lane_base + TM_X + (96 - 32 * wq);
+        __half* dst = T2 + (lane - 31) * T_PITCH + a;   // chunk q, element e -> dst[(32 q + e) * T_PITCH]
+        const int thr = 31 - lane;
+        if (g == 0) {
+          tmem_ld_32x32(xbase, va);
           tmem_ld_wait();
-          __half* dst = T2 + (32 * q + lane - 31) * T_PITCH + a;   // element e -> dst[e * T_PITCH]
-          const int thr = 31 - lane;
-          if (q == 0) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (e >= thr) dst[e * T_PITCH] = __float2half_rn(__uint_as_float(v[e]));
-          } else if (q == 4) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (e < thr) dst[e * T_PITCH] = __float2half_rn(__uint_as_float(v[e]));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) dst[e * T_PITCH] = __float2half_rn(__uint_as_float(v[e]));
-          }
+          tmem_ld_32x32(xbase + 32, vb);
+          stage_p2c<0>(dst, va, thr);
+          tmem_ld_wait();
+          tmem_ld_32x32(xbase + 64, va);
+          stage_p2c<1>(dst + 32 * T_PITCH, vb, thr);
+          tmem_ld_wait();
+          stage_p2c<1>(dst + 64 * T_PITCH, va, thr);
+        } else {
+          tmem_ld_32x32(xbase + 96, va);
+          tmem_ld_wait();
+          tmem_ld_32x32(xbase + 128, vb);
+          stage_p2c<1>(dst + 96 * T_PITCH, va, thr);
+          tmem_ld_wait();
+          stage_p2c<2>(dst + 128 * T_PITCH, vb, thr);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_xfree);
+      if (kb > 0) accumulate_o(kb - 1);
       mbar_wait(bar_mma2, ph);
       tc_fence_after();
       // ---- c2p: lane = QUERY row a of X1; keys b = a + 127 - c.  Warpgroup g needs b in [64g, 64g+64):
       //      3 chunks starting at column 32*wq + 64*(1-g); key of element e in chunk q: 64g + lane + 63 - 32q - e.
       //      chunk 0 needs e >= lane, chunk 1 is valid for every lane, chunk 2 needs e < lane.
       if constexpr (REL) {
-#pragma unroll 1
-        for (int q = 0; q < 3; ++q) {
-          uint32_t v[32];
-          tmem_ld_32x32(lane_base + TM_X + 32 * wq + 64 * (1 - g) + 32 * q, v);
-          tmem_ld_wait();
-          __half* dst = T1 + a * T_PITCH + 64 * g + lane + 63 - 32 * q;   // element e -> dst[-e]
-          if (q == 0) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (e >= lane) dst[-e] = __float2half_rn(__uint_as_float(v[e]));
-          } else if (q == 2) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (e < lane) dst[-e] = __float2half_rn(__uint_as_float(v[e]));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) dst[-e] = __float2half_rn(__uint_as_float(v[e]));
-          }
-        }
+        uint32_t va[32], vb[32];
+        const uint32_t xbase = lane_base + TM_X + 32 * wq + 64 * (1 - g);
+        __half* dst = T1 + a * T_PITCH + 64 * g + lane + 63;   // chunk q, element e -> dst[-32 q - e]
+        tmem_ld_32x32(xbase, va);
+        tmem_ld_wait();
+        tmem_ld_32x32(xbase + 32, vb);
+        stage_c2p<0>(dst, va, lane);
+        tmem_ld_wait();
+        tmem_ld_32x32(xbase + 64, va);
+        stage_c2p<1>(dst - 32, vb, lane);
+        tmem_ld_wait();
+        stage_c2p<2>(dst - 64, va, lane);
       }
+      // ---- this warpgroup's 64 scores of the row, straight into registers (both TMEM loads in flight at once)
+      uint32_t sv[2][32];
+      tmem_ld_32x32(lane_base + TM_S + 64 * g, sv[0]);
+      tmem_ld_32x32(lane_base + TM_S + 64 * g + 32, sv[1]);
       named_bar_sync(1, 256);  // T2 / kmask were written by other threads
-      // ---- pass A: combine the three terms, mask, row max over this warpgroup's 64 keys; park s in TMEM
+      tmem_ld_wait();
+      // ---- pass A: combine the three terms, mask, row max over this warpgroup's 64 keys
       float mblk = -INFINITY;
-#pragma unroll 1
+#pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int c0 = 64 * g + 32 * q;
-        uint32_t v[32];
-        tmem_ld_32x32(lane_base + TM_S + c0, v);
+        uint32_t (&v)[32] = sv[q];
         const uint32_t kbits = valid_q ? reinterpret_cast<const uint32_t*>(kmask)[2 * g + q] : 0u;
-        tmem_ld_wait();
         if constexpr (REL) {
           const uint4* t1 = reinterpret_cast<const uint4*>(T1 + a * T_PITCH + c0);
           const uint4* t2 = reinterpret_cast<const uint4*>(T2 + a * T_PITCH + c0);
@@ -273,13 +346,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             }
           }
         }
+        if (kbits == 0xffffffffu) {
+          // every key of the chunk is attended (the common case): no per-element select
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float sc = ((kbits >> e) & 1u) ? __uint_as_float(v[e]) * p.scale_log2 : -INFINITY;
-          mblk = fmaxf(mblk, sc);
-          v[e] = __float_as_uint(sc);
+          for (int e = 0; e < 32; ++e) {
+            const float sc = __uint_as_float(v[e]) * p.scale_log2;
+            mblk = fmaxf(mblk, sc);
+            v[e] = __float_as_uint(sc);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float sc = ((kbits >> e) & 1u) ? __uint_as_float(v[e]) * p.scale_log2 : -INFINITY;
+            mblk = fmaxf(mblk, sc);
+            v[e] = __float_as_uint(sc);
+          }
         }
-        tmem_st_32x32(lane_base + TM_S + c0, v);
         if (p.s_out != nullptr && i < p.L) {
           float4* dst = reinterpret_cast<float4*>(p.s_out + (((long long)b * p.h + hh) * p.L + i) * p.lp + j0 + c0);
 #pragma unroll
@@ -288,22 +370,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                                   __uint_as_float(v[4 * gg + 2]), __uint_as_float(v[4 * gg + 3]));
         }
       }
-      tmem_st_wait();
+      // S, X1 and the staging buffers of this block are consumed: the next block's S / X2 may be issued
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sfree);
       const float m_new = fmaxf(m_run, mblk);
       const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
-      const float alpha = exp2f(m_run - m_use);
+      const float alpha = ex2_approx(m_run - m_use);   // ex2(-inf) = +0
       // ---- pass B: probabilities -> bf16 A-operand chunk g (128B-swizzled, K-major), partial row sum
       float rsum = 0.0f;
-#pragma unroll 1
+#pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int c0 = 64 * g + 32 * q;
-        uint32_t v[32];
-        tmem_ld_32x32(lane_base + TM_S + c0, v);
-        tmem_ld_wait();
         float pr[32];
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          pr[e] = ex2_approx(__uint_as_float(v[e]) - m_use);   // ex2(-inf) = +0
+          pr[e] = ex2_approx(__uint_as_float(sv[q][e]) - m_use);   // ex2(-inf) = +0
           rsum += pr[e];
         }
         if (do_drop) {
@@ -326,24 +408,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
       l_run = l_run * alpha + rsum;
       m_run = m_new;
+      alpha_pend = alpha;
       fence_proxy_async_smem();  // generic-proxy writes of P -> visible to the MMA (async proxy)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_pready[g]);
-      // ---- O_g accumulation in registers (rescaled)
-      mbar_wait(&bar_mma3[g], ph);
-      tc_fence_after();
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        uint32_t v[32];
-        tmem_ld_32x32(lane_base + TM_O + 64 * g + 32 * q, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) o[32 * q + e] = o[32 * q + e] * alpha + __uint_as_float(v[e]);
-      }
     }
+    accumulate_o(p.nkb - 1);
     // ---- merge the two key halves (flash-decoding style) through shared memory, then write ctx / LSE
-    tc_fence_before();
     named_bar_sync(1, 256);                      // all staging reads are done: reuse T1/T2 as exchange space
     float* xch = reinterpret_cast<float*>(smem + OFF_T1);   // [128][66] floats = 33.8 KB <= 2 * 34.8 KB
     if (g == 1) {

@@ -47,12 +47,24 @@
 namespace fb {
 
 // ---- skewed SWIZZLE_NONE staging buffer for Z1 / Z2 (bytes) ----
-static constexpr uint32_t Z_LBO = 128;              // K-adjacent core matrices (8 k-elements each)
-static constexpr uint32_t Z_SP = 4000;              // storage stride of a row group: 31.25 units; not a multiple of
-                                                    // 128 so that the four row groups of a warp hit different banks
-static constexpr uint32_t Z_SBO = Z_SP + Z_LBO;     // group stride the tensor core is told (skew of one unit per group)
-static constexpr uint32_t Z_PRE = 15 * Z_LBO;       // zero units in front of group 0
-static constexpr uint32_t Z_BYTES = 66048;          // >= Z_PRE + 15 * Z_SP + 32 * Z_LBO = 66016
+// LBO: K-adjacent core matrices (8 k-elements each).  SP: storage stride of a row group; >= 31.25 LBO so that the
+// 32-unit view of a group never sees a neighbour's window, and chosen so that the row groups of a warp hit different
+// banks.  SBO = SP + LBO is the group stride the tensor core is told (skew of one unit per group).  PRE: zero units in
+// front of group 0.  BYTES >= PRE + 15 SP + 32 LBO.
+// fb_attn_bwd only builds "Z1-type" rows (thread = row): LBO = 128 makes those stores conflict-free.  fb_attn_bwd_rel
+// also scatters Z2 columns (thread = column): with LBO = 128 the four 8-lane groups of a warp land in the same banks
+// (4.5-way conflicts, measured 15 M conflict cycles per launch); LBO = 144 / SP = 4512 makes the Z2 scatter
+// conflict-free at 1.5-way for Z1 (bank simulation of both store patterns: DESIGN.md section 3).
+struct ZFused {
+  static constexpr uint32_t LBO = 128, SP = 4000, SBO = SP + LBO, PRE = 15 * LBO, BYTES = 66048;
+};
+struct ZRel {
+  static constexpr uint32_t LBO = 144, SP = 4512, SBO = SP + LBO, PRE = 15 * LBO, BYTES = 74496;
+};
+static_assert(ZFused::BYTES >= ZFused::PRE + 15 * ZFused::SP + 32 * ZFused::LBO, "Z buffer (fused)");
+static_assert(ZRel::BYTES >= ZRel::PRE + 15 * ZRel::SP + 32 * ZRel::LBO, "Z buffer (rel)");
+static_assert(ZFused::SP * 4 >= 125 * ZFused::LBO && ZRel::SP * 4 >= 125 * ZRel::LBO, "row-group windows overlap");
+static constexpr uint32_t Z_LBO = ZFused::LBO, Z_SBO = ZFused::SBO, Z_BYTES = ZFused::BYTES;   // fb_attn_bwd
 
 __device__ __forceinline__ uint64_t make_smem_desc_none(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -65,37 +77,37 @@ __device__ __forceinline__ uint64_t make_smem_desc_none(uint32_t smem_addr, uint
 
 // Z1 rows are queries: this thread owns row a and W of its values, keys b = j_first + e (j_first % 8 == 0).
 // Window position of key b: y = b + 7 - rho.
-template <int W>
+template <int W, class ZL = ZFused>
 __device__ __forceinline__ void build_z1(uint8_t* z, int a, int j_first, const uint32_t (&dsb)[W / 2]) {
   const int G = a >> 3, rho = a & 7;
-  uint8_t* rowbase = z + Z_PRE + G * Z_SP + rho * 16 + (j_first >> 3) * Z_LBO;
+  uint8_t* rowbase = z + ZL::PRE + G * ZL::SP + rho * 16 + (j_first >> 3) * ZL::LBO;
   uint8_t* off[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int t = 7 - rho + r;
-    off[r] = rowbase + (t >> 3) * Z_LBO + (t & 7) * 2;
+    off[r] = rowbase + (t >> 3) * ZL::LBO + (t & 7) * 2;
   }
 #pragma unroll
   for (int e = 0; e < W; ++e) {
     const uint32_t w = dsb[e >> 1];
-    *reinterpret_cast<uint16_t*>(off[e & 7] + (e >> 3) * Z_LBO) = static_cast<uint16_t>((e & 1) ? (w >> 16) : w);
+    *reinterpret_cast<uint16_t*>(off[e & 7] + (e >> 3) * ZL::LBO) = static_cast<uint16_t>((e & 1) ? (w >> 16) : w);
   }
 }
 // Z2 rows are keys: this thread (query a) contributes one value to each of the rows b = j_first + e, at window
 // position y = a + 7 - (b & 7).
-template <int W>
+template <int W, class ZL = ZFused>
 __device__ __forceinline__ void build_z2(uint8_t* z, int a, int j_first, const uint32_t (&dsb)[W / 2]) {
-  uint8_t* base = z + Z_PRE + (j_first >> 3) * Z_SP;
+  uint8_t* base = z + ZL::PRE + (j_first >> 3) * ZL::SP;
   uint8_t* off[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     const int y = a + 7 - r;
-    off[r] = base + r * 16 + (y >> 3) * Z_LBO + (y & 7) * 2;
+    off[r] = base + r * 16 + (y >> 3) * ZL::LBO + (y & 7) * 2;
   }
 #pragma unroll
   for (int e = 0; e < W; ++e) {
     const uint32_t w = dsb[e >> 1];
-    *reinterpret_cast<uint16_t*>(off[e & 7] + (e >> 3) * Z_SP) = static_cast<uint16_t>((e & 1) ? (w >> 16) : w);
+    *reinterpret_cast<uint16_t*>(off[e & 7] + (e >> 3) * ZL::SP) = static_cast<uint16_t>((e & 1) ? (w >> 16) : w);
   }
 }
 
@@ -553,7 +565,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 // exactly as in fb_attn_bwd and read by the tensor core through the MN-major (transposed) view of the same buffer.
 // ---------------------------------------------------------------------------------------------
 static constexpr int AR_THREADS = 320;   // warps 0-7 compute (thread = row, warpgroup = 64-column half), 8 control, 9 TMEM
-static constexpr uint32_t R_OFF_Q = 0, R_OFF_K = 16384, R_OFF_Z = 32768, R_OFF_BARS = R_OFF_Z + Z_BYTES,
+static constexpr uint32_t R_OFF_Q = 0, R_OFF_K = 16384, R_OFF_Z = 32768, R_OFF_BARS = R_OFF_Z + ZRel::BYTES,
                           AR_SMEM = R_OFF_BARS + 128 + 1024;
 static constexpr uint32_t TR_PK = 0, TR_PQ = 128;   // two [256 x 64] accumulators, each two 128-lane halves of 64 columns
 
@@ -610,7 +622,7 @@ attn_bwd_rel_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   }
   if (warp < 8) {
     const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-    for (uint32_t o = threadIdx.x * 16; o < Z_BYTES; o += 256 * 16) *reinterpret_cast<uint4*>(sz + o) = z4;
+    for (uint32_t o = threadIdx.x * 16; o < ZRel::BYTES; o += 256 * 16) *reinterpret_cast<uint4*>(sz + o) = z4;
   }
   tc_fence_before();
   __syncthreads();
@@ -621,20 +633,22 @@ attn_bwd_rel_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     if (elect_one_sync()) {
       constexpr uint32_t idesc_mn = make_idesc_bf16(128, 64, 1, 1);
       const uint32_t sQ = smem_u32(smem + R_OFF_Q), sK = smem_u32(smem + R_OFF_K), sZ = smem_u32(sz);
-      auto load_qk = [&](int u) {
+      auto load_q = [&](int u) {
         const int pair = u / p.B, bb = u - pair * p.B;
-        const int I = I_first + pair, J = I - d;
         mbar_arrive_expect_tx(bar_q, 16384);
-        tma_load_4d(smem + R_OFF_Q, &map_q, bar_q, 0, hh, I * 128, bb);
-        mbar_arrive_expect_tx(bar_k, 16384);
-        tma_load_4d(smem + R_OFF_K, &map_k, bar_k, 0, hh, J * 128, bb);
+        tma_load_4d(smem + R_OFF_Q, &map_q, bar_q, 0, hh, (I_first + pair) * 128, bb);
       };
-      if (u_begin < u_end) load_qk(u_begin);
+      auto load_k = [&](int u) {
+        const int pair = u / p.B, bb = u - pair * p.B;
+        mbar_arrive_expect_tx(bar_k, 16384);
+        tma_load_4d(smem + R_OFF_K, &map_k, bar_k, 0, hh, (I_first + pair - d) * 128, bb);
+      };
+      if (u_begin < u_end) { load_q(u_begin); load_k(u_begin); }
       for (int u = u_begin; u < u_end; ++u) {
         const uint32_t ph = (u - u_begin) & 1;
         const uint32_t acc = (u > u_begin) ? 1u : 0u;
         // ---- band of gpk += Z1^T . Q_I.  A = Z^T: MN-major SWIZZLE_NONE view of the skewed buffer: M = band index k
-        //      (8-element groups Z_LBO apart -> SBO field), K = the 128 rows (8-row groups Z_SBO apart -> LBO field);
+        //      (8-element groups LBO apart -> SBO field), K = the 128 rows (8-row groups SBO apart -> LBO field);
         //      two M halves of 128 (16 groups each), 8 k-steps of 16 rows
         mbar_wait(bar_q, ph);
         mbar_wait(bar_rdy1, ph);
@@ -643,10 +657,12 @@ attn_bwd_rel_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int mh = 0; mh < 2; ++mh)
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_bf16(tmem + TR_PK + 64 * mh, make_smem_desc_none(sZ + mh * 16 * Z_LBO + k * 2 * Z_SBO, Z_SBO, Z_LBO),
+            umma_bf16(tmem + TR_PK + 64 * mh,
+                      make_smem_desc_none(sZ + mh * 16 * ZRel::LBO + k * 2 * ZRel::SBO, ZRel::SBO, ZRel::LBO),
                       make_smem_desc_sw128(sQ + k * 2048, 16, 1024), idesc_mn, (acc || k > 0) ? 1u : 0u);
         umma_commit(bar_mma1);
         mbar_wait(bar_mma1, ph);
+        if (u + 1 < u_end) load_q(u + 1);   // the Q tile is free: the next one lands while Z2 is built and multiplied
         // ---- band of gpq += Z2^T . K_J
         mbar_wait(bar_k, ph);
         mbar_wait(bar_rdy2, ph);
@@ -655,11 +671,12 @@ attn_bwd_rel_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int mh = 0; mh < 2; ++mh)
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_bf16(tmem + TR_PQ + 64 * mh, make_smem_desc_none(sZ + mh * 16 * Z_LBO + k * 2 * Z_SBO, Z_SBO, Z_LBO),
+            umma_bf16(tmem + TR_PQ + 64 * mh,
+                      make_smem_desc_none(sZ + mh * 16 * ZRel::LBO + k * 2 * ZRel::SBO, ZRel::SBO, ZRel::LBO),
                       make_smem_desc_sw128(sK + k * 2048, 16, 1024), idesc_mn, (acc || k > 0) ? 1u : 0u);
         umma_commit(bar_mma2);
         mbar_wait(bar_mma2, ph);
-        if (u + 1 < u_end) load_qk(u + 1);
+        if (u + 1 < u_end) load_k(u + 1);
       }
     }
     __syncwarp();
@@ -672,6 +689,15 @@ attn_bwd_rel_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       const int pair = u / p.B, bb = u - pair * p.B;
       const int I = I_first + pair, J = I - d;
       const int i = I * 128 + a;
+      if (u + 1 < u_end) {
+        // hint the next unit's dS' row segment (one 128-byte line per thread) into L2: its load latency is otherwise
+        // the head of every unit's dependency chain
+        const int pn = (u + 1) / p.B, bn = (u + 1) - pn * p.B;
+        const int in = (I_first + pn) * 128 + a;
+        if (in < p.L)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.ds + (((long long)bn * p.h + hh) * p.L + in) * p.lp +
+                                                         (I_first + pn - d) * 128 + 64 * g));
+      }
       uint32_t dsb[32];
       if (i < p.L) {
         const uint4* src = reinterpret_cast<const uint4*>(p.ds + (((long long)bb * p.h + hh) * p.L + i) * p.lp + J * 128 + 64 * g);
@@ -685,10 +711,10 @@ attn_bwd_rel_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int q = 0; q < 32; ++q) dsb[q] = 0u;
       }
       if (u > u_begin) mbar_wait(bar_mma2, ph ^ 1);   // previous unit's MMAs no longer read the staging buffer
-      build_z1<64>(sz, a, 64 * g, dsb);
+      build_z1<64, ZRel>(sz, a, 64 * g, dsb);
       compute_arrive(bar_rdy1, lane);
       mbar_wait(bar_mma1, ph);
-      build_z2<64>(sz, a, 64 * g, dsb);
+      build_z2<64, ZRel>(sz, a, 64 * g, dsb);
       compute_arrive(bar_rdy2, lane);
     }
     // ---- flush the band accumulators (thread = band index k = 128 mh + a, warpgroup = 32-column half)

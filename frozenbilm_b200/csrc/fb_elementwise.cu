@@ -120,6 +120,16 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
   for (int it = 0; it < row_iters; ++it) {
     const int row = (it * gridDim.x + blockIdx.x) * 4 + pair;
     const bool live = row < M;                       // both warps of a pair agree; barriers stay uniform
+    {
+      // the rows of the NEXT iteration are pulled into L2 now (one bulk prefetch per row and operand), so that
+      // HBM keeps streaming while this iteration reduces, re-reads and stores: the two-pass structure otherwise
+      // leaves the memory pipe idle about half of the time (measured 3.5 of 6.5 TB/s)
+      const int nrow = ((it + 1) * gridDim.x + blockIdx.x) * 4 + pair;
+      if (half == 0 && lane == 0 && nrow < M) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + (long long)nrow * H), "r"(H * 4) : "memory");
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(dy + (long long)nrow * H), "r"(H * 4) : "memory");
+      }
+    }
     float mean = 0.f, rstd = 0.f, rm = 0.f;
     const float4* xr = nullptr;
     const float4* dr = nullptr;

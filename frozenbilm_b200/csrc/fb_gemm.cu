@@ -71,11 +71,13 @@ __device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int& 
 }
 
 __device__ __forceinline__ void apply_dropout32(const DropSpec& d, int row, int col0, float (&v)[32]) {
+  const uint32_t rowkey = drop_row_key(d, (uint32_t)row);   // same decisions as drop_keep8(d, row, group)
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const uint32_t keep = drop_keep8(d, (uint32_t)row, (uint32_t)(col0 + 8 * g) >> 3);
+    float f[8];
+    drop_factors8(rowkey, (uint32_t)(col0 + 8 * g) >> 3, d.thresh16, d.inv_keep, f);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[8 * g + e] = ((keep >> e) & 1) ? v[8 * g + e] * d.inv_keep : 0.0f;
+    for (int e = 0; e < 8; ++e) v[8 * g + e] *= f[e];
   }
 }
 

@@ -1,7 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python scripts/gpu_attn_bwd_diag.py > gpurun_out/attn_bwd_diag.log 2>&1; echo "diag exit $?"; grep -c "nan: 0" gpurun_out/attn_bwd_diag.log; grep -E "EXCEPTION" gpurun_out/attn_bwd_diag.log | head
-timeout 300 python scripts/gpu_attn_bwd_timeline.py > gpurun_out/attn_bwd_timeline.log 2>&1; echo "timeline exit $?"
-cat gpurun_out/attn_bwd_timeline.log | cut -c1-420
-( timeout 900 python -m pytest tests/test_attention_bwd_gpu.py -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log )
-tail -4 gpurun_out/pytest_gpu.log
+rm -f gpurun_out/*.ncu-rep
+timeout 300 python scripts/gpu_attn_time.py > gpurun_out/attn_time.log 2>&1; echo "attn time exit $?"; cat gpurun_out/attn_time.log | tail -6
+( timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log )
+tail -6 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; cut -c1-400 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+    --log-file gpurun_out/launches.csv python bench.py --profile-step > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches exit $?"
+python scripts/summarize_launches.py gpurun_out/launches.csv 2>/dev/null | head -24
