@@ -362,12 +362,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             v[e] = __float_as_uint(sc);
           }
         }
-        if (p.s_out != nullptr && i < p.L) {
-          float4* dst = reinterpret_cast<float4*>(p.s_out + (((long long)b * p.h + hh) * p.L + i) * p.lp + j0 + c0);
+      }
+      if (p.s_out != nullptr) {
+        // Saved scores for the backward.  A direct store would touch 32 different 128-byte lines per instruction
+        // (thread = row): instead each warp transposes its 32 x 32 chunk through the staging bytes its own lanes
+        // have just consumed (T1 / T2 rows a, columns [64g, 64g+64): private to the warp, so __syncwarp suffices)
+        // and writes four complete lines per instruction.
+        const int rowb = (T_PITCH * 2);
 #pragma unroll
-          for (int gg = 0; gg < 8; ++gg)
-            dst[gg] = make_float4(__uint_as_float(v[4 * gg]), __uint_as_float(v[4 * gg + 1]),
-                                  __uint_as_float(v[4 * gg + 2]), __uint_as_float(v[4 * gg + 3]));
+        for (int q = 0; q < 2; ++q) {
+          uint8_t* mine = reinterpret_cast<uint8_t*>(q == 0 ? T1 : T2) + a * rowb + 128 * g;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            *reinterpret_cast<float4*>(mine + 16 * u) =
+                make_float4(__uint_as_float(sv[q][4 * u]), __uint_as_float(sv[q][4 * u + 1]),
+                            __uint_as_float(sv[q][4 * u + 2]), __uint_as_float(sv[q][4 * u + 3]));
+        }
+        __syncwarp();
+        const int rr = lane >> 3, uu = lane & 7;
+        float* gbase = p.s_out + (((long long)b * p.h + hh) * p.L + i0 + 32 * wq) * p.lp + j0 + 64 * g + 4 * uu;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint8_t* tb = reinterpret_cast<const uint8_t*>(q == 0 ? T1 : T2) + (32 * wq) * rowb + 128 * g + 16 * uu;
+#pragma unroll
+          for (int st = 0; st < 8; ++st) {
+            const int r = 4 * st + rr;
+            const float4 x = *reinterpret_cast<const float4*>(tb + r * rowb);
+            if (i0 + 32 * wq + r < p.L) *reinterpret_cast<float4*>(gbase + (long long)r * p.lp + 32 * q) = x;
+          }
         }
       }
       // S, X1 and the staging buffers of this block are consumed: the next block's S / X2 may be issued

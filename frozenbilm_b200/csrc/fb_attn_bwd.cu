@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
                 const __grid_constant__ CUtensorMap map_pk, const __grid_constant__ CUtensorMap map_pq,
-                const __grid_constant__ AttnBwdFusedParams p) {
+                const __grid_constant__ CUtensorMap map_ds, const __grid_constant__ AttnBwdFusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF_BARS);
@@ -217,18 +217,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             (n == k) ? static_cast<uint16_t>(0x3F80) : static_cast<uint16_t>(0);
       }
     }
+    // Row statistics, computed ONCE per row: column group g takes query tile I = g (NG = 4 covers L <= 512), all 16
+    // loads of the row in flight together, and hands the result to the other groups through the (still unused)
+    // [Pd | dS'] staging area.  (Every group used to walk every tile with 8 dependent load round trips per tile:
+    // 16 % of the kernel's warp samples sat in this prologue.)
     const int a = (warp & 3) * 32 + lane;
-#pragma unroll
-    for (int I = 0; I < 4; ++I) {
+    {
+      const int I = warp >> 2;
       const int r = I * 128 + a;
-      float d = 0.0f;
+      float d = 0.0f, l = INFINITY;
       if (I < nb && r < p.L) {
         const uint4* o = reinterpret_cast<const uint4*>(p.ctx + ((long long)b * p.L + r) * p.ldc + hh * 64);
         const uint4* g = reinterpret_cast<const uint4*>(p.dctx + ((long long)b * p.L + r) * p.ldc + hh * 64);
-#pragma unroll 1
+        uint4 ov[8], gv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { ov[u] = __ldg(o + u); gv[u] = __ldg(g + u); }
+        l = p.lse[((long long)b * p.h + hh) * p.L + r];
+#pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const uint4 ov = __ldg(o + u), gv = __ldg(g + u);
-          const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+          const uint32_t ow[4] = {ov[u].x, ov[u].y, ov[u].z, ov[u].w}, gw[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             const float2 of = unpack_bf16(ow[w]), gf = unpack_bf16(gw[w]);
@@ -236,10 +243,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
             d = fmaf(of.y, gf.y, d);
           }
         }
-        Dr[I] = d;
-        Lr[I] = p.lse[((long long)b * p.h + hh) * p.L + r];
+      }
+      float2* xs = reinterpret_cast<float2*>(s0);
+      xs[I * 128 + a] = make_float2(d, l);
+    }
+    named_bar_sync(1, NCT);
+    {
+      const float2* xs = reinterpret_cast<const float2*>(s0);
+#pragma unroll
+      for (int I = 0; I < 4; ++I) {
+        const float2 v = xs[I * 128 + a];
+        Dr[I] = v.x; Lr[I] = v.y;
       }
     }
+    named_bar_sync(1, NCT);   // every thread has its copy: the staging area may be overwritten
   }
   tc_fence_before();
   __syncthreads();
@@ -249,6 +266,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   if (warp == 4 * NG) {
     if (elect_one_sync()) {
       // ======================= TMA + MMA control thread =======================
+      if constexpr (REL) { if (p.ds_out != nullptr) tma_prefetch_desc(&map_ds); }
       constexpr uint32_t idesc_dp = make_idesc_bf16(128, 128, 0, 0);   // dP = dO . V^T       (A, B K-major)
       constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);    // A K-major, B MN-major (dS.K, Z.band)
       constexpr uint32_t idesc_mn = make_idesc_bf16(128, 64, 1, 1);    // A, B MN-major         (Pd^T.dO, dS^T.Q)
@@ -299,6 +317,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         mbar_wait(bar_rdyA, ph);
         tc_fence_after();
         FB_STAMP(2);
+        if constexpr (REL) {
+          // dS' for fb_attn_bwd_rel: the staged [128 x 64] halves ARE 128B-swizzled TMA tiles, so two bulk stores
+          // write them (rows >= L clipped by the map) instead of 64 scattered 16-byte stores per warp, which cost
+          // ~2000 LSU cycles per tile pair on the critical path
+          if (p.ds_out != nullptr) {
+            tma_store_4d(&map_ds, s0 + 32768, J * 128, I * 128, hh, b);
+            tma_store_4d(&map_ds, s0 + 32768 + 16384, J * 128 + 64, I * 128, hh, b);
+            tma_store_commit();
+          }
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // A = Pd^T: MN-major (keys contiguous), two 64-key chunks 16 KB apart
           umma_bf16(tmem + TB_DV, make_smem_desc_sw128(sS0 + k * 2048, 16384, 1024),
@@ -360,12 +388,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           for (int k = 0; k < 16; ++k)
             umma_bf16(tmem + TB_DK, make_smem_desc_none(sZ + k * 2 * Z_LBO, Z_LBO, Z_SBO),
                       make_smem_desc_sw128(sS0 + k * 2048, 16, 1024), idesc_kn, 1u);
+          tma_store_wait_read0();   // the dS' stores have left shared memory before the staging area is released
           umma_commit(bar_mmaC);
           FB_STAMP(10);
           mbar_wait(bar_mmaC, ph);
           FB_STAMP(11);
         }
       }
+      tma_store_wait_all();   // the dS' bulk stores are globally complete before the CTA retires
     }
     __syncwarp();
   } else if (warp < 4 * NG) {
@@ -403,7 +433,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const int J = t / nb, I = t - J * nb;
       const uint32_t ph = t & 1;
       const int i = I * 128 + a, j0 = J * 128;
-      const bool row_ok = i < p.L;
       const long long srow = ((long long)b * p.h + hh) * p.L + i;
       const bool stamp = (threadIdx.x == 0);
       if (stamp) FB_STAMP(16);
@@ -479,11 +508,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         if (stamp) FB_STAMP(21);
       } else {
         compute_arrive(bar_rdyA, lane);
-      }
-      if (p.ds_out != nullptr && row_ok) {
-        uint4* dst = reinterpret_cast<uint4*>(p.ds_out + srow * p.lp + j0 + CW * g);
-#pragma unroll
-        for (int u = 0; u < CW / 8; ++u) dst[u] = make_uint4(dsb[4 * u], dsb[4 * u + 1], dsb[4 * u + 2], dsb[4 * u + 3]);
       }
       if constexpr (REL) {
         if (stamp) FB_STAMP(22);
@@ -774,7 +798,7 @@ int attn_bwd(const fb_attn_bwd_args* a, cudaStream_t st) {
              "fb_attn_bwd: relative tables too small (rel_rows=%d rel_off=%d L=%d)", a->rel_rows, a->rel_off, a->L);
   FB_REQUIRE(a->lddq % 8 == 0 && a->lddk % 8 == 0 && a->lddv % 8 == 0 && a->ldo % 8 == 0,
              "fb_attn_bwd: row pitches must be multiples of 8 elements");
-  CUtensorMap mq, mk, mv, mdo, mpk, mpq;
+  CUtensorMap mq, mk, mv, mdo, mpk, mpq, mds;
   int rc;
   if ((rc = make_rows_map(&mq, a->Q, a->ldq, a->B, a->L, a->h))) return rc;
   if ((rc = make_rows_map(&mk, a->K, a->ldk, a->B, a->L, a->h))) return rc;
@@ -785,6 +809,14 @@ int attn_bwd(const fb_attn_bwd_args* a, cudaStream_t st) {
     if ((rc = make_band_map(&mpq, a->PQrel, a->rel_rows, a->h))) return rc;
   } else {
     mpk = mk; mpq = mk;   // never dereferenced by the plain-attention instantiation
+  }
+  mds = mk;
+  if (rel && a->ds_out) {
+    // dS' [B, h, L, lp] as {key, query, head, batch} with a [64 keys x 128 queries] box (store side)
+    const uint64_t dims[4] = {(uint64_t)lpad, (uint64_t)a->L, (uint64_t)a->h, (uint64_t)a->B};
+    const uint64_t strides[3] = {(uint64_t)lpad, (uint64_t)lpad * a->L, (uint64_t)lpad * a->L * a->h};
+    const uint32_t box[4] = {64, 128, 1, 1};
+    if ((rc = make_tmap_bf16_nd(&mds, a->ds_out, 4, dims, strides, box))) return rc;
   }
   AttnBwdFusedParams p;
   memset(&p, 0, sizeof(p));
@@ -806,9 +838,9 @@ int attn_bwd(const fb_attn_bwd_args* a, cudaStream_t st) {
   }
   dim3 grid(a->h, a->B);
   if (rel)
-    attn_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, st>>>(mq, mk, mv, mdo, mpk, mpq, p);
+    attn_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, st>>>(mq, mk, mv, mdo, mpk, mpq, mds, p);
   else
-    attn_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, st>>>(mq, mk, mv, mdo, mpk, mpq, p);
+    attn_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, st>>>(mq, mk, mv, mdo, mpk, mpq, mds, p);
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
