@@ -358,6 +358,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           for (int k = 0; k < 16; ++k)
             umma_bf16(tmem + TB_DQ + 64 * I, make_smem_desc_none(sZ + k * 2 * Z_LBO, Z_LBO, Z_SBO),
                       make_smem_desc_sw128(sPK + k * 2048, 16, 1024), idesc_kn, 1u);
+          tma_store_wait_read0();   // the dS' bulk stores have left shared memory before bar_mmaB releases that half
           umma_commit(bar_mmaB);
           FB_STAMP(5);
         }
@@ -388,7 +389,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           for (int k = 0; k < 16; ++k)
             umma_bf16(tmem + TB_DK, make_smem_desc_none(sZ + k * 2 * Z_LBO, Z_LBO, Z_SBO),
                       make_smem_desc_sw128(sS0 + k * 2048, 16, 1024), idesc_kn, 1u);
-          tma_store_wait_read0();   // the dS' stores have left shared memory before the staging area is released
           umma_commit(bar_mmaC);
           FB_STAMP(10);
           mbar_wait(bar_mmaC, ph);
@@ -418,13 +418,53 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       return reinterpret_cast<const float4*>(p.s2 + (((long long)b * p.h + hh) * p.L + it) * p.lp + Jt * 128 + CW * g);
     };
     auto load_scores = [&](int tt) {
-      const float4* src = score_ptr(tt);
-      if (src != nullptr) {
+      if constexpr (REL) {
+        // Coalesced: a direct load (thread = row, 128 contiguous bytes each) touches 32 different lines per
+        // instruction and kept the LSU busy for ~4000 cycles per tile pair on the critical path.  Instead 4 lanes
+        // fetch 64 bytes of one row (8 rows per instruction), the warp exchanges the pieces through the 64 bytes per
+        // row that its own lanes own in the dS' half of the staging area (free once bar_mmaB has completed:
+        // the content / transpose MMAs and the dS' bulk store no longer read it), two rounds of 16 columns.
+        const int Jt = tt / nb, It = tt - Jt * nb;
+        if (tt >= npairs) {
 #pragma unroll
-        for (int u = 0; u < CW / 4; ++u) sc[u] = __ldg(src + u);
+          for (int u = 0; u < CW / 4; ++u) sc[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+          return;
+        }
+        const int c0 = CW * g;
+        uint8_t* area = s0 + 32768 + (c0 >> 6) * 16384;       // this column group's 64-key chunk of dS'
+        const int ub = (c0 & 63) >> 3;                          // first of its four 16-byte units in a row
+        const int rsub = lane >> 2, piece = lane & 3;
+        const float* gsrc = p.s2 + (((long long)b * p.h + hh) * p.L + It * 128 + 32 * wq) * p.lp + Jt * 128 + c0 + 4 * piece;
+        const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          float4 tmp[4];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int r = 8 * m + rsub;                         // row inside this warp's 32
+            tmp[m] = (It * 128 + 32 * wq + r < p.L)
+                         ? __ldg(reinterpret_cast<const float4*>(gsrc + (long long)r * p.lp + 16 * k)) : ninf;
+          }
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int ra = 32 * wq + 8 * m + rsub;
+            *reinterpret_cast<float4*>(area + ra * 128 + (((ub + piece) ^ (ra & 7)) << 4)) = tmp[m];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            sc[4 * k + u] = *reinterpret_cast<const float4*>(area + a * 128 + (((ub + u) ^ (a & 7)) << 4));
+          __syncwarp();
+        }
       } else {
+        const float4* src = score_ptr(tt);
+        if (src != nullptr) {
 #pragma unroll
-        for (int u = 0; u < CW / 4; ++u) sc[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+          for (int u = 0; u < CW / 4; ++u) sc[u] = __ldg(src + u);
+        } else {
+#pragma unroll
+          for (int u = 0; u < CW / 4; ++u) sc[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
       }
     };
     load_scores(0);
@@ -755,9 +795,11 @@ attn_bwd_rel_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         tmem_ld_32x32(lane_base + (w < 2 ? TR_PK : TR_PQ) + 64 * mh + 32 * g, v);
         tmem_ld_wait();
         if (k < 255 && row >= 0 && row < p.rel_rows) {
-          float* dst = (w < 2 ? p.gpk : p.gpq) + ((long long)hh * p.rel_rows + row) * 64 + 32 * g;
+          float4* dst = reinterpret_cast<float4*>((w < 2 ? p.gpk : p.gpq) + ((long long)hh * p.rel_rows + row) * 64 + 32 * g);
 #pragma unroll
-          for (int e = 0; e < 32; ++e) atomicAdd(dst + e, __uint_as_float(v[e]) * p.scale);
+          for (int e = 0; e < 8; ++e)   // 16-byte vector reductions (red.global.add.v4.f32): 4x fewer L2 atomics
+            atomicAdd(dst + e, make_float4(__uint_as_float(v[4 * e]) * p.scale, __uint_as_float(v[4 * e + 1]) * p.scale,
+                                           __uint_as_float(v[4 * e + 2]) * p.scale, __uint_as_float(v[4 * e + 3]) * p.scale));
         }
       }
     }
