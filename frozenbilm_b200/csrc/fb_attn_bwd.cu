@@ -223,29 +223,40 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // 16 % of the kernel's warp samples sat in this prologue.)
     const int a = (warp & 3) * 32 + lane;
     {
+      // 8 lanes cover the 128 bytes of one row (4 rows per load instruction: full lines, not 32 scattered 16-byte
+      // pieces), partial dot products are combined with three shuffles
       const int I = warp >> 2;
-      const int r = I * 128 + a;
-      float d = 0.0f, l = INFINITY;
-      if (I < nb && r < p.L) {
-        const uint4* o = reinterpret_cast<const uint4*>(p.ctx + ((long long)b * p.L + r) * p.ldc + hh * 64);
-        const uint4* g = reinterpret_cast<const uint4*>(p.dctx + ((long long)b * p.L + r) * p.ldc + hh * 64);
-        uint4 ov[8], gv[8];
+      const int rsub = lane >> 3, piece = lane & 7;
+      float2* xs = reinterpret_cast<float2*>(s0);
+      uint4 ov[8], gv[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { ov[u] = __ldg(o + u); gv[u] = __ldg(g + u); }
-        l = p.lse[((long long)b * p.h + hh) * p.L + r];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint32_t ow[4] = {ov[u].x, ov[u].y, ov[u].z, ov[u].w}, gw[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const float2 of = unpack_bf16(ow[w]), gf = unpack_bf16(gw[w]);
-            d = fmaf(of.x, gf.x, d);
-            d = fmaf(of.y, gf.y, d);
-          }
+      for (int m = 0; m < 8; ++m) {
+        const int r = I * 128 + (warp & 3) * 32 + 4 * m + rsub;
+        ov[m] = make_uint4(0u, 0u, 0u, 0u);
+        gv[m] = ov[m];
+        if (I < nb && r < p.L) {
+          const long long off = ((long long)b * p.L + r) * p.ldc + hh * 64 + 8 * piece;
+          ov[m] = __ldg(reinterpret_cast<const uint4*>(p.ctx + off));
+          gv[m] = __ldg(reinterpret_cast<const uint4*>(p.dctx + off));
         }
       }
-      float2* xs = reinterpret_cast<float2*>(s0);
-      xs[I * 128 + a] = make_float2(d, l);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const uint32_t ow[4] = {ov[m].x, ov[m].y, ov[m].z, ov[m].w}, gw[4] = {gv[m].x, gv[m].y, gv[m].z, gv[m].w};
+        float d = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const float2 of = unpack_bf16(ow[w]), gf = unpack_bf16(gw[w]);
+          d = fmaf(of.x, gf.x, d);
+          d = fmaf(of.y, gf.y, d);
+        }
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        if (piece == 0) xs[I * 128 + (warp & 3) * 32 + 4 * m + rsub].x = d;
+      }
+      const int r = I * 128 + a;
+      xs[I * 128 + a].y = (I < nb && r < p.L) ? p.lse[((long long)b * p.h + hh) * p.L + r] : INFINITY;
     }
     named_bar_sync(1, NCT);
     {

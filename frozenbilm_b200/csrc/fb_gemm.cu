@@ -456,10 +456,110 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         // bf16 chunks are 8 KB: two of them double-buffer inside the warpgroup's 16 KB so that a store drains
         // while the next chunk is computed; fp32 chunks (16 KB) are single-buffered
         const bool dbl = !p.d_f32;
+        // Coalesced epilogue operands.  With thread = output row, loading the aux (bf16) / residual (fp32) segment of
+        // the own row touches 32 different 128-byte lines per instruction; for the K = 192 adapter GEMMs that LSU work
+        // was the whole run time.  Here 4 (aux) / 8 (residual) lanes share one row, so an instruction covers complete
+        // lines, and the warp hands the pieces to their row owners through ITS OWN 32 rows of the output staging
+        // buffer (private to the warp between the "previous store has been read" barrier and the staging of this
+        // chunk).  Only for full, 16-byte aligned chunks without a pre-activation output; everything else takes the
+        // generic path below.
+        const bool has_aux = p.aux_op != FB_AUX_NONE, has_res = p.resid != nullptr;
+        const bool coalesced_ops =
+            !p.D_pre && (has_aux || has_res) && (!has_res || p.d_f32) &&
+            (!has_aux || (((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && (p.ld_aux & 7) == 0)) &&
+            (!has_res || (((reinterpret_cast<uintptr_t>(p.resid) & 15) == 0) && (p.ld_resid & 3) == 0));
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
           const int col0 = nb * BN + c * 32;
           if (col0 >= p.N) break;
+          if (coalesced_ops && split == 0 && col0 + 32 <= p.N) {
+            const int r0 = mb * BM + wq * 32;   // first output row of this warp
+            uint4 ax[4];
+            float4 rs[8];
+            if (has_aux) {
+#pragma unroll
+              for (int m = 0; m < 4; ++m) {
+                const int rw = r0 + 8 * m + (lane >> 2);
+                ax[m] = (rw < p.M) ? __ldg(reinterpret_cast<const uint4*>(p.aux + (long long)rw * p.ld_aux + col0) + (lane & 3))
+                                   : make_uint4(0u, 0u, 0u, 0u);
+              }
+            }
+            if (has_res) {
+#pragma unroll
+              for (int m = 0; m < 8; ++m) {
+                const int rw = r0 + 4 * m + (lane >> 3);
+                rs[m] = (rw < p.M) ? __ldg(reinterpret_cast<const float4*>(p.resid + (long long)rw * p.ld_resid + col0) + (lane & 7))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+            uint32_t acc[32];
+            tmem_ld_32x32(taddr + c * 32, acc);
+            tmem_ld_wait();
+            float v[32];
+            epi_pre(p, row, col0, acc, v);
+            if (p.act == FB_ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            } else if (p.act == FB_ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+            }
+            uint8_t* buf = buf0 + ((dbl && (nstore & 1)) ? 8192 : 0);
+            ++nstore;
+            if (leader) {                            // the store that last used this buffer has finished reading it
+              if (dbl) tma_store_wait_read1(); else tma_store_wait_read0();
+            }
+            named_bar_sync(1 + half, 128);
+            uint8_t* slice = buf + wq * 32 * (p.d_f32 ? 128 : 64);
+            if (has_aux) {
+#pragma unroll
+              for (int m = 0; m < 4; ++m) {
+                const int rr = 8 * m + (lane >> 2), pc = lane & 3;
+                *reinterpret_cast<uint4*>(slice + rr * 64 + ((pc ^ ((rr >> 1) & 3)) << 4)) = ax[m];
+              }
+              __syncwarp();
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint4 q = *reinterpret_cast<const uint4*>(slice + lane * 64 + ((u ^ ((lane >> 1) & 3)) << 4));
+                const float2 f0 = unpack_bf16(q.x), f1 = unpack_bf16(q.y), f2 = unpack_bf16(q.z), f3 = unpack_bf16(q.w);
+                const float a8[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  float& x = v[8 * u + e];
+                  if (p.aux_op == FB_AUX_MUL_GELU_GRAD) x *= gelu_erf_grad(a8[e]);
+                  else if (p.aux_op == FB_AUX_MUL_RELU_MASK) x = (a8[e] > 0.0f) ? x : 0.0f;
+                  else x += a8[e];
+                }
+              }
+              __syncwarp();
+            }
+            if (p.drop_pos == 2) apply_dropout32(p.drop, row, col0, v);
+            if (has_res) {
+#pragma unroll
+              for (int m = 0; m < 8; ++m) {
+                const int rr = 4 * m + (lane >> 3), pc = lane & 7;
+                *reinterpret_cast<float4*>(slice + rr * 128 + ((pc ^ (rr & 7)) << 4)) = rs[m];
+              }
+              __syncwarp();
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const float4 q = *reinterpret_cast<const float4*>(slice + lane * 128 + ((u ^ (lane & 7)) << 4));
+                v[4 * u] += q.x; v[4 * u + 1] += q.y; v[4 * u + 2] += q.z; v[4 * u + 3] += q.w;
+              }
+              __syncwarp();
+            }
+            if (!p.d_f32) stage_row_bf16(buf, r, v); else stage_row_f32(buf, r, v);
+            fence_proxy_async_smem();
+            named_bar_sync(1 + half, 128);
+            if (leader) {
+              if (p.tma_store == 2)
+                tma_reduce_add_2d(&map_d, buf, col0, mb * BM);
+              else
+                tma_store_2d(&map_d, buf, col0, mb * BM);
+              tma_store_commit();
+            }
+            continue;
+          }
           uint32_t acc[32];
           tmem_ld_32x32(taddr + c * 32, acc);
           tmem_ld_wait();
