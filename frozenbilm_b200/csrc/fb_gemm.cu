@@ -298,7 +298,7 @@ __device__ __forceinline__ void stage_row_f32(uint8_t* buf, int r, const float (
     *reinterpret_cast<float4*>(rowp + ((u ^ (r & 7)) << 4)) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool COAL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_pre,
@@ -463,16 +463,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         // buffer (private to the warp between the "previous store has been read" barrier and the staging of this
         // chunk).  Only for full, 16-byte aligned chunks without a pre-activation output; everything else takes the
         // generic path below.
+        // COAL is a separate instantiation (chosen by the host when the operands are 16-byte aligned and there is no
+        // pre-activation output) so that the register allocation of the plain path is untouched.
         const bool has_aux = p.aux_op != FB_AUX_NONE, has_res = p.resid != nullptr;
-        const bool coalesced_ops =
-            !p.D_pre && (has_aux || has_res) && (!has_res || p.d_f32) &&
-            (!has_aux || (((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && (p.ld_aux & 7) == 0)) &&
-            (!has_res || (((reinterpret_cast<uintptr_t>(p.resid) & 15) == 0) && (p.ld_resid & 3) == 0));
+        constexpr bool coalesced_ops = COAL;
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
           const int col0 = nb * BN + c * 32;
           if (col0 >= p.N) break;
-          if (coalesced_ops && split == 0 && col0 + 32 <= p.N) {
+          if (coalesced_ops && split == 0 && col0 + 32 <= p.N) if constexpr (COAL) {
             const int r0 = mb * BM + wq * 32;   // first output row of this warp
             uint4 ax[4];
             float4 rs[8];
@@ -707,12 +706,12 @@ static int make_tmap_operand(CUtensorMap* out, const void* ptr, uint64_t inner, 
   return make_tmap_bf16_nd(out, ptr, 4, dims, strides, box);
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& mpre,
-                       const GemmParams& p, cudaStream_t st) {
+template <int BN, bool A_MN, bool B_MN, bool COAL>
+static int launch_gemm_impl(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& mpre,
+                            const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
-  auto kern = gemm_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, COAL>;
   if (!configured) {
     FB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
@@ -723,6 +722,20 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& mpre,
+                       const GemmParams& p, cudaStream_t st) {
+  // coalesced epilogue operands (see the kernel): aligned aux / residual, TMA-store epilogue, no pre-activation output
+  const bool has_aux = p.aux_op != FB_AUX_NONE, has_res = p.resid != nullptr;
+  // (the GELU-gradient / ReLU-mask epilogues are ALU-bound and measured slightly slower this way: generic path)
+  const bool coal =
+      p.tma_store && !p.D_pre && (has_aux || has_res) && (!has_res || p.d_f32) && (!has_aux || p.aux_op == FB_AUX_ADD) &&
+      (!has_aux || (((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && (p.ld_aux & 7) == 0)) &&
+      (!has_res || (((reinterpret_cast<uintptr_t>(p.resid) & 15) == 0) && (p.ld_resid & 3) == 0));
+  if (coal) return launch_gemm_impl<BN, A_MN, B_MN, true>(ma, mb, md, mpre, p, st);
+  return launch_gemm_impl<BN, A_MN, B_MN, false>(ma, mb, md, mpre, p, st);
 }
 
 template <int BN>
