@@ -160,6 +160,8 @@ def load() -> C.CDLL:
     lib.fb_cast_f32_bf16.argtypes = [vp, ll, vp, vp]
     lib.fb_build_rel_tables.argtypes = [vp, ll, i, i, vp, i, i, i, vp, vp, vp, vp]
     lib.fb_rel_to_bucket.argtypes = [vp, vp, i, i, vp, i, i, i, vp, ll, vp]
+    lib.fb_mlm_corrupt.argtypes = [vp, vp, ll, ll, ll, ll, f, C.c_ulonglong, vp, vp, vp]
+    lib.fb_gather_frames.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -170,7 +172,7 @@ EXPORTS = [
     "fb_layernorm_fwd", "fb_layernorm_bwd", "fb_move_rows", "fb_gelu_bwd", "fb_add_rowbcast", "fb_conv_im2col",
     "fb_conv_col2im", "fb_colsum_bf16", "fb_cross_entropy", "fb_dropout_apply", "fb_sumsq", "fb_adam_step",
     "fb_cast_f32_bf16", "fb_attn_bwd_prep", "fb_rel_to_bucket", "fb_attn_bwd", "fb_attn_bwd_rel",
-    "fb_umma_probe", "fb_attn_bwd_set_debug",
+    "fb_umma_probe", "fb_attn_bwd_set_debug", "fb_mlm_corrupt", "fb_gather_frames",
 ]
 
 
@@ -469,3 +471,33 @@ def rel_to_bucket(gpq, gpk, bucket_of_rel, L, h, out):
     H = h * 64
     check(load().fb_rel_to_bucket(_ptr(gpq), _ptr(gpk), H, h, _ptr(bucket_of_rel), rel_rows, rel_off, L, _ptr(out),
                                   out.stride(0), stream_ptr()), "fb_rel_to_bucket")
+
+
+def mlm_corrupt(ids: torch.Tensor, special_mask, pad_id, mask_id: int, vocab: int, mlm_probability: float, seed: int,
+                ids_out=None, labels_out=None):
+    """fb_mlm_corrupt: ids int64 (any shape, contiguous, on the GPU); special_mask uint8 or None; returns
+    (corrupted ids, labels)."""
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and ids.is_cuda
+    if special_mask is not None:
+        assert special_mask.dtype == torch.uint8 and special_mask.numel() == ids.numel() and special_mask.is_contiguous()
+    ids_out = torch.empty_like(ids) if ids_out is None else ids_out
+    labels_out = torch.empty_like(ids) if labels_out is None else labels_out
+    check(load().fb_mlm_corrupt(_ptr(ids), _ptr(special_mask), ids.numel(), -1 if pad_id is None else int(pad_id),
+                                int(mask_id), int(vocab), float(mlm_probability), C.c_ulonglong(int(seed)),
+                                _ptr(ids_out), _ptr(labels_out), stream_ptr()), "fb_mlm_corrupt")
+    return ids_out, labels_out
+
+
+def gather_frames(shard: torch.Tensor, offsets: torch.Tensor, nframes: torch.Tensor, max_feats: int, out_f32=None,
+                  out_bf16=None, video_len=None):
+    """fb_gather_frames: shard fp16 [rows, D] (GPU), offsets int64 [B], nframes int32 [B]."""
+    assert shard.dtype == torch.float16 and shard.is_contiguous() and shard.is_cuda
+    assert offsets.dtype == torch.int64 and nframes.dtype == torch.int32
+    B, D = nframes.numel(), shard.shape[1]
+    if out_f32 is None and out_bf16 is None:
+        out_f32 = torch.empty(B, max_feats, D, device=shard.device, dtype=torch.float32)
+    if video_len is None:
+        video_len = torch.empty(B, device=shard.device, dtype=torch.int64)
+    check(load().fb_gather_frames(_ptr(shard), _ptr(offsets), _ptr(nframes), B, int(max_feats), D, _ptr(out_f32),
+                                  _ptr(out_bf16), _ptr(video_len), stream_ptr()), "fb_gather_frames")
+    return (out_f32 if out_f32 is not None else out_bf16), video_len

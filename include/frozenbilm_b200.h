@@ -242,6 +242,24 @@ typedef struct fb_umma_probe_args {
 } fb_umma_probe_args;
 int fb_umma_probe(const fb_umma_probe_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Input side of the path (fb_data.cu).
+ * ------------------------------------------------------------------------------------------ */
+/* Masked-LM corruption on the device (reference util/misc.py:14-56 mask_tokens, called from main.py:52-58):
+ * a token is selected with probability mlm_probability unless special_mask[i] != 0 (nullable) or ids[i] == pad_id
+ * (pad_id < 0: no pad token); selected tokens become mask_id (80 %), a uniform random id in [0, vocab) (10 %) or stay
+ * (10 %); labels_out = original id where selected, -100 elsewhere.  Decisions are a pure function of (seed, i):
+ * oracle/data_oracle.py reproduces them bit for bit.  ids / outputs: int64 [n] (ids_out may alias ids). */
+int fb_mlm_corrupt(const long long* ids, const unsigned char* special_mask, long long n, long long pad_id,
+                   long long mask_id, long long vocab, float mlm_probability, unsigned long long seed,
+                   long long* ids_out, long long* labels_out, void* stream);
+/* Frame subsampling / padding of CLIP features (reference datasets/videotext_dataset.py:23-44 + collate :47-57):
+ * shard_f16 holds the [n_b, D] fp16 feature matrices of all videos back to back, sample b starts at row offsets[b]
+ * and has nframes[b] rows (0 = missing video).  out[b, j] = frame (j * n) / max_feats when n > max_feats, frame j when
+ * j < n, zeros otherwise; video_len[b] = min(n, max_feats).  out_f32 and/or out_bf16: [B, max_feats, D]. */
+int fb_gather_frames(const void* shard_f16, const long long* offsets, const int* nframes, int B, int max_feats, int D,
+                     float* out_f32, void* out_bf16, long long* video_len, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
