@@ -479,21 +479,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 // Expand the per-bucket positional projections into per-relative-position tables:
 //   out[t][hh][row][0..63] = PQK[bucket_of_rel[row - rel_off + 511]][t * H + hh * 64 + ...]
 // where PQK = Linear_{q|k}(dropout(LayerNorm(rel_embeddings)))  [2S, 2H]  (deberta.py:847-853).
-__global__ void build_rel_tables_kernel(const __nv_bfloat16* __restrict__ pqk, long long ld, int H, int h,
-                                        const int* __restrict__ bucket_of_rel, int rel_rows, int rel_off, int L,
-                                        __nv_bfloat16* __restrict__ out_pq, __nv_bfloat16* __restrict__ out_pk,
-                                        __nv_bfloat16* __restrict__ out_pk_rev) {
-  const int row = blockIdx.x, hh = blockIdx.y, t = blockIdx.z;
+// 8 table rows per 256-thread CTA (one warp per row, 4 bytes per lane): the one-warp-per-CTA geometry spent its
+// 20 us on scheduling 37 000 tiny CTAs.
+__global__ void __launch_bounds__(256)
+build_rel_tables_kernel(const __nv_bfloat16* __restrict__ pqk, long long ld, int H, int h,
+                        const int* __restrict__ bucket_of_rel, int rel_rows, int rel_off, int L,
+                        __nv_bfloat16* __restrict__ out_pq, __nv_bfloat16* __restrict__ out_pk,
+                        __nv_bfloat16* __restrict__ out_pk_rev) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int hh = blockIdx.y, t = blockIdx.z;
+  if (row >= rel_rows) return;
   const int rel = row - rel_off;
   uint32_t val = 0;
   if (rel > -L && rel < L) {
     const int bucket = bucket_of_rel[rel + 511];
-    val = *reinterpret_cast<const uint32_t*>(pqk + (long long)bucket * ld + t * H + hh * 64 + threadIdx.x * 2);
+    val = *reinterpret_cast<const uint32_t*>(pqk + (long long)bucket * ld + t * H + hh * 64 + lane * 2);
   }
   __nv_bfloat16* out = (t == 0 ? out_pq : out_pk) + ((long long)hh * rel_rows + row) * 64;
-  *reinterpret_cast<uint32_t*>(out + threadIdx.x * 2) = val;
+  *reinterpret_cast<uint32_t*>(out + lane * 2) = val;
   if (t == 1 && out_pk_rev != nullptr)   // row-reversed copy of PKrel for the fused backward (fb_attn_bwd)
-    *reinterpret_cast<uint32_t*>(out_pk_rev + ((long long)hh * rel_rows + (rel_rows - 1 - row)) * 64 + threadIdx.x * 2) = val;
+    *reinterpret_cast<uint32_t*>(out_pk_rev + ((long long)hh * rel_rows + (rel_rows - 1 - row)) * 64 + lane * 2) = val;
 }
 
 
@@ -603,15 +608,19 @@ __global__ void __launch_bounds__(256) attn_bwd_z2_kernel(const __nv_bfloat16* _
 
 // Stage 3: fold the per-relative-position gradients back onto the 2S bucket rows:
 //   out[bucket_of_rel[rel], t*H + hh*64 + k] += g_t[hh, rel + rel_off, k]   (t = 0: dPQ, t = 1: dPK)
-__global__ void rel_to_bucket_kernel(const float* __restrict__ gpq, const float* __restrict__ gpk, int H, int h,
-                                     const int* __restrict__ bucket_of_rel, int rel_rows, int rel_off, int L,
-                                     float* __restrict__ out, long long ldo) {
-  const int row = blockIdx.x, hh = blockIdx.y, t = blockIdx.z;
+__global__ void __launch_bounds__(256)
+rel_to_bucket_kernel(const float* __restrict__ gpq, const float* __restrict__ gpk, int H, int h,
+                     const int* __restrict__ bucket_of_rel, int rel_rows, int rel_off, int L,
+                     float* __restrict__ out, long long ldo) {
+  // 4 table rows per CTA (64 threads = 64 columns each)
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 6), col = threadIdx.x & 63;
+  const int hh = blockIdx.y, t = blockIdx.z;
+  if (row >= rel_rows) return;
   const int rel = row - rel_off;
   if (rel <= -L || rel >= L) return;
   const int bucket = bucket_of_rel[rel + 511];
   const float* g = (t == 0 ? gpq : gpk) + ((long long)hh * rel_rows + row) * 64;
-  atomicAdd(out + (long long)bucket * ldo + t * H + hh * 64 + threadIdx.x, g[threadIdx.x]);
+  atomicAdd(out + (long long)bucket * ldo + t * H + hh * 64 + col, g[col]);
 }
 
 static int make_qkv_map(CUtensorMap* m, const void* ptr, long long ld, int B, int L, int h) {
@@ -685,8 +694,8 @@ int build_rel_tables(const void* pqk, long long ld, int H, int h, const int* buc
                      int rel_off, int L, void* out_pq, void* out_pk, void* out_pk_rev, cudaStream_t st) {
   FB_REQUIRE(pqk && bucket_of_rel && out_pq && out_pk, "fb_build_rel_tables: null arg");
   FB_REQUIRE(H == h * 64, "fb_build_rel_tables: head_dim must be 64");
-  dim3 grid(rel_rows, h, 2);
-  build_rel_tables_kernel<<<grid, 32, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(pqk), ld, H, h, bucket_of_rel,
+  dim3 grid((rel_rows + 7) / 8, h, 2);
+  build_rel_tables_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(pqk), ld, H, h, bucket_of_rel,
                                                rel_rows, rel_off, L, reinterpret_cast<__nv_bfloat16*>(out_pq),
                                                reinterpret_cast<__nv_bfloat16*>(out_pk),
                                                reinterpret_cast<__nv_bfloat16*>(out_pk_rev));
@@ -722,8 +731,8 @@ int attn_bwd_prep(const fb_attn_bwd_prep_args* a, cudaStream_t st) {
 int rel_to_bucket(const float* gpq, const float* gpk, int H, int h, const int* bucket_of_rel, int rel_rows,
                   int rel_off, int L, float* out, long long ldo, cudaStream_t st) {
   FB_REQUIRE(gpq && gpk && bucket_of_rel && out && H == h * 64, "fb_rel_to_bucket: bad args");
-  rel_to_bucket_kernel<<<dim3(rel_rows, h, 2), 64, 0, st>>>(gpq, gpk, H, h, bucket_of_rel, rel_rows, rel_off, L, out,
-                                                          ldo);
+  rel_to_bucket_kernel<<<dim3((rel_rows + 3) / 4, h, 2), 256, 0, st>>>(gpq, gpk, H, h, bucket_of_rel, rel_rows, rel_off,
+                                                                      L, out, ldo);
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
