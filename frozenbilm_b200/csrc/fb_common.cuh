@@ -34,7 +34,7 @@ int num_sms();
 // Generic bf16 tiled tensor map (rank <= 4), 128B swizzle, inner box = 64 elements (128 B).
 int make_tmap_bf16_nd(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
                       const uint64_t* strides_elems /*rank-1*/, const uint32_t* box);
-// 2-D output map for the TMA-store epilogue: [rows, cols] row-major, box {32 cols, 128 rows};
+// 2-D output map for the TMA-store epilogue: [rows, cols] row-major, box {32 cols, 32 rows};
 // bf16 -> 64B swizzle (64-byte rows), fp32 -> 128B swizzle (128-byte rows).
 int make_tmap_store_2d(CUtensorMap* out, const void* ptr, int is_f32, uint64_t cols, uint64_t rows, uint64_t ld_elems);
 const char* last_error();
@@ -131,6 +131,26 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// Multicast variant: the box lands at the same shared-memory offset of every CTA of the cluster named in cta_mask and
+// signals complete_tx on the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_4d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                                               int32_t c1, int32_t c2, int32_t c3, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, "
+      "{%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+      : "memory");
+}
+// ---- thread-block clusters ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // TMA store of a staged tile (smem -> global, clipped at the tensor bounds), bulk-group completion.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -211,6 +231,15 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
+}
+// Same, arriving on the mbarrier at this offset in every CTA of the cluster named in cta_mask (releases a pipeline
+// stage that a peer CTA's multicast TMA writes into).
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");

@@ -20,6 +20,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "../../include/frozenbilm_b200.h"
 #include "fb_common.cuh"
@@ -298,7 +299,25 @@ __device__ __forceinline__ void stage_row_f32(uint8_t* buf, int r, const float (
     *reinterpret_cast<float4*>(rowp + ((u ^ (r & 7)) << 4)) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
 }
 
-template <int BN, bool A_MN, bool B_MN, bool COAL>
+// CL = 2: thread-block cluster of two CTAs working on M-adjacent tiles of the same N block.  Each CTA fetches its own
+// A tile and HALF of the shared B tile, multicast into both CTAs' shared memory, so the L2 -> SM traffic per
+// 128 x BN x 64 step drops from 16 + BN/8 KB to 16 + BN/16 KB (the 1-CTA kernel sits at the ~42 B/clk/SM L2 fabric
+// limit: 87 FLOP/B for BN = 256).  A pipeline stage is released to BOTH producers (multicast commit), the accumulator
+// / epilogue side is unchanged.  Host side: only for batch = 1, split_k = 1, an even number of M blocks, K-major A.
+template <int CL>
+__device__ __forceinline__ void decode_tile_cl(const GemmParams& p, int t, uint32_t crank, int& split, int& b, int& mb,
+                                               int& nb) {
+  if constexpr (CL == 1) {
+    decode_tile(p, t, split, b, mb, nb);
+  } else {
+    nb = t % p.nblocks;
+    mb = (t / p.nblocks) * CL + (int)crank;
+    b = 0;
+    split = 0;
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, bool COAL, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_pre,
@@ -320,6 +339,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+  // persistent tile sequence of this CTA (CL = 2: of its cluster; both CTAs walk the same sequence of tile pairs)
+  const int tile_first = (CL > 1) ? (int)(blockIdx.x / CL) : (int)blockIdx.x;
+  const int tile_step = (CL > 1) ? (int)(gridDim.x / CL) : (int)gridDim.x;
+  const int tile_total = (CL > 1) ? p.total_tiles / CL : p.total_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -328,7 +352,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);   // released by the MMA warps of every CTA that multicasts into this stage
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -342,6 +366,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -350,9 +375,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < tile_total; tile += tile_step) {
         int split, b, mb, nb;
-        decode_tile(p, tile, split, b, mb, nb);
+        decode_tile_cl<CL>(p, tile, crank, split, b, mb, nb);
         const int m0 = mb * BM, n0 = nb * BN;
         const int k_begin = split * p.kblocks_per_split;
         const int k_end = min(k_begin + p.kblocks_per_split, p.kblocks);
@@ -370,12 +395,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             for (int c = 0; c < BM / 64; ++c)
               tma_load_4d(sa + c * (64 * BK * 2), &map_a, &full_bar[stage], m0 + c * 64, kb * BK, abi, abo);
           }
-          if constexpr (!B_MN) {
-            tma_load_4d(sb, &map_b, &full_bar[stage], kb * BK, n0, bbi, bbo);
-          } else {
+          if constexpr (CL == 1) {
+            if constexpr (!B_MN) {
+              tma_load_4d(sb, &map_b, &full_bar[stage], kb * BK, n0, bbi, bbo);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_4d(sb + c * (64 * BK * 2), &map_b, &full_bar[stage], n0 + c * 64, kb * BK, bbi, bbo);
+              for (int c = 0; c < BN / 64; ++c)
+                tma_load_4d(sb + c * (64 * BK * 2), &map_b, &full_bar[stage], n0 + c * 64, kb * BK, bbi, bbo);
+            }
+          } else {
+            // this CTA's share of the B tile, multicast to both CTAs (the peer sends the rest)
+            constexpr uint16_t kAll = (1u << CL) - 1u;
+            if constexpr (!B_MN) {
+              constexpr int ROWS = BN / CL;   // map_b was built with a box of BN / CL rows
+              tma_load_4d_mc(sb + crank * (ROWS * BK * 2), &map_b, &full_bar[stage], kb * BK, n0 + (int)crank * ROWS, bbi,
+                             bbo, kAll);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c)
+                if ((c % CL) == (int)crank)
+                  tma_load_4d_mc(sb + c * (64 * BK * 2), &map_b, &full_bar[stage], n0 + c * 64, kb * BK, bbi, bbo, kAll);
+            }
           }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -394,9 +434,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile_first; tile < tile_total; tile += tile_step, ++it) {
         int split, b, mb, nb;
-        decode_tile(p, tile, split, b, mb, nb);
+        decode_tile_cl<CL>(p, tile, crank, split, b, mb, nb);
         const int k_begin = split * p.kblocks_per_split;
         const int k_end = min(k_begin + p.kblocks_per_split, p.kblocks);
         const int as = it & 1;
@@ -415,7 +455,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             const uint64_t bdesc = make_smem_desc_sw128(sb + k * B_KSTEP, B_LBO, 1024);
             umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > k_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot once these MMAs retire (CL = 2: in both CTAs, whose producers both write into it)
+          if constexpr (CL == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_mc(&empty_bar[stage], (uint16_t)((1u << CL) - 1u));
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
@@ -430,9 +472,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     const int c_begin = half * HALF_CHUNKS, c_end = (half == 0) ? HALF_CHUNKS : CHUNKS;
     uint32_t nstore = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_first; tile < tile_total; tile += tile_step, ++it) {
       int split, b, mb, nb;
-      decode_tile(p, tile, split, b, mb, nb);
+      decode_tile_cl<CL>(p, tile, crank, split, b, mb, nb);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[as], aphase);
@@ -449,9 +491,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
         }
       } else {
         // coalesced path: each warpgroup stages a 128 x 32 chunk in smem and one thread issues a TMA store
-        uint8_t* buf0 = smem_store + half * Cfg::STORE_STAGE_BYTES;
-        const int r = wq * 32 + lane;
-        const bool leader = (wq == 0 && lane == 0);
+        // every epilogue warp owns a 4 KB staging box (its 32 rows x 32 columns) and issues its own TMA stores: no
+        // block-level barrier in the epilogue, a warp never waits for the slowest of its warpgroup (the
+        // warpgroup-wide version spent ~16 named-barrier + proxy-fence rounds per 128 x 256 tile)
+        uint8_t* buf0 = smem_store + (warp - 4) * 4096;
+        const int r = lane;
+        const bool leader = (lane == 0);
         const int n_pass = p.D_pre ? 2 : 1;
         // bf16 chunks are 8 KB: two of them double-buffer inside the warpgroup's 16 KB so that a store drains
         // while the next chunk is computed; fp32 chunks (16 KB) are single-buffered
@@ -503,13 +548,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
             }
-            uint8_t* buf = buf0 + ((dbl && (nstore & 1)) ? 8192 : 0);
+            uint8_t* buf = buf0 + ((dbl && (nstore & 1)) ? 2048 : 0);
             ++nstore;
             if (leader) {                            // the store that last used this buffer has finished reading it
               if (dbl) tma_store_wait_read1(); else tma_store_wait_read0();
             }
-            named_bar_sync(1 + half, 128);
-            uint8_t* slice = buf + wq * 32 * (p.d_f32 ? 128 : 64);
+            __syncwarp();
+            uint8_t* slice = buf;   // this warp's staging box
             if (has_aux) {
 #pragma unroll
               for (int m = 0; m < 4; ++m) {
@@ -549,12 +594,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             }
             if (!p.d_f32) stage_row_bf16(buf, r, v); else stage_row_f32(buf, r, v);
             fence_proxy_async_smem();
-            named_bar_sync(1 + half, 128);
+            __syncwarp();
             if (leader) {
               if (p.tma_store == 2)
-                tma_reduce_add_2d(&map_d, buf, col0, mb * BM);
+                tma_reduce_add_2d(&map_d, buf, col0, mb * BM + wq * 32);
               else
-                tma_store_2d(&map_d, buf, col0, mb * BM);
+                tma_store_2d(&map_d, buf, col0, mb * BM + wq * 32);
               tma_store_commit();
             }
             continue;
@@ -573,20 +618,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
           for (int pass = 0; pass < n_pass; ++pass) {
             const bool pre_only = (n_pass == 2 && pass == 0);
             if (!pre_only && split == 0) epi_post(p, row, col0, v);
-            uint8_t* buf = buf0 + ((dbl && (nstore & 1)) ? 8192 : 0);
+            uint8_t* buf = buf0 + ((dbl && (nstore & 1)) ? 2048 : 0);
             ++nstore;
             if (leader) {                            // the store that last used this buffer has finished reading it
               if (dbl) tma_store_wait_read1(); else tma_store_wait_read0();
             }
-            named_bar_sync(1 + half, 128);
+            __syncwarp();
             if (pre_only || !p.d_f32) stage_row_bf16(buf, r, v); else stage_row_f32(buf, r, v);
             fence_proxy_async_smem();
-            named_bar_sync(1 + half, 128);
+            __syncwarp();
             if (leader) {
               if (p.tma_store == 2 && !pre_only)
-                tma_reduce_add_2d(&map_d, buf, col0, mb * BM);   // D += tile (split-K / accumulate)
+                tma_reduce_add_2d(&map_d, buf, col0, mb * BM + wq * 32);   // D += tile (split-K / accumulate)
               else
-                tma_store_2d(pre_only ? &map_pre : &map_d, buf, col0, mb * BM);
+                tma_store_2d(pre_only ? &map_pre : &map_d, buf, col0, mb * BM + wq * 32);
               tma_store_commit();
             }
           }
@@ -596,11 +641,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
     }
-    if (p.tma_store && (warp & 3) == 0 && lane == 0) tma_store_wait_all();
+    if (p.tma_store && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // no CTA retires while its peer may still signal its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -657,7 +703,7 @@ int make_tmap_store_2d(CUtensorMap* out, const void* ptr, int is_f32, uint64_t c
   const uint64_t esz = is_f32 ? 4 : 2;
   cuuint64_t d[2] = {cols, rows};
   cuuint64_t st[1] = {ld_elems * esz};
-  cuuint32_t bx[2] = {32, 128}, es[2] = {1, 1};
+  cuuint32_t bx[2] = {32, 32}, es[2] = {1, 1};   // one epilogue warp's box: 32 columns x its 32 rows
   CUresult r = enc(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                    const_cast<void*>(ptr), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    is_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -706,27 +752,51 @@ static int make_tmap_operand(CUtensorMap* out, const void* ptr, uint64_t inner, 
   return make_tmap_bf16_nd(out, ptr, 4, dims, strides, box);
 }
 
-template <int BN, bool A_MN, bool B_MN, bool COAL>
+template <int BN, bool A_MN, bool B_MN, bool COAL, int CL>
 static int launch_gemm_impl(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& mpre,
                             const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, COAL>;
+  static int max_clusters = 0;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, COAL, CL>;
   if (!configured) {
     FB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    if (CL > 1) {
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(CL * 64); qc.blockDim = dim3(NUM_THREADS); qc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa; qc.numAttrs = 1;
+      FB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &qc));
+      FB_REQUIRE(max_clusters > 0, "fb_gemm: no cluster of %d CTAs fits", CL);
+    }
     configured = true;
   }
-  int grid = std::min(p.total_tiles, num_sms());
-  FB_REQUIRE(grid > 0, "no CUDA device / empty GEMM");
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, md, mpre, p);
+  if (CL == 1) {
+    int grid = std::min(p.total_tiles, num_sms());
+    FB_REQUIRE(grid > 0, "no CUDA device / empty GEMM");
+    kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, md, mpre, p);
+  } else {
+    const int clusters = std::min(p.total_tiles / CL, max_clusters);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * CL); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    FB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, md, mpre, p));
+  }
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
+// cluster_ok: the host found the shape eligible for the 2-CTA multicast kernel AND built map_b with half-height boxes
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& mpre,
-                       const GemmParams& p, cudaStream_t st) {
+                       const GemmParams& p, bool cluster_ok, cudaStream_t st) {
   // coalesced epilogue operands (see the kernel): aligned aux / residual, TMA-store epilogue, no pre-activation output
   const bool has_aux = p.aux_op != FB_AUX_NONE, has_res = p.resid != nullptr;
   // (the GELU-gradient / ReLU-mask epilogues are ALU-bound and measured slightly slower this way: generic path)
@@ -734,17 +804,23 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
       p.tma_store && !p.D_pre && (has_aux || has_res) && (!has_res || p.d_f32) && (!has_aux || p.aux_op == FB_AUX_ADD) &&
       (!has_aux || (((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && (p.ld_aux & 7) == 0)) &&
       (!has_res || (((reinterpret_cast<uintptr_t>(p.resid) & 15) == 0) && (p.ld_resid & 3) == 0));
-  if (coal) return launch_gemm_impl<BN, A_MN, B_MN, true>(ma, mb, md, mpre, p, st);
-  return launch_gemm_impl<BN, A_MN, B_MN, false>(ma, mb, md, mpre, p, st);
+  if constexpr (!A_MN && (BN == 256 || BN == 192)) {
+    if (cluster_ok) {
+      if (coal) return launch_gemm_impl<BN, A_MN, B_MN, true, 2>(ma, mb, md, mpre, p, st);
+      return launch_gemm_impl<BN, A_MN, B_MN, false, 2>(ma, mb, md, mpre, p, st);
+    }
+  }
+  if (coal) return launch_gemm_impl<BN, A_MN, B_MN, true, 1>(ma, mb, md, mpre, p, st);
+  return launch_gemm_impl<BN, A_MN, B_MN, false, 1>(ma, mb, md, mpre, p, st);
 }
 
 template <int BN>
 static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md,
-                          const CUtensorMap& mpre, const GemmParams& p, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(ma, mb, md, mpre, p, st);
-  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(ma, mb, md, mpre, p, st);
-  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(ma, mb, md, mpre, p, st);
-  return launch_gemm<BN, true, true>(ma, mb, md, mpre, p, st);
+                          const CUtensorMap& mpre, const GemmParams& p, bool cluster_ok, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false>(ma, mb, md, mpre, p, cluster_ok, st);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true>(ma, mb, md, mpre, p, cluster_ok, st);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false>(ma, mb, md, mpre, p, false, st);
+  return launch_gemm<BN, true, true>(ma, mb, md, mpre, p, false, st);
 }
 
 static int pick_block_n(int M, int N, int batch, int split_k) {
@@ -778,6 +854,12 @@ int gemm(const fb_gemm_args* a, cudaStream_t st) {
   int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N, batch_total, split_k);
   FB_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, "fb_gemm: block_n must be 64/128/192/256");
 
+  // 2-CTA multicast kernel (see gemm_kernel): big unbatched GEMMs with an even number of M blocks and K-major A
+  static const bool cluster_enabled = (getenv("FB_GEMM_CLUSTER") == nullptr) || (atoi(getenv("FB_GEMM_CLUSTER")) != 0);
+  const int mblocks_h = (a->M + BM - 1) / BM, nblocks_h = (a->N + bn - 1) / bn;
+  const bool cluster_ok = cluster_enabled && batch_total == 1 && split_k == 1 && !a->a_mn_major && (bn == 256 || bn == 192) &&
+                          (mblocks_h % 2 == 0) && ((long long)mblocks_h * nblocks_h >= 2LL * num_sms());
+
   CUtensorMap ma, mb;
   int rc;
   if (!a->a_mn_major)
@@ -786,7 +868,8 @@ int gemm(const fb_gemm_args* a, cudaStream_t st) {
     rc = make_tmap_operand(&ma, a->A, a->M, a->K, a->lda, b_in, a->stride_a_in, b_out, a->stride_a, BK);
   if (rc) return rc;
   if (!a->b_mn_major)
-    rc = make_tmap_operand(&mb, a->B, a->K, a->N, a->ldb, b_in, a->stride_b_in, b_out, a->stride_b, bn);
+    rc = make_tmap_operand(&mb, a->B, a->K, a->N, a->ldb, b_in, a->stride_b_in, b_out, a->stride_b,
+                           cluster_ok ? bn / 2 : bn);   // the cluster kernel loads half-height boxes
   else
     rc = make_tmap_operand(&mb, a->B, a->N, a->K, a->ldb, b_in, a->stride_b_in, b_out, a->stride_b, BK);
   if (rc) return rc;
@@ -834,10 +917,10 @@ int gemm(const fb_gemm_args* a, cudaStream_t st) {
     if (a->D_pre && (rc = make_tmap_store_2d(&mpre, a->D_pre, 0, a->N, a->M, a->ld_pre))) return rc;
   }
   switch (bn) {
-    case 64: return dispatch_major<64>(a->a_mn_major, a->b_mn_major, ma, mb, md, mpre, p, st);
-    case 128: return dispatch_major<128>(a->a_mn_major, a->b_mn_major, ma, mb, md, mpre, p, st);
-    case 192: return dispatch_major<192>(a->a_mn_major, a->b_mn_major, ma, mb, md, mpre, p, st);
-    default: return dispatch_major<256>(a->a_mn_major, a->b_mn_major, ma, mb, md, mpre, p, st);
+    case 64: return dispatch_major<64>(a->a_mn_major, a->b_mn_major, ma, mb, md, mpre, p, false, st);
+    case 128: return dispatch_major<128>(a->a_mn_major, a->b_mn_major, ma, mb, md, mpre, p, false, st);
+    case 192: return dispatch_major<192>(a->a_mn_major, a->b_mn_major, ma, mb, md, mpre, p, cluster_ok, st);
+    default: return dispatch_major<256>(a->a_mn_major, a->b_mn_major, ma, mb, md, mpre, p, cluster_ok, st);
   }
 }
 

@@ -137,3 +137,41 @@ def test_gemm_batched():
     lib.gemm(A, B, D)
     ref = A.float() @ B.float().transpose(1, 2)
     assert (D - ref).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K,block_n", [(5632, 2048, 320, 256), (5632, 1536, 384, 192), (5600, 1500, 200, 256),
+                                           (11264, 1536, 192, 0)])
+@pytest.mark.parametrize("b_mn", [False, True])
+def test_gemm_cluster_multicast_path(M, N, K, block_n, b_mn):
+    """Shapes with >= 2 x 148 tiles and an even number of 128-row blocks take the 2-CTA cluster kernel (each CTA
+    loads half of the shared B tile, multicast to its peer).  Plain, epilogue-operand and ragged-edge cases."""
+    from frozenbilm_b200 import lib
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(M + N + K + int(b_mn))
+    A = (0.3 * torch.randn(M, K, device=dev, generator=g)).bfloat16()
+    ldb = (N + 7) // 8 * 8
+    B = (0.3 * torch.randn(K, ldb, device=dev, generator=g)).bfloat16()[:, :N] if b_mn else \
+        (0.3 * torch.randn(N, K, device=dev, generator=g)).bfloat16()
+    bias = torch.randn(N, device=dev, generator=g)
+    ldn = (N + 7) // 8 * 8
+    resid = torch.randn(M, ldn, device=dev, generator=g)[:, :N]
+    aux = torch.randn(M, ldn, device=dev, generator=g).bfloat16()[:, :N]
+    ref, _ = _ref(A, B, False, b_mn, bias=bias)
+    tol = 3e-3 * math.sqrt(K) * 0.09 + 1e-3
+    D = torch.full((M, ldn), float("nan"), device=dev)[:, :N]
+    lib.gemm(A, B, D, b_mn_major=b_mn, bias=bias, block_n=block_n)
+    assert (D - ref).abs().max().item() < tol
+    # coalesced epilogue operands on top of the cluster kernel
+    D = torch.full((M, ldn), float("nan"), device=dev)[:, :N]
+    lib.gemm(A, B, D, b_mn_major=b_mn, bias=bias, aux=aux, aux_op=lib.FB_AUX_ADD, resid=resid, block_n=block_n)
+    assert (D - (ref + aux.float() + resid)).abs().max().item() < tol
+    # bf16 output + GELU with the pre-activation side output
+    Db = torch.empty(M, ldn, device=dev, dtype=torch.bfloat16)[:, :N]
+    Dp = torch.empty(M, ldn, device=dev, dtype=torch.bfloat16)[:, :N]
+    lib.gemm(A, B, Db, b_mn_major=b_mn, bias=bias, act=lib.FB_ACT_GELU, D_pre=Dp, block_n=block_n)
+    assert (Dp.float() - ref).abs().max().item() < 3e-2 + tol
+    assert (Db.float() - torch.nn.functional.gelu(ref)).abs().max().item() < 3e-2 + tol
+    # repeated launches reuse the pipeline barriers across many tiles: results must be identical
+    D2 = torch.empty_like(Db)
+    lib.gemm(A, B, D2, b_mn_major=b_mn, bias=bias, act=lib.FB_ACT_GELU, D_pre=Dp, block_n=block_n)
+    assert torch.equal(D2, Db)
