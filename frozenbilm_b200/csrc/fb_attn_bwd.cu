@@ -165,7 +165,9 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
                 const __grid_constant__ CUtensorMap map_pk, const __grid_constant__ CUtensorMap map_pq,
-                const __grid_constant__ CUtensorMap map_ds, const __grid_constant__ AttnBwdFusedParams p) {
+                const __grid_constant__ CUtensorMap map_ds, const __grid_constant__ CUtensorMap map_dq,
+                const __grid_constant__ CUtensorMap map_dk, const __grid_constant__ CUtensorMap map_dv,
+                const __grid_constant__ AttnBwdFusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B_OFF_BARS);
@@ -182,6 +184,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   uint64_t* bar_mmaA = bars + 10;  // MMA: dV, dQ, dK (content terms) complete
   uint64_t* bar_mmaB = bars + 11;  // MMA: dQ += Z1.PKrev complete
   uint64_t* bar_mmaC = bars + 12;  // MMA: dK += Z2.PQ complete
+  uint64_t* bar_ep = bars + 16;      // compute -> control: dK_J / dV_J (and finally the dQ tiles) staged in shared memory
+  uint64_t* bar_epfree = bars + 17;  // control -> compute: their bulk stores have left shared memory
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   uint8_t* s0 = smem + B_OFF_S0;
   uint8_t* zb = smem + B_OFF_Z;
@@ -197,6 +201,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
     mbar_init(bar_rdyA, 4 * NG); mbar_init(bar_rdyB, 4 * NG); mbar_init(bar_rdyC, 4 * NG);
     mbar_init(bar_mmaA, 1); mbar_init(bar_mmaB, 1); mbar_init(bar_mmaC, 1);
+    mbar_init(bar_ep, 4 * NG); mbar_init(bar_epfree, 1);
     fence_barrier_init();
   }
   if (warp == 4 * NG + 1) {
@@ -278,6 +283,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     if (elect_one_sync()) {
       // ======================= TMA + MMA control thread =======================
       if constexpr (REL) { if (p.ds_out != nullptr) tma_prefetch_desc(&map_ds); }
+      tma_prefetch_desc(&map_dq); tma_prefetch_desc(&map_dk); tma_prefetch_desc(&map_dv);
+      // Output tiles are staged by the compute warps as 128B-swizzled [128 x 64] bf16 tiles in the (then free)
+      // Pd half of the staging area and written by bulk stores from here: the direct version (thread = row, 32
+      // bytes per thread) kept the compute warps ~3000 cycles at every key-block boundary.
+      auto store_dkdv = [&](int Jd) {
+        mbar_wait(bar_ep, Jd & 1);
+        tma_store_4d(&map_dk, s0, 0, hh, Jd * 128, b);
+        tma_store_4d(&map_dv, s0 + 16384, 0, hh, Jd * 128, b);
+        tma_store_commit();
+        tma_store_wait_read0();
+        mbar_arrive(bar_epfree);
+      };
       constexpr uint32_t idesc_dp = make_idesc_bf16(128, 128, 0, 0);   // dP = dO . V^T       (A, B K-major)
       constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);    // A K-major, B MN-major (dS.K, Z.band)
       constexpr uint32_t idesc_mn = make_idesc_bf16(128, 64, 1, 1);    // A, B MN-major         (Pd^T.dO, dS^T.Q)
@@ -290,9 +307,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         mbar_arrive_expect_tx(bar_do, 16384);
         tma_load_4d(smem + B_OFF_DO, &map_do, bar_do, 0, hh, I * 128, b);
       };
-      auto load_kv = [&](int J) {
+      auto load_k = [&](int J) {
         mbar_arrive_expect_tx(bar_k, 16384);
         tma_load_4d(smem + B_OFF_K, &map_k, bar_k, 0, hh, J * 128, b);
+      };
+      auto load_v = [&](int J) {
         mbar_arrive_expect_tx(bar_v, 16384);
         tma_load_4d(smem + B_OFF_V, &map_v, bar_v, 0, hh, J * 128, b);
       };
@@ -300,7 +319,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       auto pq_band = [&](int I, int J) { return (I - J) * 128 - 127 + p.rel_off; };
       // PKrev band: reversed table row of k = rel_rows - 1 - ((I - J) 128 + 127 - k + rel_off)
       auto pk_band = [&](int I, int J) { return p.rel_rows - 128 - p.rel_off - (I - J) * 128; };
-      load_kv(0);
+      load_k(0);
+      load_v(0);
       load_qdo(0);
       if constexpr (REL) {
         mbar_arrive_expect_tx(bar_pk, 32768);
@@ -322,6 +342,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
                     make_smem_desc_sw128(sV + k * 32, 16, 1024), idesc_dp, k > 0);
         umma_commit(bar_dp);
         FB_STAMP(1);
+        if (I == 0 && J > 0) store_dkdv(J - 1);   // previous key block's dK / dV (staged during its last pair)
+        if (has_next && Jn != J) {
+          // last query tile of this key block: V_J has no reader left once dP is done, so the next block's V is
+          // fetched now instead of at the block boundary, where its latency sat in front of the next dP
+          mbar_wait(bar_dp, ph);
+          load_v(Jn);
+        }
         // ---- content terms: dV_J += Pd^T.dO_I ; dQ_I += dS'.K_J ; dK_J += dS'^T.Q_I
         mbar_wait(bar_q, ph);
         if (I == 0) mbar_wait(bar_k, phJ);
@@ -381,7 +408,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         if (has_next) {
           load_qdo(In);
-          if (Jn != J) load_kv(Jn);
+          if (Jn != J) load_k(Jn);
         }
         if constexpr (REL) {
           mbar_wait(bar_mmaB, ph);    // the PKrev band and Z1 are free
@@ -406,7 +433,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
           FB_STAMP(11);
         }
       }
-      tma_store_wait_all();   // the dS' bulk stores are globally complete before the CTA retires
+      store_dkdv(nb - 1);
+      mbar_wait(bar_ep, nb & 1);          // the dQ tiles (one per query tile) are staged
+      for (int I = 0; I < nb; ++I) tma_store_4d(&map_dq, s0 + I * 16384, 0, hh, I * 128, b);
+      tma_store_commit();
+      tma_store_wait_all();   // every bulk store is globally complete before the CTA retires
     }
     __syncwarp();
   } else if (warp < 4 * NG) {
@@ -447,19 +478,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         const int rsub = lane >> 2, piece = lane & 3;
         const float* gsrc = p.s2 + (((long long)b * p.h + hh) * p.L + It * 128 + 32 * wq) * p.lp + Jt * 128 + c0 + 4 * piece;
         const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        // all eight loads of both rounds are issued before the first exchange (one L2 round trip, not two)
+        float4 tmp[2][4];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          float4 tmp[4];
+        for (int k = 0; k < 2; ++k)
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
             const int r = 8 * m + rsub;                         // row inside this warp's 32
-            tmp[m] = (It * 128 + 32 * wq + r < p.L)
-                         ? __ldg(reinterpret_cast<const float4*>(gsrc + (long long)r * p.lp + 16 * k)) : ninf;
+            tmp[k][m] = (It * 128 + 32 * wq + r < p.L)
+                            ? __ldg(reinterpret_cast<const float4*>(gsrc + (long long)r * p.lp + 16 * k)) : ninf;
           }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
             const int ra = 32 * wq + 8 * m + rsub;
-            *reinterpret_cast<float4*>(area + ra * 128 + (((ub + piece) ^ (ra & 7)) << 4)) = tmp[m];
+            *reinterpret_cast<float4*>(area + ra * 128 + (((ub + piece) ^ (ra & 7)) << 4)) = tmp[k][m];
           }
           __syncwarp();
 #pragma unroll
@@ -533,6 +567,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       if (stamp) FB_STAMP(18);
       // [Pd | dS'] and Z are free once the previous pair's last MMA group has completed
       if (t > 0) mbar_wait(bar_last, (t - 1) & 1);
+      if (I == 0 && J > 0) mbar_wait(bar_epfree, (J - 1) & 1);   // the dK / dV tiles staged there have been stored
       if (stamp) FB_STAMP(19);
       {
         // stage Pd and dS' rows: K-major [row a][64 keys] chunks of 16 KB, 128B swizzle; this thread's 32 columns
@@ -583,20 +618,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         // ---- key block J is complete: dK_J (x scale), dV_J -> bf16 (thread = key row, warpgroup = OC-column slice)
         mbar_wait(bar_last, ph);
         tc_fence_after();
-        const int j = j0 + a;
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
           uint32_t v[16];
           tmem_ld_32x16(lane_base + (w == 0 ? TB_DK : TB_DV) + OC * g, v);
           tmem_ld_wait();
-          if (j < p.L) {
-            __nv_bfloat16* base = (w == 0) ? p.dk + ((long long)b * p.L + j) * p.lddk : p.dv + ((long long)b * p.L + j) * p.lddv;
-            uint4* dst = reinterpret_cast<uint4*>(base + hh * 64 + OC * g);
-            const float sc_out = (w == 0) ? p.scale : 1.0f;
+          const float sc_out = (w == 0) ? p.scale : 1.0f;
+          uint8_t* rowp = s0 + w * 16384 + a * 128;          // [128 keys x 64] bf16 tile, 128B swizzle
 #pragma unroll
-            for (int u = 0; u < OC / 8; ++u) dst[u] = pack8_scaled(v + 8 * u, sc_out);
-          }
+          for (int u = 0; u < OC / 8; ++u)
+            *reinterpret_cast<uint4*>(rowp + (((2 * g + u) ^ (a & 7)) << 4)) = pack8_scaled(v + 8 * u, sc_out);
         }
+        tc_fence_before();
+        compute_arrive(bar_ep, lane);
         tc_fence_before();   // the next key block's first MMA overwrites dK / dV (ordered by bar_rdyA)
       }
       if (stamp) FB_STAMP(25);
@@ -611,17 +645,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     // ---- dQ of every query tile (x scale)
     mbar_wait(bar_last, (npairs - 1) & 1);
     tc_fence_after();
+    mbar_wait(bar_epfree, (nb - 1) & 1);   // the last key block's dK / dV have left the staging area
     for (int I = 0; I < nb; ++I) {
-      const int i = I * 128 + a;
       uint32_t v[16];
       tmem_ld_32x16(lane_base + TB_DQ + 64 * I + OC * g, v);
       tmem_ld_wait();
-      if (i < p.L) {
-        uint4* dst = reinterpret_cast<uint4*>(p.dq + ((long long)b * p.L + i) * p.lddq + hh * 64 + OC * g);
+      uint8_t* rowp = s0 + I * 16384 + a * 128;
 #pragma unroll
-        for (int u = 0; u < OC / 8; ++u) dst[u] = pack8_scaled(v + 8 * u, p.scale);
-      }
+      for (int u = 0; u < OC / 8; ++u)
+        *reinterpret_cast<uint4*>(rowp + (((2 * g + u) ^ (a & 7)) << 4)) = pack8_scaled(v + 8 * u, p.scale);
     }
+    tc_fence_before();
+    compute_arrive(bar_ep, lane);
   }
 
   tc_fence_before();
@@ -863,6 +898,10 @@ int attn_bwd(const fb_attn_bwd_args* a, cudaStream_t st) {
   } else {
     mpk = mk; mpq = mk;   // never dereferenced by the plain-attention instantiation
   }
+  CUtensorMap mdq, mdk, mdv;
+  if ((rc = make_rows_map(&mdq, a->dQ, a->lddq, a->B, a->L, a->h))) return rc;
+  if ((rc = make_rows_map(&mdk, a->dK, a->lddk, a->B, a->L, a->h))) return rc;
+  if ((rc = make_rows_map(&mdv, a->dV, a->lddv, a->B, a->L, a->h))) return rc;
   mds = mk;
   if (rel && a->ds_out) {
     // dS' [B, h, L, lp] as {key, query, head, batch} with a [64 keys x 128 queries] box (store side)
@@ -891,9 +930,9 @@ int attn_bwd(const fb_attn_bwd_args* a, cudaStream_t st) {
   }
   dim3 grid(a->h, a->B);
   if (rel)
-    attn_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, st>>>(mq, mk, mv, mdo, mpk, mpq, mds, p);
+    attn_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, st>>>(mq, mk, mv, mdo, mpk, mpq, mds, mdq, mdk, mdv, p);
   else
-    attn_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, st>>>(mq, mk, mv, mdo, mpk, mpq, mds, p);
+    attn_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, st>>>(mq, mk, mv, mdo, mpk, mpq, mds, mdq, mdk, mdv, p);
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -838,6 +838,28 @@ static int pick_block_n(int M, int N, int batch, int split_k) {
   return best;
 }
 
+// How many 2-CTA clusters of the GEMM kernel can be resident at once (GPC layout dependent); 0 when the query fails.
+int cluster_capacity() {
+  static int cap = -1;
+  if (cap < 0) {
+    using Cfg = GemmCfg<256>;
+    auto kern = gemm_kernel<256, false, false, false, 2>;
+    cap = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) == cudaSuccess) {
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(2 * 64); qc.blockDim = dim3(NUM_THREADS); qc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa; qc.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &qc) == cudaSuccess) cap = n;
+    }
+    (void)cudaGetLastError();
+  }
+  return cap;
+}
+
 int gemm(const fb_gemm_args* a, cudaStream_t st) {
   FB_REQUIRE(a != nullptr, "fb_gemm: null args");
   FB_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->batch >= 1, "fb_gemm: bad shape M=%d N=%d K=%d batch=%d", a->M,
@@ -857,8 +879,11 @@ int gemm(const fb_gemm_args* a, cudaStream_t st) {
   // 2-CTA multicast kernel (see gemm_kernel): big unbatched GEMMs with an even number of M blocks and K-major A
   static const bool cluster_enabled = (getenv("FB_GEMM_CLUSTER") == nullptr) || (atoi(getenv("FB_GEMM_CLUSTER")) != 0);
   const int mblocks_h = (a->M + BM - 1) / BM, nblocks_h = (a->N + bn - 1) / bn;
+  // (only when the cluster kernel can occupy (nearly) every SM: on a part whose GPCs leave SMs unpaired the 1-CTA
+  // kernel with all SMs is the better choice)
   const bool cluster_ok = cluster_enabled && batch_total == 1 && split_k == 1 && !a->a_mn_major && (bn == 256 || bn == 192) &&
-                          (mblocks_h % 2 == 0) && ((long long)mblocks_h * nblocks_h >= 2LL * num_sms());
+                          (mblocks_h % 2 == 0) && ((long long)mblocks_h * nblocks_h >= 2LL * num_sms()) &&
+                          (2 * cluster_capacity() >= num_sms() - 2);
 
   CUtensorMap ma, mb;
   int rc;
@@ -930,5 +955,6 @@ extern "C" {
 const char* fb_last_error(void) { return fb::last_error(); }
 int fb_abi_version(void) { return FB_ABI_VERSION; }
 long long fb_launch_count(void) { return fb::g_launches.load(); }
+int fb_gemm_cluster_capacity(void) { return fb::cluster_capacity(); }
 int fb_gemm(const fb_gemm_args* args, void* stream) { return fb::gemm(args, reinterpret_cast<cudaStream_t>(stream)); }
 }

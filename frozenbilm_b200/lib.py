@@ -173,6 +173,7 @@ EXPORTS = [
     "fb_conv_col2im", "fb_colsum_bf16", "fb_cross_entropy", "fb_dropout_apply", "fb_sumsq", "fb_adam_step",
     "fb_cast_f32_bf16", "fb_attn_bwd_prep", "fb_rel_to_bucket", "fb_attn_bwd", "fb_attn_bwd_rel",
     "fb_umma_probe", "fb_attn_bwd_set_debug", "fb_mlm_corrupt", "fb_gather_frames",
+    "fb_gemm_cluster_capacity",
 ]
 
 

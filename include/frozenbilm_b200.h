@@ -71,6 +71,8 @@ typedef struct fb_gemm_args {
 } fb_gemm_args;
 
 int fb_gemm(const fb_gemm_args* args, void* stream);
+/* Resident 2-CTA clusters of the multicast GEMM kernel on the current device (0: cluster kernel unavailable). */
+int fb_gemm_cluster_capacity(void);
 
 /* ------------------------------------------------------------------------------------------
  * fb_attn_fwd: fused disentangled self-attention forward for one layer pass (head_dim = 64).
