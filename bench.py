@@ -28,8 +28,8 @@ from frozenbilm_b200.config import CONFIG_XL  # noqa: E402
 from frozenbilm_b200.synth import synth_batch, synth_params, is_trainable  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one FFN up-projection launch at B = 32 (ncu --set full capture,
-# profiles/r1_ncu_full_summary.md: 56.1 MB read + 229.3 MB written)
-NCU_FFN1_DRAM_BYTES = 285.4e6
+# profiles/r1_ncu_full_summary.md: 66.5 MB read + 227.0 MB written)
+NCU_FFN1_DRAM_BYTES = 293.5e6
 METRIC = "samples/sec DeBERTa-XL+adapters seq352 bf16 train step (fwd+bwd+allreduce+clip+Adam)"
 B_PER_GPU, N_FRAMES, N_TEXT = 32, 10, 342
 
