@@ -79,6 +79,10 @@ class DebertaEngine:
         self.use_rel = True                                   # disentangled (c2p + p2c) attention
         # attention backward: one fused kernel per pass (default) or the staged GEMM schedule (FB_ATTN_BWD=staged)
         self.fused_attn_bwd = os.environ.get("FB_ATTN_BWD", "fused") != "staged"
+        # adapter weight gradients on a low-priority side stream (FB_DW_STREAM=0 keeps everything on one stream)
+        self.dw_side_stream = os.environ.get("FB_DW_STREAM", "1") != "0"
+        self._streams = None
+        self._side = None
         self.attn_scale = 1.0 / math.sqrt(3 * 64)             # deberta.py:769-777
         self.layer_prefix = "deberta.encoder.layer."
         if cfg.hidden_size % 128 != 0:
@@ -399,8 +403,32 @@ class DebertaEngine:
         B, L, F, Lt, T = self.dims
         H = cfg.hidden_size
         self.g = gviews
-        dy32 = self._bwd_head(scale, dlogits)
-        self._bwd_encoder(dy32)
+        if not self.dw_side_stream:
+            self._side = None
+            dy32 = self._bwd_head(scale, dlogits)
+            self._bwd_encoder(dy32)
+            self.saved = None
+            return
+        # The adapter weight gradients (dW = dY^T X, bias column sums: ~100 us of small split-K GEMMs per layer pass)
+        # feed nothing downstream.  They are issued on a LOW-priority stream while the backward chain runs on a
+        # high-priority one, so their CTAs are only scheduled on SMs the chain leaves idle: the partial last wave of
+        # the attention kernels (768 CTAs on 148 SMs) and every kernel's tail.  Their operands get per-pass buffers,
+        # so the chain never waits for them; the streams join before the optimizer.
+        cur = torch.cuda.current_stream()
+        if self._streams is None:
+            lo_p, hi_p = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
+            self._streams = (torch.cuda.Stream(device=self.device, priority=hi_p),
+                             torch.cuda.Stream(device=self.device, priority=lo_p))
+        hi, lo = self._streams
+        hi.wait_stream(cur)
+        lo.wait_stream(cur)
+        self._side = lo
+        with torch.cuda.stream(hi):
+            dy32 = self._bwd_head(scale, dlogits)
+            self._bwd_encoder(dy32)
+        self._side = None
+        cur.wait_stream(hi)
+        cur.wait_stream(lo)
         self.saved = None
 
     def _bwd_head(self, scale, dlogits):
@@ -504,7 +532,9 @@ class DebertaEngine:
         T, H = dy32.shape
         r = cfg.r_attn if name == "att" else cfg.r_ff
         ds32 = ws.get(f"bw.{name}.ds32.{slot}", (T, H), F32)
-        gw16 = ws.get(f"bw.{name}.gw16", (T, H), BF16)
+        r_ = cfg.r_attn if name == "att" else cfg.r_ff
+        # per-pass operand buffers when the weight gradients run asynchronously (never overwritten before they are read)
+        gw16 = ws.get(f"bw.{name}.gw16" + (f".{pass_id}" if (self._side is not None and r_) else ""), (T, H), BF16)
         lib.layernorm_bwd(dy32, rec["s"], rec["mean"], rec["rstd"], P[ln_prefix + "weight"],
                           in_drop=self.drop(cfg.hidden_dropout_prob, pass_id * 8 + site_hid), dx32=ds32, dx16=gw16,
                           dgamma=self._g(ln_prefix + "weight"), dbeta=self._g(ln_prefix + "bias"),
@@ -514,15 +544,26 @@ class DebertaEngine:
             wu, wd = self.t16(ad_prefix + "up.weight"), self.t16(ad_prefix + "down.weight")
             ad = self.drop(cfg.adapter_dropout, pass_id * 8 + site_ad)
             inv_keep = 1.0 / (1.0 - ad.p) if ad.p > 0 else 1.0
-            dz16 = ws.get(f"bw.{name}.dz16", (T, r), BF16)
+            side = self._side
+            dz16 = ws.get(f"bw.{name}.dz16" + (f".{pass_id}" if side is not None else ""), (T, r), BF16)
             # d(zd) = gw . Wu ; through dropout and ReLU: zd > 0 <=> kept and pre-activation > 0
             lib.gemm(gw16, wu, dz16, b_mn_major=True, alpha=inv_keep, aux=z16, aux_op=lib.FB_AUX_MUL_RELU_MASK)
             sk = max(1, min(32, T // 512))
-            lib.gemm(gw16, z16, self._g(ad_prefix + "up.weight"), a_mn_major=True, b_mn_major=True, split_k=sk,
-                     accumulate=True)
-            lib.gemm(dz16, u16, self._g(ad_prefix + "down.weight"), a_mn_major=True, b_mn_major=True, split_k=sk,
-                     accumulate=True)
-            lib.colsum_bf16(dz16, self._g(ad_prefix + "down.bias"))
+
+            def weight_grads():
+                lib.gemm(gw16, z16, self._g(ad_prefix + "up.weight"), a_mn_major=True, b_mn_major=True, split_k=sk,
+                         accumulate=True)
+                lib.gemm(dz16, u16, self._g(ad_prefix + "down.weight"), a_mn_major=True, b_mn_major=True, split_k=sk,
+                         accumulate=True)
+                lib.colsum_bf16(dz16, self._g(ad_prefix + "down.bias"))
+
+            if side is None:
+                weight_grads()
+            else:
+                ev = torch.cuda.current_stream().record_event()
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    weight_grads()
             du16 = ws.get(f"bw.{name}.du16", (T, H), BF16)
             lib.gemm(dz16, wd, du16, b_mn_major=True, aux=gw16, aux_op=lib.FB_AUX_ADD)
         else:
