@@ -34,6 +34,20 @@ def _ceil8(n):
     return (n + 7) // 8 * 8
 
 
+_STREAMS = {}
+
+
+def _priority_streams(device):
+    """(high-priority, low-priority) stream pair of a device, created once per process."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    st = _STREAMS.get(key)
+    if st is None:
+        lo_p, hi_p = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
+        st = (torch.cuda.Stream(device=device, priority=hi_p), torch.cuda.Stream(device=device, priority=lo_p))
+        _STREAMS[key] = st
+    return st
+
+
 class Workspace:
     """Named, shape-keyed scratch tensors reused across steps (no per-step cudaMalloc)."""
 
@@ -81,7 +95,6 @@ class DebertaEngine:
         self.fused_attn_bwd = os.environ.get("FB_ATTN_BWD", "fused") != "staged"
         # adapter weight gradients on a low-priority side stream (FB_DW_STREAM=0 keeps everything on one stream)
         self.dw_side_stream = os.environ.get("FB_DW_STREAM", "1") != "0"
-        self._streams = None
         self._side = None
         self.attn_scale = 1.0 / math.sqrt(3 * 64)             # deberta.py:769-777
         self.layer_prefix = "deberta.encoder.layer."
@@ -415,11 +428,7 @@ class DebertaEngine:
         # the attention kernels (768 CTAs on 148 SMs) and every kernel's tail.  Their operands get per-pass buffers,
         # so the chain never waits for them; the streams join before the optimizer.
         cur = torch.cuda.current_stream()
-        if self._streams is None:
-            lo_p, hi_p = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
-            self._streams = (torch.cuda.Stream(device=self.device, priority=hi_p),
-                             torch.cuda.Stream(device=self.device, priority=lo_p))
-        hi, lo = self._streams
+        hi, lo = _priority_streams(self.device)
         hi.wait_stream(cur)
         lo.wait_stream(cur)
         self._side = lo
