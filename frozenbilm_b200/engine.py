@@ -96,6 +96,11 @@ class DebertaEngine:
         # adapter weight gradients on a low-priority side stream (FB_DW_STREAM=0 keeps everything on one stream)
         self.dw_side_stream = os.environ.get("FB_DW_STREAM", "1") != "0"
         self._side = None
+        # ... and the whole positional-gradient chain (fb_attn_bwd_rel -> dR; FB_REL_STREAM=0 keeps it in the chain).
+        # FB_REL_UNITS = tile pairs per CTA of the low-priority band-gradient kernel (0 = the kernel's own choice);
+        # measured at config 2: off 75.2 ms, 8 units 73.9, 4 units 73.8, 2 units 76.0 (too many accumulator flushes)
+        self.rel_side_stream = self.dw_side_stream and os.environ.get("FB_REL_STREAM", "1") != "0"
+        self.rel_side_units = int(os.environ.get("FB_REL_UNITS", "0"))
         self.attn_scale = 1.0 / math.sqrt(3 * 64)             # deberta.py:769-777
         self.layer_prefix = "deberta.encoder.layer."
         if cfg.hidden_size % 128 != 0:
@@ -508,6 +513,8 @@ class DebertaEngine:
             lib.conv_col2im(dcol16, B, L, H, dx32, accumulate=True)
         self._bwd_embeddings(dx32, "deberta.embeddings.", rowmask=self.mask_u8)
         # ---- relative-embedding LayerNorm (trainable under ft_ln): gamma/beta only, the table is frozen
+        if self._side is not None and self.rel_side_stream:
+            torch.cuda.current_stream().wait_stream(self._side)   # dR has been accumulated on the side stream
         lib.layernorm_bwd(self._dR32, P[c + "rel_embeddings.weight"], sv["rel_mean"], sv["rel_rstd"],
                           P[c + "LayerNorm.weight"], dgamma=self._g(c + "LayerNorm.weight"),
                           dbeta=self._g(c + "LayerNorm.bias"))
@@ -621,7 +628,10 @@ class DebertaEngine:
         Q, K, V = rec["Q"], rec["K"], rec["V"]
         lp = (L + 127) // 128 * 128
         rel = self.use_rel
-        ds = ws.get("bw.ds", (B, h, L, lp), BF16) if rel else None
+        # The gradients of the positional projections (fb_attn_bwd_rel and the chain down to dR) feed nothing on the
+        # token path: with the side stream they run at low priority from a per-pass copy of dS'.
+        side = self._side if self.rel_side_stream else None
+        ds = ws.get("bw.ds" + (f".{pass_id}" if side is not None else ""), (B, h, L, lp), BF16) if rel else None
         ad = self.drop(cfg.attention_probs_dropout_prob, pass_id * 8 + SITE_PROBS)
         lib.attn_bwd(Q, K, V, rec["ctx"], dctx16, rec["s2"], rec["lse"], rec["pkr"], rec["pq"],
                      dqkv16[:, :H], dqkv16[:, H:2 * H], dqkv16[:, 2 * H:], ds_out=ds, B=B, L=L, h=h,
@@ -631,8 +641,19 @@ class DebertaEngine:
         rel_rows, _ = lib.rel_table_geometry(L)
         gpk = ws.get("bw.gpk", (h, rel_rows, 64), F32)
         gpq = ws.get("bw.gpq", (h, rel_rows, 64), F32)
-        lib.attn_bwd_rel(ds, Q, K, gpk, gpq, B=B, L=L, h=h, scale=self.attn_scale)
-        self._bwd_rel_tables(gpq, gpk, i, pass_id, L, h)
+
+        def positional_grads():
+            lib.attn_bwd_rel(ds, Q, K, gpk, gpq, B=B, L=L, h=h, scale=self.attn_scale,
+                             units_per_cta=self.rel_side_units if side is not None else 0)
+            self._bwd_rel_tables(gpq, gpk, i, pass_id, L, h)
+
+        if side is None:
+            positional_grads()
+        else:
+            ev = torch.cuda.current_stream().record_event()
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                positional_grads()
 
     def _bwd_rel_tables(self, gpq, gpk, i, pass_id, L, h):
         """d(per-relative-position tables) -> d(Linear_{q|k}(dropout(R))) -> accumulate dR (deberta.py:847-853)."""
