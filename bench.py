@@ -121,7 +121,11 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = CONFIG_XL.replace(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, adapter_dropout=0.0)
+    base = CONFIG_XL
+    if args.tiny:   # contract self-test only (tests/test_bench_contract_cpu.py): same code path, toy dimensions
+        from frozenbilm_b200.config import CONFIG_TINY
+        base = CONFIG_TINY
+    cfg = base.replace(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, adapter_dropout=0.0)
     step, bsz = cpu_step_fn(cfg, batch=1)
     for _ in range(args.warmup):
         step()
@@ -135,7 +139,8 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "DeBERTa-V2-XL frozen + adapters ds8, 10 frames + 342 tokens (WebVid MLM shape)",
+            "config": {"workload": ("TOY MODEL (contract self-test), " if args.tiny else "") +
+                                   "DeBERTa-V2-XL frozen + adapters ds8, 10 frames + 342 tokens (WebVid MLM shape)",
                        "global_batch": bsz, "seq_len": N_FRAMES + N_TEXT, "parallelism": "cpu"},
             "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -154,6 +159,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", type=int, default=0, help="debug: override the layer count")
+    ap.add_argument("--tiny", action="store_true", help="reference arm only: toy model (JSON-contract self-test)")
     ap.add_argument("--profile-step", action="store_true",
                     help="profiling aid (ncu --profile-from-start off): warm up, bracket ONE resident step with "
                          "cudaProfilerStart/Stop, print nothing, exit")
