@@ -112,7 +112,7 @@ def cpu_step_fn(cfg, seed=1234, batch=1):
         out["loss"].backward()
         torch.nn.utils.clip_grad_norm_([P[n] for n in names_t], 0.1)
         opt.step()
-        return float(out["loss"])
+        return float(out["loss"].detach())
 
     return step, batch
 
@@ -367,13 +367,16 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         try:
             cfg_cpu = cfg.replace(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, adapter_dropout=0.0)
-            step, bsz = cpu_step_fn(cfg_cpu, batch=1)
-            t0 = time.perf_counter()
+            # bounded sample of the same workload: B = 2 per step, 1 untimed + 3 timed steps (about 10-15 s of CPU work)
+            step, bsz = cpu_step_fn(cfg_cpu, batch=2)
             step()
-            dt = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            for _ in range(3):
+                step()
+            dt = (time.perf_counter() - t0) / 3
             line["cpu_baseline"] = {"value": bsz / dt, "unit": "samples/s", "cores": torch.get_num_threads(),
-                                    "kind": "port", "sample": "1 step of B=1 (10 frames + 342 tokens), fp32 oracle "
-                                    "port of the reference path, fwd+bwd+clip+Adam, dropout off"}
+                                    "kind": "port", "sample": "3 timed steps (after 1 warm-up) of B=2 (10 frames + 342 "
+                                    "tokens), fp32 oracle port of the reference path, fwd+bwd+clip+Adam, dropout off"}
         except Exception as ex:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "error": repr(ex)[:200]}
     print(json.dumps(line), flush=True)
