@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 105 python bench.py --steps 6 > gpurun_out/bench_final.json 2> gpurun_out/bench.err; echo "bench exit $?"; cat gpurun_out/bench_final.json | cut -c1-200; tail -2 gpurun_out/bench.err
+timeout 25 python scripts/gpu_umma_m64_probe.py > gpurun_out/umma_m64_probe.log 2>&1; echo "probe exit $?"; head -70 gpurun_out/umma_m64_probe.log | cut -c1-160
