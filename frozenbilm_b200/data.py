@@ -68,6 +68,18 @@ class FeatureShard:
                 arrays.append(None)
         return cls.from_arrays(arrays, features_dim, device)
 
+    def save(self, path):
+        """One file for the whole feature set (what a dataset preparation step writes once): packed fp16 rows +
+        per-video offsets / frame counts, readable with ``FeatureShard.load``."""
+        np.savez(path, shard=self.shard.cpu().numpy(), offsets=self.offsets.cpu().numpy(),
+                 nframes=self.nframes.cpu().numpy())
+
+    @classmethod
+    def load(cls, path, device="cuda"):
+        z = np.load(path)
+        return cls(torch.from_numpy(z["shard"]).to(device), torch.from_numpy(z["offsets"]).to(device),
+                   torch.from_numpy(z["nframes"]).to(device))
+
     def batch(self, indices, max_feats=10, bf16=False):
         """-> {"video": [B, max_feats, D] (fp32, or bf16 for the projection GEMM), "video_len": int64 [B]}."""
         idx = torch.as_tensor(indices, device=self.shard.device, dtype=torch.int64)

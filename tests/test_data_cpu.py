@@ -57,3 +57,27 @@ def test_mlm_corrupt_semantics():
     assert (l0 == -100).all()
     _, l1 = dor.mlm_corrupt(ids, None, None, MASK, V, 1.0, seed=1)
     assert (l1 != -100).mean() > 0.999999
+
+
+def test_feature_shard_packing_and_roundtrip(tmp_path):
+    """Host side of the feature reader: packing, offsets, missing videos, save / load (no GPU involved)."""
+    import torch
+    from frozenbilm_b200.data import FeatureShard
+    rng = np.random.default_rng(1)
+    arrays = [rng.standard_normal((3, 8)).astype(np.float16), None, rng.standard_normal((5, 8)).astype(np.float16),
+              np.zeros((0, 8), np.float16)]
+    fs = FeatureShard.from_arrays(arrays, features_dim=8, device="cpu")
+    assert fs.nframes.tolist() == [3, 0, 5, 0] and fs.offsets.tolist() == [0, 3, 3, 8]
+    assert fs.shard.dtype == torch.float16 and fs.shard.shape == (8, 8)
+    assert np.array_equal(fs.shard[3:8].numpy(), arrays[2])
+    p = tmp_path / "shard.npz"
+    fs.save(p)
+    fs2 = FeatureShard.load(p, device="cpu")
+    assert torch.equal(fs2.shard, fs.shard) and torch.equal(fs2.offsets, fs.offsets) and torch.equal(fs2.nframes, fs.nframes)
+    # the oracle on the packed representation reproduces the per-video rule
+    v, l = dor.gather_frames(fs2.shard.numpy(), fs2.offsets.numpy(), fs2.nframes.numpy(), 4)
+    assert l.tolist() == [3, 0, 4, 0] and np.array_equal(v[2], arrays[2][[0, 1, 2, 3]].astype(np.float32))
+    # files: a missing path becomes an empty video (reference videotext_dataset.py:39-41)
+    np.save(tmp_path / "7.mp4.npy", arrays[0])
+    fs3 = FeatureShard.from_files([str(tmp_path / "7.mp4.npy"), str(tmp_path / "missing.mp4.npy")], features_dim=8, device="cpu")
+    assert fs3.nframes.tolist() == [3, 0]
