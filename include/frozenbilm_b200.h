@@ -134,7 +134,9 @@ int fb_rel_to_bucket(const float* gpq, const float* gpk, int H, int h, const int
  *   dV = Pd^T.dO ; dQ = scale (dS'.K + Z1.PKrel) ; dK = scale (dS'^T.Q + Z2.PQrel)   (Z1/Z2 = dS' regrouped by
  *   relative position inside shared memory, never in HBM).  ds_out (optional, bf16 [B,h,L,lp]) receives the
  *   UNSCALED dS' and feeds fb_attn_bwd_rel.  PKrev is the row-reversed PKrel table of fb_build_rel_tables.
- * PKrev = PQrel = NULL selects plain attention (BERT, bert.py:141-191).  O and dO share the row pitch ldo. */
+ * PKrev = PQrel = NULL selects plain attention (BERT, bert.py:141-191).  O and dO share the row pitch ldo.
+ * Every operand and output is moved by TMA: base pointers 16-byte aligned, row pitches multiples of 8 elements;
+ * rows >= L of the last 128-row tile are clipped by the tensor maps (nothing is written past L). */
 typedef struct fb_attn_bwd_args {
   int B, L, h, lp;                           /* lp = L rounded up to 128 = row pitch of s2 / ds_out */
   const void* Q; long long ldq;              /* bf16 [B*L, >= h*64] views, as in fb_attn_fwd */
