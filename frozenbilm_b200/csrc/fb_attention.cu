@@ -40,7 +40,7 @@ struct AttnParams {
   const uint8_t* mask;
   __nv_bfloat16* ctx; long long ldc;
   float* lse;
-  float* s_out; int lp;   // optional [B, h, L, lp] fp32 copy of the masked, scaled scores (log2 domain)
+  __half* s_out; int lp;  // optional [B, h, L, lp] fp16 copy of the masked, scaled scores (log2 domain)
   float scale_log2;
   int mask_queries;                        // DeBERTa: M[i,j] = m_i * m_j;  BERT: key mask only
   float inv_keep; uint32_t drop_thresh16;  // keep iff rnd16 >= thresh
@@ -364,32 +364,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
       }
       if (p.s_out != nullptr) {
-        // Saved scores for the backward.  A direct store would touch 32 different 128-byte lines per instruction
-        // (thread = row): instead each warp transposes its 32 x 32 chunk through the staging bytes its own lanes
-        // have just consumed (T1 / T2 rows a, columns [64g, 64g+64): private to the warp, so __syncwarp suffices)
-        // and writes four complete lines per instruction.
+        // Saved scores for the backward, as fp16 (11-bit mantissa: |error| <= 2^-7 in the log2 domain for |s| < 16,
+        // i.e. <= 0.55 % on a probability -- the size of the bf16 rounding of P that feeds P.V; the fp32 dump this
+        // replaces cost 415 MB of writes + 415 MB of reads per layer pass at B = 32).  A direct store would touch 32
+        // different 128-byte lines per instruction (thread = row): instead each warp transposes its 32 rows x 128
+        // bytes through the staging bytes its own lanes have just consumed (T1 rows a, halves [64g, 64g+64): private
+        // to the warp, so __syncwarp suffices) and writes four complete lines per instruction.
         const int rowb = (T_PITCH * 2);
+        uint8_t* mine = reinterpret_cast<uint8_t*>(T1) + a * rowb + 128 * g;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          uint8_t* mine = reinterpret_cast<uint8_t*>(q == 0 ? T1 : T2) + a * rowb + 128 * g;
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            *reinterpret_cast<float4*>(mine + 16 * u) =
-                make_float4(__uint_as_float(sv[q][4 * u]), __uint_as_float(sv[q][4 * u + 1]),
-                            __uint_as_float(sv[q][4 * u + 2]), __uint_as_float(sv[q][4 * u + 3]));
+          for (int u = 0; u < 4; ++u) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __half2 h2 = __floats2half2_rn(__uint_as_float(sv[q][8 * u + 2 * e]), __uint_as_float(sv[q][8 * u + 2 * e + 1]));
+              w[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(mine + 64 * q + 16 * u) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
         }
         __syncwarp();
         const int rr = lane >> 3, uu = lane & 7;
-        float* gbase = p.s_out + (((long long)b * p.h + hh) * p.L + i0 + 32 * wq) * p.lp + j0 + 64 * g + 4 * uu;
+        __half* gbase = p.s_out + (((long long)b * p.h + hh) * p.L + i0 + 32 * wq) * p.lp + j0 + 64 * g + 8 * uu;
+        const uint8_t* tb = reinterpret_cast<const uint8_t*>(T1) + (32 * wq) * rowb + 128 * g + 16 * uu;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const uint8_t* tb = reinterpret_cast<const uint8_t*>(q == 0 ? T1 : T2) + (32 * wq) * rowb + 128 * g + 16 * uu;
-#pragma unroll
-          for (int st = 0; st < 8; ++st) {
-            const int r = 4 * st + rr;
-            const float4 x = *reinterpret_cast<const float4*>(tb + r * rowb);
-            if (i0 + 32 * wq + r < p.L) *reinterpret_cast<float4*>(gbase + (long long)r * p.lp + 32 * q) = x;
-          }
+        for (int st = 0; st < 8; ++st) {
+          const int r = 4 * st + rr;
+          const uint4 x = *reinterpret_cast<const uint4*>(tb + r * rowb);
+          if (i0 + 32 * wq + r < p.L) *reinterpret_cast<uint4*>(gbase + (long long)r * p.lp) = x;
         }
       }
       // S, X1 and the staging buffers of this block are consumed: the next block's S / X2 may be issued
@@ -512,7 +516,7 @@ build_rel_tables_kernel(const __nv_bfloat16* __restrict__ pqk, long long ld, int
 // ---------------------------------------------------------------------------------------------
 struct AttnBwdParams {
   int B, L, h, lp, rel_rows, rel_off;
-  const float* s2; const float* lse; const __nv_bfloat16* dp; const __nv_bfloat16* ctx; const __nv_bfloat16* dctx;
+  const __half* s2; const float* lse; const __nv_bfloat16* dp; const __nv_bfloat16* ctx; const __nv_bfloat16* dctx;
   long long ldc;
   __nv_bfloat16* ds; __nv_bfloat16* pd; __nv_bfloat16* z1;
   float scale; DropSpec drop;
@@ -543,9 +547,11 @@ __global__ void __launch_bounds__(256) attn_bwd_ds_kernel(const AttnBwdParams p)
   for (int j0 = lane * 4; j0 < p.lp; j0 += 128) {
     float dsv[4] = {0.f, 0.f, 0.f, 0.f}, pdv[4] = {0.f, 0.f, 0.f, 0.f};
     if (j0 < p.L) {   // L is a multiple of 4 or the tail columns are masked scores (-inf) anyway
-      const float4 s4 = *reinterpret_cast<const float4*>(p.s2 + row * p.lp + j0);
+      const uint2 s4 = *reinterpret_cast<const uint2*>(p.s2 + row * p.lp + j0);
       const uint2 dp2 = *reinterpret_cast<const uint2*>(p.dp + row * p.lp + j0);
-      const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+      const float2 s01 = __half22float2(*reinterpret_cast<const __half2*>(&s4.x));
+      const float2 s23 = __half22float2(*reinterpret_cast<const __half2*>(&s4.y));
+      const float sv[4] = {s01.x, s01.y, s23.x, s23.y};
       const float2 d01 = unpack_bf16(dp2.x), d23 = unpack_bf16(dp2.y);
       float dpv[4] = {d01.x, d01.y, d23.x, d23.y};
       uint32_t keep = 0xF;
@@ -661,7 +667,7 @@ int attn_fwd(const fb_attn_args* a, cudaStream_t st) {
   p.mask = a->mask;
   p.ctx = reinterpret_cast<__nv_bfloat16*>(a->ctx); p.ldc = a->ldc;
   p.lse = a->lse;
-  p.s_out = a->s_out; p.lp = lpad;
+  p.s_out = reinterpret_cast<__half*>(a->s_out); p.lp = lpad;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.mask_queries = a->key_mask_only ? 0 : 1;
   if (a->dropout_p > 0.0f) {
@@ -710,7 +716,7 @@ int attn_bwd_prep(const fb_attn_bwd_prep_args* a, cudaStream_t st) {
   FB_REQUIRE(a->L > 0 && a->L <= 512 && a->lp >= a->L && a->lp <= 512, "fb_attn_bwd_prep: bad L/lp");
   AttnBwdParams p;
   p.B = a->B; p.L = a->L; p.h = a->h; p.lp = a->lp; p.rel_rows = a->rel_rows; p.rel_off = a->rel_off;
-  p.s2 = a->s2; p.lse = a->lse; p.dp = (const __nv_bfloat16*)a->dp; p.ctx = (const __nv_bfloat16*)a->ctx;
+  p.s2 = (const __half*)a->s2; p.lse = a->lse; p.dp = (const __nv_bfloat16*)a->dp; p.ctx = (const __nv_bfloat16*)a->ctx;
   p.dctx = (const __nv_bfloat16*)a->dctx; p.ldc = a->ldc;
   p.ds = (__nv_bfloat16*)a->ds; p.pd = (__nv_bfloat16*)a->pd; p.z1 = (__nv_bfloat16*)a->z1;
   p.scale = a->scale; p.drop = make_drop(a->dropout_p, a->seed, a->offset);

@@ -39,9 +39,13 @@
 // fb_attn_bwd_rel:  gradients of the positional projections.  They are sums over batch AND over all tile
 //                   pairs of one diagonal, so a CTA owns (head, diagonal, slice of the batch), keeps the two
 //                   [256 x 64] fp32 band accumulators in TMEM across its whole slice and flushes once.
+#include <cuda_fp16.h>
 #include <cstring>
 
 #include "../../include/frozenbilm_b200.h"
+#ifdef FB_DEBUG_SURFACE
+#include "../../include/frozenbilm_b200_debug.h"
+#endif
 #include "fb_common.cuh"
 
 namespace fb {
@@ -146,7 +150,7 @@ static constexpr uint32_t TB_DP = 0, TB_DQ = 128, TB_DK = 384, TB_DV = 448;
 
 struct AttnBwdFusedParams {
   int B, L, h, nb, lp, rel_off, rel_rows;
-  const float* s2; const float* lse;
+  const __half* s2; const float* lse;
   const __nv_bfloat16* ctx; const __nv_bfloat16* dctx; long long ldc;
   __nv_bfloat16* dq; long long lddq;
   __nv_bfloat16* dk; long long lddk;
@@ -155,10 +159,14 @@ struct AttnBwdFusedParams {
   float scale; DropSpec drop;
   long long* dbg;   // optional [pairs][32] clock64 stamps of CTA (0,0): events 0-15 control thread, 16-31 compute warp 0
 };
+#ifdef FB_DEBUG_SURFACE   // phase stamps exist only in the test-only debug library (include/frozenbilm_b200_debug.h)
 #define FB_STAMP(ev)                                                                         \
   do {                                                                                       \
     if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[t * 32 + (ev)] = clock64(); \
   } while (0)
+#else
+#define FB_STAMP(ev) do { } while (0)
+#endif
 
 template <bool REL>
 __global__ void __launch_bounds__(AB_THREADS, 1)
@@ -449,66 +457,64 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     constexpr int OC = 64 / NG;                       // output columns per thread in the dQ / dK / dV epilogues
     const bool do_drop = p.drop.thresh16 != 0;
 
-    // This thread's CW saved scores of a pair (fp32, log2 domain; -inf where masked or padded).  HBM latency under
-    // this access pattern is several microseconds, so the segment of pair t+1 is hinted into L2 at the start of
+    // This thread's CW saved scores of a pair (fp16 pairs, log2 domain; -inf where masked or padded).  HBM latency
+    // under this access pattern is several microseconds, so the segment of pair t+1 is hinted into L2 at the start of
     // pair t and loaded into registers while the last MMA group of pair t runs.
-    float4 sc[CW / 4];
-    auto score_ptr = [&](int tt) -> const float4* {
+    uint32_t sc[CW / 2];
+    constexpr uint32_t NINF2 = 0xFC00FC00u;   // half2(-inf, -inf)
+    auto score_ptr = [&](int tt) -> const __half* {
       const int Jt = tt / nb, It = tt - Jt * nb;
       const int it = It * 128 + a;
       if (tt >= npairs || it >= p.L) return nullptr;
-      return reinterpret_cast<const float4*>(p.s2 + (((long long)b * p.h + hh) * p.L + it) * p.lp + Jt * 128 + CW * g);
+      return p.s2 + (((long long)b * p.h + hh) * p.L + it) * p.lp + Jt * 128 + CW * g;
     };
     auto load_scores = [&](int tt) {
       if constexpr (REL) {
-        // Coalesced: a direct load (thread = row, 128 contiguous bytes each) touches 32 different lines per
-        // instruction and kept the LSU busy for ~4000 cycles per tile pair on the critical path.  Instead 4 lanes
-        // fetch 64 bytes of one row (8 rows per instruction), the warp exchanges the pieces through the 64 bytes per
-        // row that its own lanes own in the dS' half of the staging area (free once bar_mmaB has completed:
-        // the content / transpose MMAs and the dS' bulk store no longer read it), two rounds of 16 columns.
+        // Coalesced: a direct load (thread = row, 64 contiguous bytes each) touches 32 different lines per
+        // instruction.  Instead 4 lanes fetch the 64 bytes of one row (8 rows per instruction), and the warp exchanges
+        // the pieces through the 64 bytes per row that its own lanes own in the dS' half of the staging area (free
+        // once bar_mmaB has completed: the content / transpose MMAs and the dS' bulk store no longer read it).
         const int Jt = tt / nb, It = tt - Jt * nb;
         if (tt >= npairs) {
 #pragma unroll
-          for (int u = 0; u < CW / 4; ++u) sc[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+          for (int u = 0; u < CW / 2; ++u) sc[u] = NINF2;
           return;
         }
         const int c0 = CW * g;
         uint8_t* area = s0 + 32768 + (c0 >> 6) * 16384;       // this column group's 64-key chunk of dS'
         const int ub = (c0 & 63) >> 3;                          // first of its four 16-byte units in a row
         const int rsub = lane >> 2, piece = lane & 3;
-        const float* gsrc = p.s2 + (((long long)b * p.h + hh) * p.L + It * 128 + 32 * wq) * p.lp + Jt * 128 + c0 + 4 * piece;
-        const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        // all eight loads of both rounds are issued before the first exchange (one L2 round trip, not two)
-        float4 tmp[2][4];
+        const __half* gsrc = p.s2 + (((long long)b * p.h + hh) * p.L + It * 128 + 32 * wq) * p.lp + Jt * 128 + c0 + 8 * piece;
+        const uint4 ninf = make_uint4(NINF2, NINF2, NINF2, NINF2);
+        uint4 tmp[4];
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const int r = 8 * m + rsub;                         // row inside this warp's 32
-            tmp[k][m] = (It * 128 + 32 * wq + r < p.L)
-                            ? __ldg(reinterpret_cast<const float4*>(gsrc + (long long)r * p.lp + 16 * k)) : ninf;
-          }
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const int ra = 32 * wq + 8 * m + rsub;
-            *reinterpret_cast<float4*>(area + ra * 128 + (((ub + piece) ^ (ra & 7)) << 4)) = tmp[k][m];
-          }
-          __syncwarp();
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            sc[4 * k + u] = *reinterpret_cast<const float4*>(area + a * 128 + (((ub + u) ^ (a & 7)) << 4));
-          __syncwarp();
+        for (int m = 0; m < 4; ++m) {
+          const int r = 8 * m + rsub;                           // row inside this warp's 32
+          tmp[m] = (It * 128 + 32 * wq + r < p.L) ? __ldg(reinterpret_cast<const uint4*>(gsrc + (long long)r * p.lp)) : ninf;
         }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int ra = 32 * wq + 8 * m + rsub;
+          *reinterpret_cast<uint4*>(area + ra * 128 + (((ub + piece) ^ (ra & 7)) << 4)) = tmp[m];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint4 q = *reinterpret_cast<const uint4*>(area + a * 128 + (((ub + u) ^ (a & 7)) << 4));
+          sc[4 * u] = q.x; sc[4 * u + 1] = q.y; sc[4 * u + 2] = q.z; sc[4 * u + 3] = q.w;
+        }
+        __syncwarp();
       } else {
-        const float4* src = score_ptr(tt);
+        const uint4* src = reinterpret_cast<const uint4*>(score_ptr(tt));
         if (src != nullptr) {
 #pragma unroll
-          for (int u = 0; u < CW / 4; ++u) sc[u] = __ldg(src + u);
+          for (int u = 0; u < CW / 8; ++u) {
+            const uint4 q = __ldg(src + u);
+            sc[4 * u] = q.x; sc[4 * u + 1] = q.y; sc[4 * u + 2] = q.z; sc[4 * u + 3] = q.w;
+          }
         } else {
 #pragma unroll
-          for (int u = 0; u < CW / 4; ++u) sc[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+          for (int u = 0; u < CW / 2; ++u) sc[u] = NINF2;
         }
       }
     };
@@ -522,7 +528,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const bool stamp = (threadIdx.x == 0);
       if (stamp) FB_STAMP(16);
       {
-        const float4* nxt = score_ptr(t + 1);
+        const __half* nxt = score_ptr(t + 1);
         if (nxt != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
       }
       float lse = Lr[0], D = Dr[0];
@@ -551,8 +557,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int idx = 8 * gg + e;           // column inside this thread's CW
-            const float4 s4 = sc[idx >> 2];
-            const float s = (idx & 3) == 0 ? s4.x : (idx & 3) == 1 ? s4.y : (idx & 3) == 2 ? s4.z : s4.w;
+            const float2 s2f = __half22float2(*reinterpret_cast<const __half2*>(&sc[idx >> 1]));
+            const float s = (idx & 1) ? s2f.y : s2f.x;
             const float pr = ex2_approx(s - lse);   // s = -inf (masked / padded row) or lse = +inf (dead row) -> 0
             pdv[e] = pr * fk[e];
             dsv[e] = pr * fmaf(__uint_as_float(v[idx]), fk[e], -D);
@@ -913,7 +919,7 @@ int attn_bwd(const fb_attn_bwd_args* a, cudaStream_t st) {
   AttnBwdFusedParams p;
   memset(&p, 0, sizeof(p));
   p.B = a->B; p.L = a->L; p.h = a->h; p.nb = lpad / 128; p.lp = lpad; p.rel_off = a->rel_off; p.rel_rows = a->rel_rows;
-  p.s2 = a->s2; p.lse = a->lse;
+  p.s2 = (const __half*)a->s2; p.lse = a->lse;
   p.ctx = (const __nv_bfloat16*)a->O; p.dctx = (const __nv_bfloat16*)a->dO; p.ldc = a->ldo;
   p.dq = (__nv_bfloat16*)a->dQ; p.lddq = a->lddq;
   p.dk = (__nv_bfloat16*)a->dK; p.lddk = a->lddk;
@@ -987,10 +993,12 @@ extern "C" {
 int fb_attn_bwd(const fb_attn_bwd_args* args, void* stream) {
   return fb::attn_bwd(args, reinterpret_cast<cudaStream_t>(stream));
 }
+#ifdef FB_DEBUG_SURFACE
 int fb_attn_bwd_set_debug(long long* stamps) {
   fb::g_attn_bwd_dbg = stamps;
   return 0;
 }
+#endif
 int fb_attn_bwd_rel(const fb_attn_bwd_rel_args* args, void* stream) {
   return fb::attn_bwd_rel(args, reinterpret_cast<cudaStream_t>(stream));
 }

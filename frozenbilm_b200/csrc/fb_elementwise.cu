@@ -366,9 +366,19 @@ __device__ __forceinline__ void ce_combine(float& m, float& s, float m2, float s
   s = s * a + s2 * b;
   m = mn;
 }
+__device__ __forceinline__ void ce_store4(__nv_bfloat16* d, const float (&g)[4]) {
+  *reinterpret_cast<uint2*>(d) = make_uint2(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]));
+}
+__device__ __forceinline__ void ce_store4(float* d, const float (&g)[4]) {
+  d[0] = g[0]; d[1] = g[1]; d[2] = g[2]; d[3] = g[3];   // rows need not be 16-byte aligned
+}
+__device__ __forceinline__ void ce_store1(__nv_bfloat16* d, float g) { *d = __float2bfloat16_rn(g); }
+__device__ __forceinline__ void ce_store1(float* d, float g) { *d = g; }
+// GT = gradient type: bf16 (training path) or float (fp32-class instantiation, fb_cross_entropy_f32)
+template <typename GT>
 __global__ void __launch_bounds__(CE_THREADS, 1)
 ce_kernel(const float* __restrict__ logits, long long ld, int V, const long long* __restrict__ labels,
-          float* __restrict__ loss_sum, float loss_scale, __nv_bfloat16* __restrict__ dlogits, long long ldd,
+          float* __restrict__ loss_sum, float loss_scale, GT* __restrict__ dlogits, long long ldd,
           float grad_scale) {
   __shared__ float sm[32], ss[32];
   __shared__ float sbc[2];
@@ -411,7 +421,7 @@ ce_kernel(const float* __restrict__ logits, long long ld, int V, const long long
   if (threadIdx.x == 0) atomicAdd(loss_sum, (mx + logf(total) - lr[lab]) * loss_scale);
   if (dlogits) {
     const float inv = grad_scale / total;
-    __nv_bfloat16* dr = dlogits + (long long)row * ldd;
+    GT* dr = dlogits + (long long)row * ldd;
     const bool vecd = vec && ((reinterpret_cast<uintptr_t>(dr) & 7) == 0);
     const int V4d = vecd ? (V >> 2) : 0;
     for (int c4 = threadIdx.x; c4 < V4d; c4 += CE_THREADS) {
@@ -419,12 +429,12 @@ ce_kernel(const float* __restrict__ logits, long long ld, int V, const long long
       float g[4] = {__expf(x.x - mx) * inv, __expf(x.y - mx) * inv, __expf(x.z - mx) * inv, __expf(x.w - mx) * inv};
       const long long d = lab - 4LL * c4;
       if (d >= 0 && d < 4) g[d] -= grad_scale;
-      *reinterpret_cast<uint2*>(dr + 4 * c4) = make_uint2(pack_bf16(g[0], g[1]), pack_bf16(g[2], g[3]));
+      ce_store4(dr + 4 * c4, g);
     }
     for (int c = V4d * 4 + threadIdx.x; c < V; c += CE_THREADS) {
       float g = __expf(lr[c] - mx) * inv;
       if (c == lab) g -= grad_scale;
-      dr[c] = __float2bfloat16_rn(g);
+      ce_store1(dr + c, g);
     }
   }
 }
@@ -604,11 +614,26 @@ int fb_cross_entropy(const float* logits, long long ld, int P, int V, const long
   FB_REQUIRE(logits && labels && loss_sum && P > 0 && V > 0, "fb_cross_entropy: bad args");
   static bool configured = false;
   if (!configured) {
-    FB_CHECK_CUDA(cudaFuncSetAttribute(fb::ce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fb::CE_SMEM));
+    FB_CHECK_CUDA(cudaFuncSetAttribute(fb::ce_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       fb::CE_SMEM));
     configured = true;
   }
-  fb::ce_kernel<<<P, fb::CE_THREADS, fb::CE_SMEM, ST(stream)>>>(logits, ld, V, labels, loss_sum, loss_scale,
-                                                                (__nv_bfloat16*)dlogits_bf16, ldd, grad_scale);
+  fb::ce_kernel<__nv_bfloat16><<<P, fb::CE_THREADS, fb::CE_SMEM, ST(stream)>>>(
+      logits, ld, V, labels, loss_sum, loss_scale, (__nv_bfloat16*)dlogits_bf16, ldd, grad_scale);
+  count_launch();
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int fb_cross_entropy_f32(const float* logits, long long ld, int P, int V, const long long* labels, float* loss_sum,
+                         float loss_scale, float* dlogits_f32, long long ldd, float grad_scale, void* stream) {
+  FB_REQUIRE(logits && labels && loss_sum && P > 0 && V > 0, "fb_cross_entropy_f32: bad args");
+  static bool configured = false;
+  if (!configured) {
+    FB_CHECK_CUDA(cudaFuncSetAttribute(fb::ce_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb::CE_SMEM));
+    configured = true;
+  }
+  fb::ce_kernel<float><<<P, fb::CE_THREADS, fb::CE_SMEM, ST(stream)>>>(logits, ld, V, labels, loss_sum, loss_scale,
+                                                                       dlogits_f32, ldd, grad_scale);
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -6,7 +6,7 @@
 // returns it as fp32 [128, N] (row = TMEM lane).  Not on the training path.
 #include <cstring>
 
-#include "../../include/frozenbilm_b200.h"
+#include "../../include/frozenbilm_b200_debug.h"
 #include "fb_common.cuh"
 
 namespace fb {

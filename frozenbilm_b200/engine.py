@@ -49,25 +49,35 @@ def _priority_streams(device):
 
 
 class Workspace:
-    """Named, shape-keyed scratch tensors reused across steps (no per-step cudaMalloc)."""
+    """Named scratch tensors reused across steps (no per-step cudaMalloc).  A buffer is keyed by NAME and grows to the
+    largest element count ever requested; ``get`` hands out a view of its head, so a run whose (B, L) changes from
+    batch to batch (``padding='longest'`` in the reference's loaders) keeps ONE set of buffers sized for the largest
+    batch instead of one set per distinct shape."""
 
     def __init__(self, device):
         self.device = device
         self.bufs = {}
 
     def get(self, name, shape, dtype, zero=False):
-        key = (name, tuple(shape), dtype)
+        key = (name, dtype)
+        n = 1
+        for d in shape:
+            n *= int(d)
         t = self.bufs.get(key)
-        if t is None:
-            t = torch.empty(shape, device=self.device, dtype=dtype)
+        if t is None or t.numel() < n:
+            t = torch.empty(max(n, 1), device=self.device, dtype=dtype)
             self.bufs[key] = t
+        v = t[:n].view(*shape)
         if zero:
-            t.zero_()
-        return t
+            v.zero_()
+        return v
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in self.bufs.values())
 
     def rows(self, name, nrows, ncols, dtype):
         """[nrows, ncols] view of a growable buffer (row counts that vary per step, e.g. labelled positions)."""
-        key = (name, ncols, dtype)
+        key = (name + "#rows", ncols, dtype)
         t = self.bufs.get(key)
         if t is None or t.shape[0] < nrows:
             cap = max(256, int(nrows * 1.25) + 8)
@@ -76,25 +86,70 @@ class Workspace:
         return t[:nrows]
 
 
+class ForwardState:
+    """Everything ONE forward leaves behind for its backward: the saved activations (in a workspace slot of their
+    own), the head state, the dimensions, the mask and the dropout seed.  The autograd node of that forward holds it,
+    so several train-mode forwards may be pending before one ``loss.backward()`` (the multiple-choice loop of the
+    reference's mc.py runs one forward per answer candidate)."""
+
+    def __init__(self, engine, slot):
+        self.engine, self.slot = engine, slot
+        self.sv = None
+        self.head = None
+        self.dims = None
+        self.mask_u8 = None
+        self.seed = None
+        self.o2 = None
+        self.released = False
+
+    def release(self):
+        if not self.released:
+            self.released = True
+            self.sv = self.head = None
+            if self.slot is not None:
+                self.engine._free_slots.append(self.slot)
+                self.slot = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
 class DebertaEngine:
-    def __init__(self, cfg: FBConfig, params: dict, device):
-        """params: name -> fp32 CUDA tensor (the module's parameters; reference names)."""
+    def __init__(self, cfg: FBConfig, params: dict, device, precision: str = "bf16"):
+        """params: name -> fp32 CUDA tensor (the module's parameters; reference names).
+        precision: "bf16" (training path: bf16 tensor-core operands, fp32 accumulation) or "fp32x3" (fp32-class
+        instantiation: every contraction as a 3-pass split-bf16 product on the same tcgen05 GEMM, attention in fp32;
+        the parity gate of BASELINE configs[0], see fb_precise.cu)."""
         lib.load()
         if device.type != "cuda":
             raise lib.FbError("frozenbilm_b200 has no CPU path: move the model to a CUDA device")
+        if precision not in ("bf16", "fp32x3"):
+            raise ValueError(f"unknown precision {precision!r} (bf16 | fp32x3)")
         self.cfg = cfg
         self.P = params
         self.device = device
+        self.precise = precision == "fp32x3"
+        self.AD = F32 if self.precise else BF16      # dtype of the GEMM-operand ("16") buffers
         self.ws = Workspace(device)
+        self.sws = self.ws                           # where the current forward keeps what its backward needs
+        self._free_slots = []
+        self._n_slots = 0
+        self.max_pending = int(os.environ.get("FB_MAX_PENDING_FORWARDS", "8"))
+        self.cur = None
         self.saved = None
+        self.head_saved = None
         self.step_seed = 0x5EED0000
+        self.cur_seed = self.step_seed
         if cfg.head_dim != 64:
             raise NotImplementedError("the fused attention kernel is specialised for head_dim = 64")
         self.use_rel = True                                   # disentangled (c2p + p2c) attention
         # attention backward: one fused kernel per pass (default) or the staged GEMM schedule (FB_ATTN_BWD=staged)
-        self.fused_attn_bwd = os.environ.get("FB_ATTN_BWD", "fused") != "staged"
+        self.fused_attn_bwd = self.precise or os.environ.get("FB_ATTN_BWD", "fused") != "staged"
         # adapter weight gradients on a low-priority side stream (FB_DW_STREAM=0 keeps everything on one stream)
-        self.dw_side_stream = os.environ.get("FB_DW_STREAM", "1") != "0"
+        self.dw_side_stream = os.environ.get("FB_DW_STREAM", "1") != "0" and not self.precise
         self._side = None
         # ... and the whole positional-gradient chain (fb_attn_bwd_rel -> dR; FB_REL_STREAM=0 keeps it in the chain).
         # FB_REL_UNITS = tile pairs per CTA of the low-priority band-gradient kernel (0 = the kernel's own choice);
@@ -107,7 +162,6 @@ class DebertaEngine:
             raise NotImplementedError("hidden_size must be a multiple of 128")
         self.bucket_of_rel = torch.from_numpy(bucket_of_rel(cfg.position_buckets, cfg.max_position_embeddings)).to(device) \
             if cfg.position_buckets > 0 else None
-        self._frozen_versions = None
         self.W = {}
         # head parameter names (DeBERTa: lm_predictions.lm_head.*; BERT: cls.predictions.*)
         self.hn = dict(dense_b="lm_predictions.lm_head.dense.bias", ln_w="lm_predictions.lm_head.LayerNorm.weight",
@@ -115,13 +169,12 @@ class DebertaEngine:
         self.prepare_frozen()
 
     # ------------------------------------------------------------------ weight preparation
-    def _frozen_sig(self):
-        return tuple((k, v._version, v.data_ptr()) for k, v in self.P.items())
-
     def prepare_frozen(self):
-        """bf16 operand copies of the LM matrices (one-time, or after load_state_dict)."""
+        """bf16 operand copies of the LM matrices.  Re-run by the module whenever a frozen Parameter's version counter
+        or storage changes (load_state_dict, in-place edits, .to()): see FrozenBiLMBase._ensure_engine."""
         cfg, P, W = self.cfg, self.P, self.W
         H = cfg.hidden_size
+        BF16 = self.AD   # fp32-class mode keeps the operands unrounded (split at the GEMM)
         with torch.no_grad():
             for i in range(cfg.num_hidden_layers):
                 p = f"deberta.encoder.layer.{i}."
@@ -140,35 +193,78 @@ class DebertaEngine:
             W["emb16"] = P["deberta.embeddings.word_embeddings.weight"].to(BF16).contiguous()
             if cfg.n_ans:
                 self.refresh_answer_embeddings()
-        self._frozen_versions = self._frozen_sig()
 
     def refresh_answer_embeddings(self):
         E = self.P["answer_embeddings.weight"]
         n = E.shape[0]
-        Ep = torch.zeros(_ceil8(n), self.cfg.hidden_size, device=self.device, dtype=BF16)
-        Ep[:n] = E.to(BF16)
+        Ep = torch.zeros(_ceil8(n), self.cfg.hidden_size, device=self.device, dtype=self.AD)
+        Ep[:n] = E.to(self.AD)
         self.W["ans16"] = Ep
         self.W["ans_n"] = n
 
     def refresh_trainable(self, flat32, flat16, slices):
         """flat16 = bf16 copy of the flat trainable bucket (one cast kernel); slices: name -> (a, b, shape)."""
         lib.cast_bf16(flat32, flat16)
-        self.T16 = {k: flat16[a:b].view(shape) for k, (a, b, shape) in slices.items()}
+        src = flat32 if self.precise else flat16
+        self.T16 = {k: src[a:b].view(shape) for k, (a, b, shape) in slices.items()}
 
     def t16(self, name):
         return self.T16[name]
 
     # ------------------------------------------------------------------ helpers
     def drop(self, p, offset):
-        return lib.drop(p if self.training else 0.0, self.step_seed, offset)
+        return lib.drop(p if self.training else 0.0, self.cur_seed, offset)
+
+    def _acquire_slot(self):
+        """Workspace for the activations one train-mode forward saves (returned to the pool by its backward, or when
+        its autograd node is dropped)."""
+        if self._free_slots:
+            return self._free_slots.pop()
+        if self._n_slots >= self.max_pending:
+            raise lib.FbError(f"{self._n_slots} train-mode forwards are pending without a backward "
+                              "(FB_MAX_PENDING_FORWARDS); run them under torch.no_grad() or call backward()")
+        self._n_slots += 1
+        return Workspace(self.device)
+
+    def begin_forward(self, training):
+        self.training = bool(training)
+        self.step_seed += 1
+        self.cur_seed = self.step_seed
+        st = ForwardState(self, self._acquire_slot() if self.training else None)
+        st.seed = self.cur_seed
+        self.sws = st.slot if st.slot is not None else self.ws
+        self.cur = st
+        self.saved = None
+        self.head_saved = None
+        return st
+
+    def _video_prefix(self, video, B, F, L, e32, wname, bname):
+        """linear_video(video) into the F visual rows of every sample of e32 [B*L, H] (deberta.py:993-1010)."""
+        cfg, ws, dev = self.cfg, self.ws, self.device
+        Dv, H = cfg.features_dim, cfg.hidden_size
+        v16 = self.sws.get("video16", (B * F, _ceil8(Dv)), self.AD)
+        vin = video.to(dev, F32).reshape(B * F, Dv).contiguous()
+        if _ceil8(Dv) != Dv:
+            v16.zero_()
+            v16[:, :Dv] = vin.to(self.AD)
+        else:
+            lib.cast_bf16(vin, v16)
+        ar = torch.arange(B, device=dev)[:, None] * L
+        if self.precise:
+            pv32 = ws.get("video.proj", (B * F, H), F32)
+            lib.gemm(v16, self.t16(wname), pv32, bias=self.P[bname], N=H, K=Dv)
+            lib.move_rows(pv32, e32, idx_out=(ar + torch.arange(F, device=dev)[None, :]).reshape(-1).contiguous())
+        else:
+            lib.gemm(v16, self.t16(wname), e32, bias=self.P[bname], M=F, N=H, K=Dv,
+                     batch={"outer": (B, F * v16.stride(0), 0, L * H)})
+        idx_out = (ar + F + torch.arange(L - F, device=dev)[None, :]).reshape(-1).contiguous()
+        return v16, idx_out
 
     # ------------------------------------------------------------------ forward
     def forward_encoder(self, video, video_mask, input_ids, attention_mask, training):
         cfg, P, W, ws = self.cfg, self.P, self.W, self.ws
-        if self._frozen_versions != self._frozen_sig():
-            self.prepare_frozen()
-        self.training = bool(training)
-        self.step_seed += 1
+        st = self.begin_forward(training)
+        sws, AD = self.sws, self.AD
         dev = self.device
         H, NL, h = cfg.hidden_size, cfg.num_hidden_layers, cfg.num_attention_heads
         B, Lt = input_ids.shape
@@ -178,7 +274,7 @@ class DebertaEngine:
         T = B * L
         if L > cfg.max_position_embeddings or L > 512:
             raise ValueError(f"sequence length {L} exceeds max_position_embeddings / kernel limit 512")
-        self.dims = (B, L, F, Lt, T)
+        self.dims = st.dims = (B, L, F, Lt, T)
         hid_p, att_p, ad_p = cfg.hidden_dropout_prob, cfg.attention_probs_dropout_prob, cfg.adapter_dropout
         e = "deberta.embeddings."
         sv = {"passes": []} if training else None
@@ -193,31 +289,18 @@ class DebertaEngine:
         else:
             m = attention_mask.to(dev)
         mask_u8 = (m != 0).to(torch.uint8).contiguous()
-        self.mask_u8 = mask_u8
+        self.mask_u8 = st.mask_u8 = mask_u8
 
         # ---- embeddings: [linear_video(video) ; word_emb[ids]] -> LN -> * mask -> dropout
-        e32 = ws.get("e32", (T, H), F32)
+        e32 = sws.get("e32", (T, H), F32)
+        v16, idx_out = None, None
         if use_video:
-            Dv = cfg.features_dim
-            v16 = ws.get("video16", (B * F, _ceil8(Dv)), BF16)
-            vin = video.to(dev, F32).reshape(B * F, Dv).contiguous()
-            if _ceil8(Dv) != Dv:
-                v16.zero_()
-                v16[:, :Dv] = vin.to(BF16)
-            else:
-                lib.cast_bf16(vin, v16)
-            wv = self.t16(e + "linear_video.weight")
-            lib.gemm(v16, wv, e32, bias=P[e + "linear_video.bias"], M=F, N=H, K=Dv,
-                     batch={"outer": (B, F * v16.stride(0), 0, L * H)})
-            idx_out = (torch.arange(B, device=dev)[:, None] * L + F + torch.arange(Lt, device=dev)[None, :]).reshape(-1)
-        else:
-            idx_out = None
+            v16, idx_out = self._video_prefix(video, B, F, L, e32, e + "linear_video.weight", e + "linear_video.bias")
         ids = input_ids.to(dev).reshape(-1).contiguous()
-        lib.move_rows(P[e + "word_embeddings.weight"], e32, idx_in=ids,
-                      idx_out=idx_out.contiguous() if idx_out is not None else None)
+        lib.move_rows(P[e + "word_embeddings.weight"], e32, idx_in=ids, idx_out=idx_out)
         x32 = ws.get("x32.0", (T, H), F32)
-        x16 = ws.get("x16.0", (T, H), BF16)
-        emb_mean, emb_rstd = ws.get("emb.mean", (T,), F32), ws.get("emb.rstd", (T,), F32)
+        x16 = ws.get("x16.0", (T, H), AD)
+        emb_mean, emb_rstd = sws.get("emb.mean", (T,), F32), sws.get("emb.rstd", (T,), F32)
         lib.layernorm_fwd(e32, P[e + "LayerNorm.weight"], P[e + "LayerNorm.bias"], cfg.layer_norm_eps,
                           rowmask=mask_u8, out_drop=self.drop(hid_p, OFF_EMB), y32=x32, y16=x16,
                           mean=emb_mean, rstd=emb_rstd)
@@ -227,7 +310,7 @@ class DebertaEngine:
         c = "deberta.encoder."
         S2 = 2 * cfg.position_buckets
         R32 = ws.get("R32", (S2, H), F32)
-        rel_mean, rel_rstd = ws.get("rel.mean", (S2,), F32), ws.get("rel.rstd", (S2,), F32)
+        rel_mean, rel_rstd = sws.get("rel.mean", (S2,), F32), sws.get("rel.rstd", (S2,), F32)
         lib.layernorm_fwd(P[c + "rel_embeddings.weight"], P[c + "LayerNorm.weight"], P[c + "LayerNorm.bias"],
                           cfg.layer_norm_eps, y32=R32, mean=rel_mean, rstd=rel_rstd)
         self._R32 = R32
@@ -236,21 +319,21 @@ class DebertaEngine:
         # ---- encoder: NL-1 ordinary passes (the NL-th only feeds hidden_states[-1], which nothing reads)
         pass_id = 0
         for i in range(NL - 1):
-            qkv = ws.get(f"qkv.{pass_id}" if training else "qkv", (T, 3 * H), BF16)
+            qkv = sws.get(f"qkv.{pass_id}", (T, 3 * H), AD) if training else ws.get("qkv", (T, 3 * H), AD)
             lib.gemm(x16, W[f"qkv.w.{i}"], qkv, bias=W[f"qkv.b.{i}"])
             y32, y16, rec = self._layer_pass(i, pass_id, x32, qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], training)
             if training:
                 rec["qkv"] = qkv
             if i == 0:
                 # ConvLayer on the EMBEDDING output; LN(layer0_out + gelu(dropout(conv))) * mask
-                col16 = ws.get("col16", (T, 3 * H), BF16)
+                col16 = ws.get("col16", (T, 3 * H), AD)
                 lib.conv_im2col(x0_16, B, L, H, col16)
-                sc32 = ws.get("conv.s", (T, H), F32)
-                cg16 = ws.get("conv.pre", (T, H), BF16)
+                sc32 = sws.get("conv.s", (T, H), F32)
+                cg16 = sws.get("conv.pre", (T, H), AD)
                 lib.gemm(col16, W["conv.w"], sc32, bias=P[c + "conv.conv.bias"], rowmask=mask_u8,
                          dropout=self.drop(hid_p, OFF_CONV), drop_pos=1, D_pre=cg16, act=lib.FB_ACT_GELU, resid=y32)
-                cm, cr = ws.get("conv.mean", (T,), F32), ws.get("conv.rstd", (T,), F32)
-                y32b, y16b = ws.get("x32.c", (T, H), F32), ws.get("x16.c", (T, H), BF16)
+                cm, cr = sws.get("conv.mean", (T,), F32), sws.get("conv.rstd", (T,), F32)
+                y32b, y16b = ws.get("x32.c", (T, H), F32), ws.get("x16.c", (T, H), AD)
                 lib.layernorm_fwd(sc32, P[c + "conv.LayerNorm.weight"], P[c + "conv.LayerNorm.bias"],
                                   cfg.layer_norm_eps, rowmask=mask_u8, y32=y32b, y16=y16b, mean=cm, rstd=cr)
                 y32, y16 = y32b, y16b
@@ -264,13 +347,13 @@ class DebertaEngine:
         # ---- enhanced mask decoder: 2 passes of the last layer, Q from z / o1, K/V from h[-2] (computed once)
         last = NL - 1
         kv32, kv16 = x32, x16
-        z32, z16 = ws.get("emd.z32", (T, H), F32), ws.get("emd.z16", (T, H), BF16)
+        z32, z16 = ws.get("emd.z32", (T, H), F32), ws.get("emd.z16", (T, H), AD)
         lib.add_rowbcast(kv32, P[e + "position_embeddings.weight"][:L].contiguous(), B, L, H, z32, z16)
-        kvp = ws.get("emd.kv", (T, 2 * H), BF16)
+        kvp = sws.get("emd.kv", (T, 2 * H), AD)
         lib.gemm(kv16, W[f"qkv.w.{last}"][H:], kvp, bias=W[f"qkv.b.{last}"][H:].contiguous())
         q32, q16 = z32, z16
         for j in range(2):
-            qp = ws.get(f"emd.q.{j}", (T, H), BF16)
+            qp = sws.get(f"emd.q.{j}", (T, H), AD)
             lib.gemm(q16, W[f"qkv.w.{last}"][:H], qp, bias=W[f"qkv.b.{last}"][:H].contiguous())
             y32, y16, rec = self._layer_pass(last, pass_id, q32, qp, kvp[:, :H], kvp[:, H:], training, tag=f"e{j}")
             if training:
@@ -281,14 +364,16 @@ class DebertaEngine:
             pass_id += 1
         if training:
             sv.update(e32=e32, emb_mean=emb_mean, emb_rstd=emb_rstd, rel_mean=rel_mean, rel_rstd=rel_rstd,
-                      video16=v16 if use_video else None, use_video=use_video)
-            self.saved = sv
+                      video16=v16, use_video=use_video)
+            self.saved = st.sv = sv
         self.o2_32, self.o2_16 = q32, q16
+        st.o2 = (q32, q16)
         return q32, q16
 
     def _rel_tables(self, layer, pass_id, L):
-        """PQrel / PKrel for one layer pass: Linear_{q|k}(dropout(R)) expanded to relative positions."""
-        cfg, W, ws = self.cfg, self.W, self.ws
+        """PQrel / PKrel for one layer pass: Linear_{q|k}(dropout(R)) expanded to relative positions
+        (fp32-class mode: the un-expanded [2S, 2H] projections, the fp32 attention indexes them by bucket)."""
+        cfg, W, ws, sws = self.cfg, self.W, self.ws, self.sws
         H, h = cfg.hidden_size, cfg.num_attention_heads
         p = cfg.hidden_dropout_prob if self.training else 0.0
         key = layer if p == 0.0 else None
@@ -296,34 +381,42 @@ class DebertaEngine:
             return self._rel_tables_cache[key]
         S2 = 2 * cfg.position_buckets
         tagk = f".{pass_id}" if self.training else ""
-        Rd16 = ws.get("Rd16", (S2, H), BF16)
+        tws = sws if self.training else ws
+        Rd16 = ws.get("Rd16", (S2, H), self.AD)
         lib.dropout_apply(self._R32, self.drop(cfg.hidden_dropout_prob, pass_id * 8 + SITE_POS), out16=Rd16)
-        pqk = ws.get("pqk16", (S2, 2 * H), BF16)
-        lib.gemm(Rd16, W[f"qkv.w.{layer}"][:2 * H], pqk, bias=W[f"qkv.b.{layer}"][:2 * H].contiguous())
-        rel_rows, _ = lib.rel_table_geometry(L)
-        pq = ws.get("PQrel" + tagk, (h, rel_rows, 64), BF16)
-        pk = ws.get("PKrel" + tagk, (h, rel_rows, 64), BF16)
-        pkr = ws.get("PKrev" + tagk, (h, rel_rows, 64), BF16) if (self.training and self.fused_attn_bwd) else None
-        lib.build_rel_tables(pqk, self.bucket_of_rel, L, h, out_pq=pq, out_pk=pk, out_pk_rev=pkr)
+        if self.precise:
+            pqk = tws.get("pqk32" + tagk, (S2, 2 * H), F32)
+            lib.gemm(Rd16, W[f"qkv.w.{layer}"][:2 * H], pqk, bias=W[f"qkv.b.{layer}"][:2 * H].contiguous())
+            out = (pqk, None, None)
+        else:
+            pqk = ws.get("pqk16", (S2, 2 * H), BF16)
+            lib.gemm(Rd16, W[f"qkv.w.{layer}"][:2 * H], pqk, bias=W[f"qkv.b.{layer}"][:2 * H].contiguous())
+            rel_rows, _ = lib.rel_table_geometry(L)
+            pq = tws.get("PQrel" + tagk, (h, rel_rows, 64), BF16)
+            pk = tws.get("PKrel" + tagk, (h, rel_rows, 64), BF16)
+            pkr = tws.get("PKrev" + tagk, (h, rel_rows, 64), BF16) if (self.training and self.fused_attn_bwd) else None
+            lib.build_rel_tables(pqk, self.bucket_of_rel, L, h, out_pq=pq, out_pk=pk, out_pk_rev=pkr)
+            out = (pq, pk, pkr)
         if key is not None:
-            self._rel_tables_cache[key] = (pq, pk, pkr)
-        return pq, pk, pkr
+            self._rel_tables_cache[key] = out
+        return out
 
     def _sublayer_out(self, name, i, pass_id, u_in16, W_dense, b_dense, ad_prefix, ln_prefix, resid32, site_ad,
                       site_hid, training, tag):
         """dense -> adapter -> dropout -> + residual -> LayerNorm  (deberta.py:254-260 / 328-334)."""
-        cfg, P, ws = self.cfg, self.P, self.ws
+        cfg, P, ws, AD = self.cfg, self.P, self.ws, self.AD
+        tws = self.sws if training else ws
         T = u_in16.shape[0]
         H = cfg.hidden_size
         sfx = f".{tag}" if training else ""
         hid = self.drop(cfg.hidden_dropout_prob, pass_id * 8 + site_hid)
-        s32 = ws.get(f"{name}.s{sfx}", (T, H), F32)
+        s32 = tws.get(f"{name}.s{sfx}", (T, H), F32)
         rec = {}
         r = cfg.r_attn if name == "att" else cfg.r_ff
         if r:
-            u16 = ws.get(f"{name}.u{sfx}", (T, H), BF16)
+            u16 = tws.get(f"{name}.u{sfx}", (T, H), AD)
             lib.gemm(u_in16, W_dense, u16, bias=b_dense)
-            z16 = ws.get(f"{name}.z{sfx}", (T, r), BF16)
+            z16 = tws.get(f"{name}.z{sfx}", (T, r), AD)
             lib.gemm(u16, self.t16(ad_prefix + "down.weight"), z16, bias=P[ad_prefix + "down.bias"],
                      act=lib.FB_ACT_RELU, dropout=self.drop(cfg.adapter_dropout, pass_id * 8 + site_ad), drop_pos=2)
             lib.gemm(z16, self.t16(ad_prefix + "up.weight"), s32, bias=P[ad_prefix + "up.bias"], aux=u16,
@@ -332,9 +425,9 @@ class DebertaEngine:
         else:
             lib.gemm(u_in16, W_dense, s32, bias=b_dense, dropout=hid, drop_pos=2, resid=resid32)
         y32 = ws.get(f"{name}.y32.{pass_id % 2}", (T, H), F32)
-        y16 = ws.get(f"{name}.y16.{pass_id % 2}", (T, H), BF16)
-        mean = ws.get(f"{name}.mean{sfx}", (T,), F32)
-        rstd = ws.get(f"{name}.rstd{sfx}", (T,), F32)
+        y16 = ws.get(f"{name}.y16.{pass_id % 2}", (T, H), AD)
+        mean = tws.get(f"{name}.mean{sfx}", (T,), F32)
+        rstd = tws.get(f"{name}.rstd{sfx}", (T,), F32)
         lib.layernorm_fwd(s32, P[ln_prefix + "weight"], P[ln_prefix + "bias"], cfg.layer_norm_eps, y32=y32, y16=y16,
                           mean=mean, rstd=rstd)
         rec.update(s=s32, mean=mean, rstd=rstd)
@@ -342,25 +435,32 @@ class DebertaEngine:
 
     def _layer_pass(self, i, pass_id, xq32, Q, K, V, training, tag=None):
         """One DebertaV2Layer pass (deberta.py:351-375) given the projected Q/K/V views."""
-        cfg, P, W, ws = self.cfg, self.P, self.W, self.ws
+        cfg, P, W, ws, AD = self.cfg, self.P, self.W, self.ws, self.AD
+        tws = self.sws if training else ws
         B, L, F, Lt, T = self.dims
         H, h, I = cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size
         tag = tag if tag is not None else str(pass_id)
         sfx = f".{tag}" if training else ""
         p = f"{self.layer_prefix}{i}."
         pq, pk, pkr = self._rel_tables(i, pass_id, L) if self.use_rel else (None, None, None)
-        ctx16 = ws.get("ctx" + sfx, (T, H), BF16)
-        lse = ws.get("lse" + sfx, (B, h, L), F32)
+        ctx16 = tws.get("ctx" + sfx, (T, H), AD)
+        lse = tws.get("lse" + sfx, (B, h, L), F32)
         att_drop = self.drop(cfg.attention_probs_dropout_prob, pass_id * 8 + SITE_PROBS)
-        s2 = ws.get("s2" + sfx, (B, h, L, (L + 127) // 128 * 128), F32) if training else None
-        lib.attn_fwd(Q, K, V, pk, pq, self.mask_u8, ctx16, lse, B=B, L=L, h=h, scale=self.attn_scale,
-                     dropout_p=att_drop.p, seed=att_drop.seed, offset=att_drop.offset, s_out=s2,
-                     key_mask_only=not self.use_rel)
+        s2 = None
+        if self.precise:
+            # fp32-class mode: pq holds the [2S, 2H] projections; the backward recomputes the probabilities
+            lib.attn_fwd_f32(Q, K, V, pq, self.bucket_of_rel, self.mask_u8, ctx16, lse, B=B, L=L, h=h,
+                             scale=self.attn_scale, drop=att_drop, key_mask_only=not self.use_rel)
+        else:
+            s2 = tws.get("s2" + sfx, (B, h, L, (L + 127) // 128 * 128), lib.SCORE_DTYPE) if training else None
+            lib.attn_fwd(Q, K, V, pk, pq, self.mask_u8, ctx16, lse, B=B, L=L, h=h, scale=self.attn_scale,
+                         dropout_p=att_drop.p, seed=att_drop.seed, offset=att_drop.offset, s_out=s2,
+                         key_mask_only=not self.use_rel)
         a32, a16, rec1 = self._sublayer_out("att", i, pass_id, ctx16, W[f"o.w.{i}"], P[p + "attention.output.dense.bias"],
                                             p + "attention.output.adapter.", p + "attention.output.LayerNorm.",
                                             xq32, SITE_AD1, SITE_HID1, training, tag)
-        f16 = ws.get("ffn.f", (T, I), BF16)
-        h1 = ws.get("ffn.h1" + sfx, (T, I), BF16) if training else None
+        f16 = ws.get("ffn.f", (T, I), AD)
+        h1 = tws.get("ffn.h1" + sfx, (T, I), AD) if training else None
         lib.gemm(a16, W[f"ffn1.w.{i}"], f16, bias=P[p + "intermediate.dense.bias"], act=lib.FB_ACT_GELU, D_pre=h1)
         y32, y16, rec2 = self._sublayer_out("ffn", i, pass_id, f16, W[f"ffn2.w.{i}"], P[p + "output.dense.bias"],
                                             p + "output.adapter.", p + "output.LayerNorm.", a32, SITE_AD2, SITE_HID2,
@@ -375,14 +475,15 @@ class DebertaEngine:
     def head_logits(self, rows16, n_rows, mlm, out=None, scratch=False):
         """logits = LN(gelu(dense(x))) . E^T + bias for the given rows (deberta.py:1544-1558).
         ``scratch`` uses separate buffers and leaves the state saved for the backward untouched."""
-        cfg, P, W, ws = self.cfg, self.P, self.W, self.ws
+        cfg, P, W, AD = self.cfg, self.P, self.W, self.AD
+        ws = self.ws if scratch else self.sws
         H = cfg.hidden_size
         hn = self.hn
         pfx = "headx." if scratch else "head."
         hd32 = ws.rows(pfx + "hd32", n_rows, H, F32)
-        pre16 = ws.rows(pfx + "pre16", n_rows, H, BF16)
+        pre16 = ws.rows(pfx + "pre16", n_rows, H, AD)
         lib.gemm(rows16, W["head.w"], hd32, bias=P[hn["dense_b"]], act=lib.FB_ACT_GELU, D_pre=pre16)
-        t16 = ws.rows(pfx + "t16", n_rows, H, BF16)
+        t16 = ws.rows(pfx + "t16", n_rows, H, AD)
         mean, rstd = ws.rows(pfx + "mean", n_rows, 1, F32), ws.rows(pfx + "rstd", n_rows, 1, F32)
         lib.layernorm_fwd(hd32, P[hn["ln_w"]], P[hn["ln_b"]], cfg.layer_norm_eps, y16=t16,
                           mean=mean, rstd=rstd)
@@ -396,36 +497,46 @@ class DebertaEngine:
         if scratch:
             return out, V
         self.head_saved = dict(hd32=hd32, pre16=pre16, t16=t16, mean=mean, rstd=rstd, E=E, V=V, n_rows=n_rows)
+        if self.cur is not None:
+            self.cur.head = self.head_saved
         return out, V
 
     def head_mlm_loss(self, sel, labels_sel, n_sel, want_grad):
         """MLM loss over the labelled positions only (CrossEntropyLoss ignores -100, deberta.py:1481-1488): the
         head runs on n_sel rows instead of all B*L and the [B, L, V] logits are never materialised."""
-        cfg, ws = self.cfg, self.ws
+        cfg, ws = self.cfg, self.sws
         H = cfg.hidden_size
-        rows16 = ws.rows("head.rows16", n_sel, H, BF16)
+        rows16 = ws.rows("head.rows16", n_sel, H, self.AD)
         lib.move_rows(self.o2_16, rows16, idx_in=sel)
         logits, V = self.head_logits(rows16, n_sel, mlm=True)
         loss_sum = ws.get("head.loss", (1,), F32, zero=True)
-        dlog16 = ws.rows("head.dlog16", n_sel, _ceil8(V), BF16) if want_grad else None
+        dlog16 = ws.rows("head.dlog16", n_sel, _ceil8(V), self.AD) if want_grad else None
         lib.cross_entropy(logits, V, labels_sel, loss_sum, 1.0 / n_sel, dlog16, 1.0 / n_sel)
         self.head_saved.update(sel=sel, dlog16=dlog16, mode="mlm")
-        return loss_sum[0]
+        return loss_sum[0].clone()   # never a view of the reused workspace (a kept loss must not change later)
 
     # ------------------------------------------------------------------ backward
-    def backward(self, gviews, scale=None, dlogits=None):
-        """Selective backward: accumulates into ``gviews`` (name -> fp32 view of the flat gradient bucket)."""
-        cfg, P, W, ws, sv, hs = self.cfg, self.P, self.W, self.ws, self.saved, self.head_saved
-        if sv is None:
-            raise lib.FbError("backward() without a training-mode forward")
-        B, L, F, Lt, T = self.dims
-        H = cfg.hidden_size
+    def backward(self, gviews, scale=None, dlogits=None, state=None):
+        """Selective backward of ONE forward (``state``; default: the latest): accumulates into ``gviews``
+        (name -> fp32 view of the flat gradient bucket)."""
+        st = state if state is not None else self.cur
+        if st is None or st.sv is None or st.released:
+            raise lib.FbError("backward() without a training-mode forward (or its state was already consumed)")
+        # the engine attributes the backward helpers read are those of THAT forward
+        self.saved, self.head_saved, self.dims, self.mask_u8 = st.sv, st.head, st.dims, st.mask_u8
+        self.cur_seed, self.training = st.seed, True
         self.g = gviews
+        try:
+            self._backward_impl(scale, dlogits)
+        finally:
+            self.saved = self.head_saved = None
+            st.release()
+
+    def _backward_impl(self, scale, dlogits):
         if not self.dw_side_stream:
             self._side = None
             dy32 = self._bwd_head(scale, dlogits)
             self._bwd_encoder(dy32)
-            self.saved = None
             return
         # The adapter weight gradients (dW = dY^T X, bias column sums: ~100 us of small split-K GEMMs per layer pass)
         # feed nothing downstream.  They are issued on a LOW-priority stream while the backward chain runs on a
@@ -443,7 +554,6 @@ class DebertaEngine:
         self._side = None
         cur.wait_stream(hi)
         cur.wait_stream(lo)
-        self.saved = None
 
     def _bwd_head(self, scale, dlogits):
         cfg, P, W, ws, hs = self.cfg, self.P, self.W, self.ws, self.head_saved
@@ -459,13 +569,13 @@ class DebertaEngine:
                 dt32.mul_(scale)
         else:
             nans = hs["V"]
-            d16 = ws.get("bw.dlog_ans", (n, _ceil8(nans)), BF16, zero=True)
-            d16[:, :nans] = dlogits.reshape(n, nans).to(BF16)
+            d16 = ws.get("bw.dlog_ans", (n, _ceil8(nans)), self.AD, zero=True)
+            d16[:, :nans] = dlogits.reshape(n, nans).to(self.AD)
             lib.gemm(d16, hs["E"], dt32, b_mn_major=True, N=H)
         dhd32 = ws.rows("bw.dhd32", n, H, F32)
         lib.layernorm_bwd(dt32, hs["hd32"], hs["mean"], hs["rstd"], P[hn["ln_w"]], dx32=dhd32,
                           dgamma=self._g(hn["ln_w"]), dbeta=self._g(hn["ln_b"]))
-        dpre16 = ws.rows("bw.dpre16", n, H, BF16)
+        dpre16 = ws.rows("bw.dpre16", n, H, self.AD)
         lib.gelu_bwd(dhd32, hs["pre16"], dpre16)
         dy32 = ws.get("bw.dy32.a", (T, H), F32)
         if dlogits is None:
@@ -502,10 +612,10 @@ class DebertaEngine:
                 lib.layernorm_bwd(dx32, sv["conv_s"], sv["conv_mean"], sv["conv_rstd"], P[c + "conv.LayerNorm.weight"],
                                   rowmask=self.mask_u8, dx32=ds_c, dgamma=self._g(c + "conv.LayerNorm.weight"),
                                   dbeta=self._g(c + "conv.LayerNorm.bias"))
-                dconv16 = ws.get("bw.dconv16", (T, H), BF16)
+                dconv16 = ws.get("bw.dconv16", (T, H), self.AD)
                 lib.gelu_bwd(ds_c, sv["conv_pre"], dconv16, rowmask=self.mask_u8,
                              dropout=self.drop(cfg.hidden_dropout_prob, OFF_CONV))
-                dcol16 = ws.get("bw.dcol16", (T, 3 * H), BF16)
+                dcol16 = ws.get("bw.dcol16", (T, 3 * H), self.AD)
                 lib.gemm(dconv16, W["conv.w"], dcol16, b_mn_major=True)
                 dx32 = ds_c
             dx32 = self._bwd_pass(rec, dx32, emd=False, slot=rec["pass_id"] % 2)
@@ -524,12 +634,12 @@ class DebertaEngine:
         cfg, P, ws, sv = self.cfg, self.P, self.ws, self.saved
         B, L, F, Lt, T = self.dims
         H = cfg.hidden_size
-        de16 = ws.get("bw.de16", (T, H), BF16)
+        de16 = ws.get("bw.de16", (T, H), self.AD)
         lib.layernorm_bwd(dx32, sv["e32"], sv["emb_mean"], sv["emb_rstd"], P[e + "LayerNorm.weight"],
                           rowmask=rowmask, out_drop=self.drop(cfg.hidden_dropout_prob, OFF_EMB), dx16=de16,
                           dgamma=self._g(e + "LayerNorm.weight"), dbeta=self._g(e + "LayerNorm.bias"))
         if sv["use_video"]:
-            dv16 = ws.get("bw.dv16", (B * F, H), BF16)
+            dv16 = ws.get("bw.dv16", (B * F, H), self.AD)
             idx = (torch.arange(B, device=self.device)[:, None] * L + torch.arange(F, device=self.device)[None, :])
             lib.move_rows(de16, dv16, idx_in=idx.reshape(-1).contiguous())
             v16 = sv["video16"]
@@ -550,7 +660,7 @@ class DebertaEngine:
         ds32 = ws.get(f"bw.{name}.ds32.{slot}", (T, H), F32)
         r_ = cfg.r_attn if name == "att" else cfg.r_ff
         # per-pass operand buffers when the weight gradients run asynchronously (never overwritten before they are read)
-        gw16 = ws.get(f"bw.{name}.gw16" + (f".{pass_id}" if (self._side is not None and r_) else ""), (T, H), BF16)
+        gw16 = ws.get(f"bw.{name}.gw16" + (f".{pass_id}" if (self._side is not None and r_) else ""), (T, H), self.AD)
         lib.layernorm_bwd(dy32, rec["s"], rec["mean"], rec["rstd"], P[ln_prefix + "weight"],
                           in_drop=self.drop(cfg.hidden_dropout_prob, pass_id * 8 + site_hid), dx32=ds32, dx16=gw16,
                           dgamma=self._g(ln_prefix + "weight"), dbeta=self._g(ln_prefix + "bias"),
@@ -561,7 +671,7 @@ class DebertaEngine:
             ad = self.drop(cfg.adapter_dropout, pass_id * 8 + site_ad)
             inv_keep = 1.0 / (1.0 - ad.p) if ad.p > 0 else 1.0
             side = self._side
-            dz16 = ws.get(f"bw.{name}.dz16" + (f".{pass_id}" if side is not None else ""), (T, r), BF16)
+            dz16 = ws.get(f"bw.{name}.dz16" + (f".{pass_id}" if side is not None else ""), (T, r), self.AD)
             # d(zd) = gw . Wu ; through dropout and ReLU: zd > 0 <=> kept and pre-activation > 0
             lib.gemm(gw16, wu, dz16, b_mn_major=True, alpha=inv_keep, aux=z16, aux_op=lib.FB_AUX_MUL_RELU_MASK)
             sk = max(1, min(32, T // 512))
@@ -580,7 +690,7 @@ class DebertaEngine:
                 side.wait_event(ev)
                 with torch.cuda.stream(side):
                     weight_grads()
-            du16 = ws.get(f"bw.{name}.du16", (T, H), BF16)
+            du16 = ws.get(f"bw.{name}.du16", (T, H), self.AD)
             lib.gemm(dz16, wd, du16, b_mn_major=True, aux=gw16, aux_op=lib.FB_AUX_ADD)
         else:
             du16 = gw16
@@ -595,7 +705,7 @@ class DebertaEngine:
         # ---- FFN sub-layer
         ds2, du2 = self._bwd_sublayer("ffn", rec["ffn"], dy32, p + "output.adapter.", p + "output.LayerNorm.",
                                       W[f"ffn2.w.{i}"], pass_id, SITE_AD2, SITE_HID2, slot)
-        dh1 = ws.get("bw.dh1", (T, I), BF16)
+        dh1 = ws.get("bw.dh1", (T, I), self.AD)
         lib.gemm(du2, W[f"ffn2.w.{i}"], dh1, b_mn_major=True, aux=rec["h1"], aux_op=lib.FB_AUX_MUL_GELU_GRAD)
         da32 = ws.get("bw.da32", (T, H), F32)
         lib.gemm(dh1, W[f"ffn1.w.{i}"], da32, b_mn_major=True, resid=ds2)
@@ -603,9 +713,9 @@ class DebertaEngine:
         ds1, du1 = self._bwd_sublayer("att", rec["att"], da32, p + "attention.output.adapter.",
                                       p + "attention.output.LayerNorm.", W[f"o.w.{i}"], pass_id, SITE_AD1,
                                       SITE_HID1, slot)
-        dctx16 = ws.get("bw.dctx16", (T, H), BF16)
+        dctx16 = ws.get("bw.dctx16", (T, H), self.AD)
         lib.gemm(du1, W[f"o.w.{i}"], dctx16, b_mn_major=True)
-        dqkv16 = ws.get(f"bw.dqkv16.{slot if emd else 0}", (T, 3 * H), BF16)
+        dqkv16 = ws.get(f"bw.dqkv16.{slot if emd else 0}", (T, 3 * H), self.AD)
         if self.fused_attn_bwd:
             self._attn_bwd_fused(rec, dctx16, dqkv16)
         else:
@@ -628,11 +738,20 @@ class DebertaEngine:
         Q, K, V = rec["Q"], rec["K"], rec["V"]
         lp = (L + 127) // 128 * 128
         rel = self.use_rel
+        ad = self.drop(cfg.attention_probs_dropout_prob, pass_id * 8 + SITE_PROBS)
+        if self.precise:
+            # fp32-class mode: fp32 CUDA-core backward straight into the bucket rows of d(Linear_{q|k}(dropout(R)))
+            dpqk32 = ws.get("bw.dpqk32", (2 * cfg.position_buckets, 2 * H), F32, zero=True) if rel else None
+            lib.attn_bwd_f32(Q, K, V, rec["pq"], self.bucket_of_rel, self.mask_u8, rec["ctx"], rec["lse"], dctx16,
+                             dqkv16[:, :H], dqkv16[:, H:2 * H], dqkv16[:, 2 * H:], dpqk32, B=B, L=L, h=h,
+                             scale=self.attn_scale, drop=ad, key_mask_only=not rel)
+            if rel:
+                self._bwd_rel_from_buckets(dpqk32, i, pass_id)
+            return
         # The gradients of the positional projections (fb_attn_bwd_rel and the chain down to dR) feed nothing on the
         # token path: with the side stream they run at low priority from a per-pass copy of dS'.
         side = self._side if self.rel_side_stream else None
         ds = ws.get("bw.ds" + (f".{pass_id}" if side is not None else ""), (B, h, L, lp), BF16) if rel else None
-        ad = self.drop(cfg.attention_probs_dropout_prob, pass_id * 8 + SITE_PROBS)
         lib.attn_bwd(Q, K, V, rec["ctx"], dctx16, rec["s2"], rec["lse"], rec["pkr"], rec["pq"],
                      dqkv16[:, :H], dqkv16[:, H:2 * H], dqkv16[:, 2 * H:], ds_out=ds, B=B, L=L, h=h,
                      scale=self.attn_scale, dropout_p=ad.p, seed=ad.seed, offset=ad.offset)
@@ -657,12 +776,16 @@ class DebertaEngine:
 
     def _bwd_rel_tables(self, gpq, gpk, i, pass_id, L, h):
         """d(per-relative-position tables) -> d(Linear_{q|k}(dropout(R))) -> accumulate dR (deberta.py:847-853)."""
+        cfg, ws = self.cfg, self.ws
+        dpqk32 = ws.get("bw.dpqk32", (2 * cfg.position_buckets, 2 * cfg.hidden_size), F32, zero=True)
+        lib.rel_to_bucket(gpq, gpk, self.bucket_of_rel, L, h, dpqk32)
+        self._bwd_rel_from_buckets(dpqk32, i, pass_id)
+
+    def _bwd_rel_from_buckets(self, dpqk32, i, pass_id):
         cfg, W, ws = self.cfg, self.W, self.ws
         H = cfg.hidden_size
         S2 = 2 * cfg.position_buckets
-        dpqk32 = ws.get("bw.dpqk32", (S2, 2 * H), F32, zero=True)
-        lib.rel_to_bucket(gpq, gpk, self.bucket_of_rel, L, h, dpqk32)
-        dpqk16 = ws.get("bw.dpqk16", (S2, 2 * H), BF16)
+        dpqk16 = ws.get("bw.dpqk16", (S2, 2 * H), self.AD)
         lib.cast_bf16(dpqk32, dpqk16)
         dRd32 = ws.get("bw.dRd32", (S2, H), F32)
         lib.gemm(dpqk16, W[f"qkv.w.{i}"][:2 * H], dRd32, b_mn_major=True)
@@ -732,8 +855,8 @@ class BertEngine(DebertaEngine):
     blocks without adapters (:281-292, 349-360), MLM head on ``cls.predictions.decoder`` (:74-96).  Same kernels
     as the DeBERTa path: fb_attn_fwd in plain mode (no relative tables), the same GEMM / LayerNorm schedule."""
 
-    def __init__(self, cfg, params, device):
-        super().__init__(cfg, params, device)
+    def __init__(self, cfg, params, device, precision="bf16"):
+        super().__init__(cfg, params, device, precision)
         self.use_rel = False
         self.attn_scale = 1.0 / math.sqrt(64)
         self.layer_prefix = "bert.encoder.layer."
@@ -742,6 +865,7 @@ class BertEngine(DebertaEngine):
 
     def prepare_frozen(self):
         cfg, P, W = self.cfg, self.P, self.W
+        BF16 = self.AD
         with torch.no_grad():
             for i in range(cfg.num_hidden_layers):
                 p = f"bert.encoder.layer.{i}."
@@ -757,14 +881,11 @@ class BertEngine(DebertaEngine):
             W["emb16"] = P["cls.predictions.decoder.weight"].to(BF16).contiguous()
             if cfg.n_ans:
                 self.refresh_answer_embeddings()
-        self._frozen_versions = self._frozen_sig()
 
     def forward_encoder(self, video, video_mask, input_ids, attention_mask, training):
         cfg, P, W, ws = self.cfg, self.P, self.W, self.ws
-        if self._frozen_versions != self._frozen_sig():
-            self.prepare_frozen()
-        self.training = bool(training)
-        self.step_seed += 1
+        st = self.begin_forward(training)
+        sws, AD = self.sws, self.AD
         dev = self.device
         H, NL = cfg.hidden_size, cfg.num_hidden_layers
         B, Lt = input_ids.shape
@@ -774,7 +895,7 @@ class BertEngine(DebertaEngine):
         T = B * L
         if L > cfg.max_position_embeddings or L > 512:
             raise ValueError(f"sequence length {L} exceeds max_position_embeddings / kernel limit 512")
-        self.dims = (B, L, F, Lt, T)
+        self.dims = st.dims = (B, L, F, Lt, T)
         e = "bert.embeddings."
         sv = {"passes": []} if training else None
         if attention_mask is None:
@@ -785,36 +906,24 @@ class BertEngine(DebertaEngine):
             m = torch.cat([video_mask.to(dev), attention_mask.to(dev)], 1)
         else:
             m = attention_mask.to(dev)
-        self.mask_u8 = (m != 0).to(torch.uint8).contiguous()
+        self.mask_u8 = st.mask_u8 = (m != 0).to(torch.uint8).contiguous()
         # ---- embeddings: [linear_video(video) ; word_emb[ids]] + pos + type(0) -> LN -> dropout (no mask multiply)
         g32 = ws.get("g32", (T, H), F32)
-        v16 = None
+        v16, idx_out = None, None
         if use_video:
-            Dv = cfg.features_dim
-            v16 = ws.get("video16", (B * F, _ceil8(Dv)), BF16)
-            vin = video.to(dev, F32).reshape(B * F, Dv).contiguous()
-            if _ceil8(Dv) != Dv:
-                v16.zero_()
-                v16[:, :Dv] = vin.to(BF16)
-            else:
-                lib.cast_bf16(vin, v16)
-            lib.gemm(v16, self.t16(e + "linear_video.weight"), g32, bias=P[e + "linear_video.bias"], M=F, N=H, K=Dv,
-                     batch={"outer": (B, F * v16.stride(0), 0, L * H)})
-            idx_out = (torch.arange(B, device=dev)[:, None] * L + F + torch.arange(Lt, device=dev)[None, :]).reshape(-1)
-        else:
-            idx_out = None
+            v16, idx_out = self._video_prefix(video, B, F, L, g32, e + "linear_video.weight", e + "linear_video.bias")
         lib.move_rows(P[e + "word_embeddings.weight"], g32, idx_in=input_ids.to(dev).reshape(-1).contiguous(),
-                      idx_out=idx_out.contiguous() if idx_out is not None else None)
+                      idx_out=idx_out)
         pos_type = (P[e + "position_embeddings.weight"][:L] + P[e + "token_type_embeddings.weight"][0]).contiguous()
-        e32 = ws.get("e32", (T, H), F32)
+        e32 = sws.get("e32", (T, H), F32)
         lib.add_rowbcast(g32, pos_type, B, L, H, e32)
-        x32, x16 = ws.get("x32.0", (T, H), F32), ws.get("x16.0", (T, H), BF16)
-        emb_mean, emb_rstd = ws.get("emb.mean", (T,), F32), ws.get("emb.rstd", (T,), F32)
+        x32, x16 = ws.get("x32.0", (T, H), F32), ws.get("x16.0", (T, H), AD)
+        emb_mean, emb_rstd = sws.get("emb.mean", (T,), F32), sws.get("emb.rstd", (T,), F32)
         lib.layernorm_fwd(e32, P[e + "LayerNorm.weight"], P[e + "LayerNorm.bias"], cfg.layer_norm_eps,
                           out_drop=self.drop(cfg.hidden_dropout_prob, OFF_EMB), y32=x32, y16=x16, mean=emb_mean,
                           rstd=emb_rstd)
         for i in range(NL):
-            qkv = ws.get(f"qkv.{i}" if training else "qkv", (T, 3 * H), BF16)
+            qkv = sws.get(f"qkv.{i}", (T, 3 * H), AD) if training else ws.get("qkv", (T, 3 * H), AD)
             lib.gemm(x16, W[f"qkv.w.{i}"], qkv, bias=W[f"qkv.b.{i}"])
             x32, x16, rec = self._layer_pass(i, i, x32, qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], training)
             if training:
@@ -822,8 +931,9 @@ class BertEngine(DebertaEngine):
                 sv["passes"].append(rec)
         if training:
             sv.update(e32=e32, emb_mean=emb_mean, emb_rstd=emb_rstd, video16=v16, use_video=use_video)
-            self.saved = sv
+            self.saved = st.sv = sv
         self.o2_32, self.o2_16 = x32, x16
+        st.o2 = (x32, x16)
         return x32, x16
 
     def _bwd_encoder(self, dy32):

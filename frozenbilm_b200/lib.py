@@ -11,10 +11,12 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfrozenbilm_sm100.so")
+LIB_DBG_PATH = os.path.join(_HERE, "libfrozenbilm_sm100_dbg.so")   # test-only (include/frozenbilm_b200_debug.h)
 
 FB_ACT_NONE, FB_ACT_GELU, FB_ACT_RELU = 0, 1, 2
 FB_AUX_NONE, FB_AUX_MUL_GELU_GRAD, FB_AUX_MUL_RELU_MASK, FB_AUX_ADD = 0, 1, 2, 3
 FB_DT_BF16, FB_DT_F32 = 0, 1
+SCORE_DTYPE = torch.float16   # dtype of the saved attention scores (fb_attn_fwd s_out -> fb_attn_bwd s2)
 
 
 class FbError(RuntimeError):
@@ -111,6 +113,33 @@ class AttnBwdRelArgs(C.Structure):
     ]
 
 
+class EpilogueArgs(C.Structure):
+    _fields_ = [
+        ("M", C.c_int), ("N", C.c_int),
+        ("inp", C.c_void_p), ("ld_in", C.c_longlong), ("alpha", C.c_float),
+        ("bias", C.c_void_p), ("rowmask", C.c_void_p), ("drop", Dropout), ("drop_pos", C.c_int),
+        ("D_pre", C.c_void_p), ("ld_pre", C.c_longlong), ("act", C.c_int),
+        ("aux", C.c_void_p), ("ld_aux", C.c_longlong), ("aux_op", C.c_int),
+        ("resid", C.c_void_p), ("ld_resid", C.c_longlong), ("accumulate", C.c_int),
+        ("D", C.c_void_p), ("ldd", C.c_longlong),
+    ]
+
+
+class AttnF32Args(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("L", C.c_int), ("h", C.c_int),
+        ("Q", C.c_void_p), ("ldq", C.c_longlong), ("K", C.c_void_p), ("ldk", C.c_longlong),
+        ("V", C.c_void_p), ("ldv", C.c_longlong),
+        ("pqk", C.c_void_p), ("ld_pqk", C.c_longlong), ("bucket_of_rel", C.c_void_p),
+        ("mask", C.c_void_p), ("key_mask_only", C.c_int),
+        ("scale", C.c_float), ("dropout_p", C.c_float), ("seed", C.c_ulonglong), ("offset", C.c_ulonglong),
+        ("ctx", C.c_void_p), ("ldc", C.c_longlong), ("lse", C.c_void_p),
+        ("dctx", C.c_void_p), ("dQ", C.c_void_p), ("lddq", C.c_longlong), ("dK", C.c_void_p), ("lddk", C.c_longlong),
+        ("dV", C.c_void_p), ("lddv", C.c_longlong),
+        ("dpqk", C.c_void_p), ("ld_dpqk", C.c_longlong), ("ws_ds", C.c_void_p), ("ws_pd", C.c_void_p),
+    ]
+
+
 class UmmaProbeArgs(C.Structure):
     _fields_ = [
         ("a_image", C.c_void_p), ("a_bytes", C.c_int),
@@ -125,6 +154,17 @@ class UmmaProbeArgs(C.Structure):
 
 
 _lib = None
+_lib_dbg = None
+
+
+def use_debug_library():
+    """scripts/ and tests/ only: route every call of this process through the debug build (same kernels compiled with
+    -DFB_DEBUG_SURFACE plus fb_umma_probe / fb_attn_bwd_set_debug).  Must be called before the first load()."""
+    global _lib, _lib_dbg
+    if _lib is not None and _lib is not _lib_dbg:
+        raise FbError("use_debug_library() must be called before the product library is loaded")
+    _lib = _lib_dbg = _load(LIB_DBG_PATH, EXPORTS + DEBUG_EXPORTS)
+    return _lib
 
 
 def load() -> C.CDLL:
@@ -132,14 +172,19 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise FbError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+    _lib = _load(LIB_PATH, EXPORTS)
+    return _lib
+
+
+def _load(path, exports) -> C.CDLL:
+    if not os.path.exists(path):
+        raise FbError(f"{path} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
                       "(there is no CPU / eager fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     lib.fb_last_error.restype = C.c_char_p
     lib.fb_abi_version.restype = C.c_int
     lib.fb_launch_count.restype = C.c_longlong
-    for name in EXPORTS:
+    for name in exports:
         if name in ("fb_last_error", "fb_abi_version", "fb_launch_count"):
             continue
         getattr(lib, name).restype = C.c_int
@@ -162,7 +207,11 @@ def load() -> C.CDLL:
     lib.fb_rel_to_bucket.argtypes = [vp, vp, i, i, vp, i, i, i, vp, ll, vp]
     lib.fb_mlm_corrupt.argtypes = [vp, vp, ll, ll, ll, ll, f, C.c_ulonglong, vp, vp, vp]
     lib.fb_gather_frames.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp]
-    _lib = lib
+    lib.fb_split3.argtypes = [vp, ll, i, i, i, i, ll, vp, ll, vp]
+    lib.fb_colsum_f32.argtypes = [vp, ll, i, i, vp, vp]
+    lib.fb_conv_im2col_f32.argtypes = [vp, i, i, i, vp, vp]
+    lib.fb_conv_col2im_f32.argtypes = [vp, i, i, i, vp, i, vp]
+    lib.fb_cross_entropy_f32.argtypes = [vp, ll, i, i, vp, vp, f, vp, ll, f, vp]
     return lib
 
 
@@ -172,9 +221,12 @@ EXPORTS = [
     "fb_layernorm_fwd", "fb_layernorm_bwd", "fb_move_rows", "fb_gelu_bwd", "fb_add_rowbcast", "fb_conv_im2col",
     "fb_conv_col2im", "fb_colsum_bf16", "fb_cross_entropy", "fb_dropout_apply", "fb_sumsq", "fb_adam_step",
     "fb_cast_f32_bf16", "fb_attn_bwd_prep", "fb_rel_to_bucket", "fb_attn_bwd", "fb_attn_bwd_rel",
-    "fb_umma_probe", "fb_attn_bwd_set_debug", "fb_mlm_corrupt", "fb_gather_frames",
-    "fb_gemm_cluster_capacity",
+    "fb_mlm_corrupt", "fb_gather_frames", "fb_gemm_cluster_capacity",
+    "fb_split3", "fb_epilogue_f32", "fb_colsum_f32", "fb_conv_im2col_f32", "fb_conv_col2im_f32",
+    "fb_cross_entropy_f32", "fb_attn_fwd_f32", "fb_attn_bwd_f32",
 ]
+# include/frozenbilm_b200_debug.h: only in libfrozenbilm_sm100_dbg.so
+DEBUG_EXPORTS = ["fb_umma_probe", "fb_attn_bwd_set_debug"]
 
 
 def check(rc: int, what: str):
@@ -207,6 +259,10 @@ def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, a_mn_major=False,
     A: bf16 [M, K] (or [K, M] when a_mn_major);  B: bf16 [N, K] (or [K, N] when b_mn_major);
     2-D (or 3-D batched) views with unit inner stride.  D: bf16 or fp32 [M, N].
     """
+    if A.dtype == torch.float32:
+        return _gemm_split3(A, B, D, a_mn_major=a_mn_major, b_mn_major=b_mn_major, bias=bias, act=act, D_pre=D_pre,
+                            aux=aux, aux_op=aux_op, resid=resid, alpha=alpha, accumulate=accumulate or split_k > 1,
+                            M=M, N=N, K=K, rowmask=rowmask, dropout=dropout, drop_pos=drop_pos, batch=batch)
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
     assert A.stride(-1) == 1 and B.stride(-1) == 1 and D.stride(-1) == 1
     nbatch = 1
@@ -263,6 +319,107 @@ def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, a_mn_major=False,
     return D
 
 
+# --------------------------------------------------------------------------------------------------------------
+# fp32-class instantiation (FB_PRECISION=fp32x3): the engine keeps its "bf16" buffers in fp32 and every wrapper
+# below routes an fp32-typed operand to the split-bf16 / fp32 kernels of fb_precise.cu.  Same schedule, same call
+# sites; only the operand precision differs.  Not tuned (temporaries are allocated per call).
+# --------------------------------------------------------------------------------------------------------------
+def split3(x: torch.Tensor, rows: int, cols: int, *, along_rows: bool, b_mode: bool):
+    """fp32 2-D view [>= rows, >= cols] -> bf16 [rows, 3 Kp] (K = columns) or [3 Kp, ceil8(cols)] (K = rows)."""
+    assert x.dtype == torch.float32 and x.stride(-1) == 1
+    if along_rows:
+        kp = (rows + 7) // 8 * 8
+        out = torch.zeros(3 * kp, (cols + 7) // 8 * 8, device=x.device, dtype=torch.bfloat16)
+    else:
+        kp = (cols + 7) // 8 * 8
+        out = torch.zeros(rows, 3 * kp, device=x.device, dtype=torch.bfloat16)
+    check(load().fb_split3(_ptr(x), x.stride(0), rows, cols, int(along_rows), int(b_mode), kp, _ptr(out),
+                           out.stride(0), stream_ptr()), "fb_split3")
+    return out, kp
+
+
+def epilogue_f32(inp, D, *, alpha=1.0, bias=None, rowmask=None, dropout=None, drop_pos=0, D_pre=None, act=FB_ACT_NONE,
+                 aux=None, aux_op=FB_AUX_NONE, resid=None, accumulate=False, M=None, N=None):
+    a = EpilogueArgs()
+    a.M, a.N = (inp.shape[0] if M is None else M), (inp.shape[1] if N is None else N)
+    for t in (inp, D, D_pre, aux, resid):
+        assert t is None or (t.dtype == torch.float32 and t.stride(-1) == 1)
+    a.inp, a.ld_in, a.alpha = _ptr(inp), inp.stride(0), float(alpha)
+    a.bias, a.rowmask = _ptr(bias), _ptr(rowmask)
+    if dropout is not None and dropout.p > 0:
+        a.drop, a.drop_pos = dropout, int(drop_pos)
+    if D_pre is not None:
+        a.D_pre, a.ld_pre = _ptr(D_pre), D_pre.stride(0)
+    a.act = act
+    if aux is not None:
+        a.aux, a.ld_aux, a.aux_op = _ptr(aux), aux.stride(0), aux_op
+    if resid is not None:
+        a.resid, a.ld_resid = _ptr(resid), resid.stride(0)
+    a.accumulate = int(accumulate)
+    a.D, a.ldd = _ptr(D), D.stride(0)
+    check(load().fb_epilogue_f32(C.byref(a), stream_ptr()), "fb_epilogue_f32")
+    return D
+
+
+def _gemm_split3(A, B, D, *, a_mn_major, b_mn_major, bias, act, D_pre, aux, aux_op, resid, alpha, accumulate, M, N, K,
+                 rowmask, dropout, drop_pos, batch):
+    """fb_gemm at fp32-class precision: operands split into bf16 (hi, lo) blocks along K, ONE tcgen05 GEMM over the
+    tripled K (hi.hi + hi.lo + lo.hi, fp32 accumulation), then the fp32 epilogue."""
+    if batch is not None or A.dim() != 2:
+        raise NotImplementedError("split-bf16 GEMM: batched mode is not part of the fp32-class instantiation")
+    assert B.dtype == torch.float32 and D.dtype == torch.float32
+    if M is None:
+        M = A.shape[1] if a_mn_major else A.shape[0]
+    if K is None:
+        K = A.shape[0] if a_mn_major else A.shape[1]
+    if N is None:
+        N = B.shape[1] if b_mn_major else B.shape[0]
+    A3, kp = split3(A, K, M, along_rows=True, b_mode=False) if a_mn_major else \
+        split3(A, M, K, along_rows=False, b_mode=False)
+    B3, kp2 = split3(B, K, N, along_rows=True, b_mode=True) if b_mn_major else \
+        split3(B, N, K, along_rows=False, b_mode=True)
+    assert kp == kp2
+    raw = torch.empty(M, (N + 7) // 8 * 8, device=A.device, dtype=torch.float32)
+    gemm(A3, B3, raw, a_mn_major=a_mn_major, b_mn_major=b_mn_major, M=M, N=N, K=3 * kp)
+    return epilogue_f32(raw, D, alpha=alpha, bias=bias, rowmask=rowmask, dropout=dropout, drop_pos=drop_pos,
+                        D_pre=D_pre, act=act, aux=aux, aux_op=aux_op, resid=resid, accumulate=accumulate, M=M, N=N)
+
+
+def _attn_f32_args(Q, K, V, pqk, bucket_of_rel, mask_u8, ctx, lse, B, L, h, scale, drop, key_mask_only):
+    a = AttnF32Args()
+    a.B, a.L, a.h = B, L, h
+    for t in (Q, K, V, ctx, lse):
+        assert t.dtype == torch.float32
+    a.Q, a.ldq, a.K, a.ldk, a.V, a.ldv = _ptr(Q), Q.stride(0), _ptr(K), K.stride(0), _ptr(V), V.stride(0)
+    if pqk is not None:
+        assert pqk.dtype == torch.float32 and bucket_of_rel.dtype == torch.int32
+        a.pqk, a.ld_pqk, a.bucket_of_rel = _ptr(pqk), pqk.stride(0), _ptr(bucket_of_rel)
+    a.mask, a.key_mask_only = _ptr(mask_u8), int(key_mask_only)
+    a.scale = float(scale)
+    if drop is not None:
+        a.dropout_p, a.seed, a.offset = float(drop.p), int(drop.seed), int(drop.offset)
+    a.ctx, a.ldc, a.lse = _ptr(ctx), ctx.stride(0), _ptr(lse)
+    return a
+
+
+def attn_fwd_f32(Q, K, V, pqk, bucket_of_rel, mask_u8, ctx, lse, *, B, L, h, scale, drop=None, key_mask_only=False):
+    a = _attn_f32_args(Q, K, V, pqk, bucket_of_rel, mask_u8, ctx, lse, B, L, h, scale, drop, key_mask_only)
+    check(load().fb_attn_fwd_f32(C.byref(a), stream_ptr()), "fb_attn_fwd_f32")
+
+
+def attn_bwd_f32(Q, K, V, pqk, bucket_of_rel, mask_u8, ctx, lse, dctx, dQ, dK, dV, dpqk, *, B, L, h, scale, drop=None,
+                 key_mask_only=False):
+    a = _attn_f32_args(Q, K, V, pqk, bucket_of_rel, mask_u8, ctx, lse, B, L, h, scale, drop, key_mask_only)
+    assert dctx.stride(0) == ctx.stride(0)
+    ws = torch.empty(2, B, h, L, L, device=Q.device, dtype=torch.float32)
+    a.dctx = _ptr(dctx)
+    a.dQ, a.lddq, a.dK, a.lddk, a.dV, a.lddv = _ptr(dQ), dQ.stride(0), _ptr(dK), dK.stride(0), _ptr(dV), dV.stride(0)
+    if dpqk is not None:
+        a.dpqk, a.ld_dpqk = _ptr(dpqk), dpqk.stride(0)
+    a.ws_ds, a.ws_pd = _ptr(ws[0]), _ptr(ws[1])
+    check(load().fb_attn_bwd_f32(C.byref(a), stream_ptr()), "fb_attn_bwd_f32")
+
+
 def rel_table_geometry(L: int):
     """(rel_rows, rel_off) of the per-relative-position tables for sequence length L."""
     lpad = (L + 127) // 128 * 128
@@ -305,7 +462,7 @@ def attn_fwd(Q, K, V, PKrel, PQrel, mask_u8, ctx, lse, *, B, L, h, scale, dropou
     a.scale = float(scale)
     a.dropout_p, a.seed, a.offset = float(dropout_p), int(seed), int(offset)
     if s_out is not None:
-        assert s_out.dtype == torch.float32 and s_out.shape[-1] == (L + 127) // 128 * 128
+        assert s_out.dtype == SCORE_DTYPE and s_out.shape[-1] == (L + 127) // 128 * 128
         a.s_out = _ptr(s_out)
     check(load().fb_attn_fwd(C.byref(a), stream_ptr()), "fb_attn_fwd")
     return ctx, lse
@@ -314,14 +471,30 @@ def attn_fwd(Q, K, V, PKrel, PQrel, mask_u8, ctx, lse, *, B, L, h, scale, dropou
 def layernorm_fwd(x, gamma, beta, eps, *, rowmask=None, out_drop=None, y32=None, y16=None, mean=None, rstd=None):
     M, H = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous()
+    wide16 = y16 if (y16 is not None and y16.dtype == torch.float32) else None   # fp32-class mode: no rounding
+    if wide16 is not None:
+        y16 = None
+        y32 = wide16 if y32 is None else y32
     check(load().fb_layernorm_fwd(_ptr(x), M, H, _ptr(gamma), _ptr(beta), float(eps), _ptr(rowmask), _dp(out_drop),
                                   _ptr(y32), _ptr(y16), _ptr(mean), _ptr(rstd), stream_ptr()), "fb_layernorm_fwd")
+    if wide16 is not None and wide16 is not y32:
+        wide16.copy_(y32)
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, *, rowmask=None, out_drop=None, in_drop=None, dx32=None, dx16=None,
                   dgamma=None, dbeta=None, dx16_colsum=None):
     M, H = x.shape
     assert dy.dtype == torch.float32 and dy.is_contiguous() and x.is_contiguous()
+    if dx16 is not None and dx16.dtype == torch.float32:
+        # fp32-class mode: dx "16" = dropout_bwd(dx32) unrounded, its column sums from the fp32 kernel
+        tmp = dx32 if dx32 is not None else torch.empty_like(dx16)
+        check(load().fb_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), M, H, _ptr(rowmask),
+                                      _dp(out_drop), None, _ptr(tmp), None, _ptr(dgamma), _ptr(dbeta), None,
+                                      stream_ptr()), "fb_layernorm_bwd")
+        dropout_apply(tmp, in_drop, out32=dx16)
+        if dx16_colsum is not None:
+            colsum_bf16(dx16, dx16_colsum)
+        return
     check(load().fb_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(gamma), M, H, _ptr(rowmask),
                                   _dp(out_drop), _dp(in_drop), _ptr(dx32), _ptr(dx16), _ptr(dgamma), _ptr(dbeta),
                                   _ptr(dx16_colsum), stream_ptr()), "fb_layernorm_bwd")
@@ -344,30 +517,55 @@ def move_rows(src, dst, *, idx_in=None, idx_out=None, R=None, ncols=None):
 
 def gelu_bwd(dy, pre16, out16, *, rowmask=None, dropout=None):
     M, N = dy.shape
+    if pre16.dtype == torch.float32:
+        # same order as gelu_bwd_kernel: gelu'(pre), dropout backward, row mask
+        epilogue_f32(dy, out16, aux=pre16, aux_op=FB_AUX_MUL_GELU_GRAD, dropout=dropout, drop_pos=2)
+        if rowmask is not None:
+            epilogue_f32(out16, out16, rowmask=rowmask)
+        return
     check(load().fb_gelu_bwd(_ptr(dy), _ptr(pre16), M, N, _ptr(rowmask), _dp(dropout), _ptr(out16), stream_ptr()),
           "fb_gelu_bwd")
 
 
 def add_rowbcast(a, b, B, L, H, out32, out16=None):
+    if out16 is not None and out16.dtype == torch.float32:
+        add_rowbcast(a, b, B, L, H, out32, None)
+        out16.copy_(out32)
+        return
     check(load().fb_add_rowbcast(_ptr(a), _ptr(b), B, L, H, _ptr(out32), _ptr(out16), stream_ptr()), "fb_add_rowbcast")
 
 
 def conv_im2col(x16, B, L, H, out16):
+    if x16.dtype == torch.float32:
+        check(load().fb_conv_im2col_f32(_ptr(x16), B, L, H, _ptr(out16), stream_ptr()), "fb_conv_im2col_f32")
+        return
     check(load().fb_conv_im2col(_ptr(x16), B, L, H, _ptr(out16), stream_ptr()), "fb_conv_im2col")
 
 
 def conv_col2im(dcol16, B, L, H, dx32, accumulate=False):
+    if dcol16.dtype == torch.float32:
+        check(load().fb_conv_col2im_f32(_ptr(dcol16), B, L, H, _ptr(dx32), int(accumulate), stream_ptr()),
+              "fb_conv_col2im_f32")
+        return
     check(load().fb_conv_col2im(_ptr(dcol16), B, L, H, _ptr(dx32), int(accumulate), stream_ptr()), "fb_conv_col2im")
 
 
 def colsum_bf16(x16, out32):
     M, N = x16.shape
+    if x16.dtype == torch.float32:
+        check(load().fb_colsum_f32(_ptr(x16), x16.stride(0), M, N, _ptr(out32), stream_ptr()), "fb_colsum_f32")
+        return
     check(load().fb_colsum_bf16(_ptr(x16), x16.stride(0), M, N, _ptr(out32), stream_ptr()), "fb_colsum_bf16")
 
 
 def cross_entropy(logits32, V, labels, loss_sum, loss_scale, dlogits16=None, grad_scale=0.0):
     P = logits32.shape[0]
     assert labels.dtype == torch.int64 and labels.is_contiguous()
+    if dlogits16 is not None and dlogits16.dtype == torch.float32:
+        check(load().fb_cross_entropy_f32(_ptr(logits32), logits32.stride(0), P, V, _ptr(labels), _ptr(loss_sum),
+                                          float(loss_scale), _ptr(dlogits16), dlogits16.stride(0), float(grad_scale),
+                                          stream_ptr()), "fb_cross_entropy_f32")
+        return
     check(load().fb_cross_entropy(_ptr(logits32), logits32.stride(0), P, V, _ptr(labels), _ptr(loss_sum),
                                   float(loss_scale), _ptr(dlogits16),
                                   dlogits16.stride(0) if dlogits16 is not None else 0, float(grad_scale),
@@ -376,6 +574,9 @@ def cross_entropy(logits32, V, labels, loss_sum, loss_scale, dlogits16=None, gra
 
 def dropout_apply(x32, dropout, *, out32=None, accumulate=False, out16=None):
     M, N = x32.shape
+    if out16 is not None and out16.dtype == torch.float32:
+        assert out32 is None
+        out32, out16 = out16, None
     check(load().fb_dropout_apply(_ptr(x32), M, N, _dp(dropout), _ptr(out32), int(accumulate), _ptr(out16),
                                   stream_ptr()), "fb_dropout_apply")
 
@@ -391,12 +592,16 @@ def adam_step(p, g, m, v, *, lr, beta1, beta2, eps, step, gnorm_sq=None, max_nor
 
 
 def cast_bf16(x32, out16):
+    if out16.dtype == torch.float32:
+        out16.copy_(x32.reshape(out16.shape))
+        return
     check(load().fb_cast_f32_bf16(_ptr(x32), x32.numel(), _ptr(out16), stream_ptr()), "fb_cast_f32_bf16")
 
 
 def attn_bwd_prep(s2, lse, dp, ctx, dctx, ds, pd, z1=None, z2=None, *, B, L, h, scale, dropout_p=0.0, seed=0,
                   offset=0):
     rel_rows, rel_off = rel_table_geometry(L)
+    assert s2.dtype == SCORE_DTYPE
     a = AttnBwdPrepArgs()
     a.B, a.L, a.h, a.lp, a.rel_rows, a.rel_off = B, L, h, s2.shape[-1], rel_rows, rel_off
     a.s2, a.lse, a.dp = _ptr(s2), _ptr(lse), _ptr(dp)
@@ -414,7 +619,7 @@ def attn_bwd(Q, K, V, O, dO, s2, lse, PKrev, PQrel, dQ, dK, dV, ds_out=None, *, 
     [B,h,L,lp]; lse: fp32 [B,h,L]; PKrev: row-reversed PKrel (build_rel_tables(out_pk_rev=...)); ds_out: optional
     bf16 [B,h,L,lp], receives the UNSCALED dS'."""
     rel_rows, rel_off = rel_table_geometry(L)
-    assert s2.dtype == torch.float32 and lse.dtype == torch.float32
+    assert s2.dtype == SCORE_DTYPE and lse.dtype == torch.float32
     assert O.stride(0) == dO.stride(0)
     a = AttnBwdArgs()
     a.B, a.L, a.h, a.lp = B, L, h, s2.shape[-1]
@@ -462,7 +667,7 @@ def umma_probe(a_image, b_image, a_off, b_off, a_desc, b_desc, idesc, N, cycles=
     a.a_desc, a.b_desc, a.idesc, a.N = int(a_desc), int(b_desc), int(idesc), int(N)
     a.out = _ptr(out)
     a.cycles = _ptr(cycles)
-    check(load().fb_umma_probe(C.byref(a), stream_ptr()), "fb_umma_probe")
+    check(use_debug_library().fb_umma_probe(C.byref(a), stream_ptr()), "fb_umma_probe")
     return out
 
 

@@ -21,6 +21,7 @@ class BertForMaskedLM(FrozenBiLMBase):
     def __init__(self, config, max_feats=10, features_dim=768, freeze_lm=True, freeze_mlm=True, ft_ln=True, n_ans=0,
                  freeze_last=True):
         super().__init__()
+        self._require_frozen(freeze_lm, freeze_mlm, freeze_last)
         self.config = config
         self.fb = bert_from_hf(config, features_dim=features_dim, max_feats=max_feats, n_ans=n_ans,
                                freeze_lm=freeze_lm, freeze_mlm=freeze_mlm, ft_ln=ft_ln, freeze_last=freeze_last)

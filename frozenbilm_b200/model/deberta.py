@@ -65,31 +65,34 @@ class FBMaskedLMOutput(dict):
 
 
 class _MLMLossFn(torch.autograd.Function):
-    """Bridges loss.backward() (main.py:81) to the hand-scheduled selective backward."""
+    """Bridges loss.backward() (main.py:81) to the hand-scheduled selective backward.  The node owns the
+    ForwardState of ITS forward, so any number of train-mode forwards may precede one backward."""
 
     @staticmethod
-    def forward(ctx, anchor, module, loss):
-        ctx.module = module
+    def forward(ctx, anchor, module, state, loss):
+        ctx.module, ctx.state = module, state
         return loss.clone()
 
     @staticmethod
     def backward(ctx, dloss):
-        ctx.module._run_backward(scale=float(dloss))
-        return None, None, None
+        ctx.module._run_backward(ctx.state, scale=float(dloss))
+        ctx.state = None
+        return None, None, None, None
 
 
 class _LogitsFn(torch.autograd.Function):
     """Downstream mode (mc.py / videoqa.py): gradients arrive through the answer-head logits."""
 
     @staticmethod
-    def forward(ctx, anchor, module, logits):
-        ctx.module = module
+    def forward(ctx, anchor, module, state, logits):
+        ctx.module, ctx.state = module, state
         return logits.clone()
 
     @staticmethod
     def backward(ctx, dlogits):
-        ctx.module._run_backward(dlogits=dlogits)
-        return None, None, None
+        ctx.module._run_backward(ctx.state, dlogits=dlogits)
+        ctx.state = None
+        return None, None, None, None
 
 
 class FrozenBiLMBase(nn.Module):
@@ -105,6 +108,30 @@ class FrozenBiLMBase(nn.Module):
         self._engine_obj = None
         self._flat = None
         self._anchor = None
+        self._frozen_sig = None
+        # "bf16" (training path) | "fp32x3" (fp32-class instantiation, the configs[0] parity gate)
+        self.precision = os.environ.get("FB_PRECISION", "bf16")
+
+    def set_precision(self, precision: str):
+        """Selects the arithmetic of the contractions: "bf16" or "fp32x3" (see DebertaEngine)."""
+        if precision not in ("bf16", "fp32x3"):
+            raise ValueError(f"unknown precision {precision!r}")
+        if precision != self.precision:
+            self.precision = precision
+            self._engine_obj = None
+        return self
+
+    @staticmethod
+    def _require_frozen(freeze_lm, freeze_mlm, freeze_last):
+        """The selective backward only produces gradients for adapters, LayerNorms and linear_video.  The reference's
+        --ft_lm / --ft_mlm / --ft_last (UnFrozenBiLM recipes) would need dW for every LM matrix, the embeddings and
+        the answer head: refuse loudly instead of silently training nothing."""
+        bad = [n for n, v in (("freeze_lm", freeze_lm), ("freeze_mlm", freeze_mlm), ("freeze_last", freeze_last))
+               if not v]
+        if bad:
+            raise NotImplementedError(
+                f"{', '.join(bad)}=False (--ft_lm / --ft_mlm / --ft_last) is not supported: this build implements the "
+                "FROZEN-LM path (gradients for adapters, LayerNorms and linear_video only)")
 
     @property
     def device(self):
@@ -147,10 +174,17 @@ class FrozenBiLMBase(nn.Module):
                               grad32=torch.zeros(total_pad, device=dev, dtype=torch.float32), slices=slices,
                               sig=tuple((n, p.data_ptr()) for n, p in train), version=-1, total=total)
             self._engine_obj = None
+        # frozen tensors: version counters of the PARAMETERS (p.data has its own, which load_state_dict never bumps)
+        fsig = tuple((n, p._version, p.data_ptr()) for n, p in named.items() if not p.requires_grad)
         if self._engine_obj is None:
-            self._engine_obj = self.engine_cls(self.fb, self._engine_params(named), dev)
+            self._engine_obj = self.engine_cls(self.fb, self._engine_params(named), dev, self.precision)
             self._anchor = torch.zeros(1, device=dev, requires_grad=True)
             self._flat["version"] = -1
+        elif fsig != self._frozen_sig:
+            # load_state_dict / in-place edit / .to(): refresh the operand copies of the frozen matrices
+            self._engine_obj.P = self._engine_params(named)
+            self._engine_obj.prepare_frozen()
+        self._frozen_sig = fsig
         fl = self._flat
         ver = fl["flat32"]._version + sum(p._version for n, p in train)
         if fl["version"] != ver:
@@ -180,6 +214,8 @@ class FrozenBiLMBase(nn.Module):
         a2v = we.data[a2tok]
         nz = (a2tok != pad)
         sum_tokens = nz.sum(1, keepdim=True)
+        if not freeze_last:
+            self._require_frozen(True, True, freeze_last)
         if len(a2v) != self.n_ans:
             assert not self.training
             self.n_ans = len(a2v)
@@ -219,32 +255,38 @@ class FrozenBiLMBase(nn.Module):
             n_sel = int(sel.numel())
         with torch.no_grad():
             eng.forward_encoder(video, video_mask, input_ids, attention_mask, training)
+            state = eng.cur
             if labels is not None:
                 if n_sel == 0:
                     loss = torch.full((), float("nan"), device=dev)
                 else:
                     loss = eng.head_mlm_loss(sel, flat_lab[sel].contiguous(), n_sel, want_grad=training)
             else:
-                logits = self._full_logits(eng, B, L, mlm=mlm)
+                logits = self._full_logits(eng, state, B, L, mlm=mlm)
         if labels is not None:
-            logits_fn = lambda: self._full_logits(eng, B, L, mlm=True, scratch=True)
+            logits_fn = lambda: self._full_logits(eng, state, B, L, mlm=True, scratch=True)
             if training and n_sel > 0:
-                loss = _MLMLossFn.apply(self._anchor, self, loss)
+                loss = _MLMLossFn.apply(self._anchor, self, state, loss)
+            else:
+                state.release()
             return FBMaskedLMOutput(loss=loss, logits_fn=logits_fn)
         if training:
-            logits = _LogitsFn.apply(self._anchor, self, logits)
+            logits = _LogitsFn.apply(self._anchor, self, state, logits)
         return FBMaskedLMOutput(logits=logits)
 
-    def _full_logits(self, eng, B, L, mlm, keep_for_backward=False, scratch=False):
+    def _full_logits(self, eng, state, B, L, mlm, scratch=False):
+        if eng.cur is not state:
+            raise lib.FbError("the lazily materialised logits of an earlier forward are gone: read out['logits'] "
+                              "before the next forward()")
         T = B * L
         n = self.fb.vocab_size if (mlm or not self.fb.n_ans) else self.fb.n_ans
         out = torch.empty(T, n, device=self.device, dtype=torch.float32)
         with torch.no_grad():
-            eng.head_logits(eng.o2_16, T, mlm=(mlm or not self.fb.n_ans), out=out, scratch=scratch)
+            eng.head_logits(state.o2[1], T, mlm=(mlm or not self.fb.n_ans), out=out, scratch=scratch)
         return out.view(B, L, n)
 
     # ------------------------------------------------------------------ backward bridge
-    def _run_backward(self, scale=None, dlogits=None):
+    def _run_backward(self, state, scale=None, dlogits=None):
         eng = self._engine_obj
         fl = self._flat
         named = self._param_dict()
@@ -257,7 +299,7 @@ class FrozenBiLMBase(nn.Module):
             fl["grad32"].zero_()
         else:
             foreign = {}
-        eng.backward(views, scale=scale, dlogits=dlogits)
+        eng.backward(views, scale=scale, dlogits=dlogits, state=state)
         for n, p in train:
             if n in foreign:
                 views[n].add_(foreign[n])
@@ -269,6 +311,7 @@ class DebertaV2ForMaskedLM(FrozenBiLMBase):
     def __init__(self, config, max_feats=10, features_dim=768, freeze_lm=True, freeze_mlm=True, ds_factor_attn=8,
                  ds_factor_ff=8, ft_ln=True, dropout=0.1, n_ans=0, freeze_last=True):
         super().__init__()
+        self._require_frozen(freeze_lm, freeze_mlm, freeze_last)
         self.config = config
         self.fb = FBConfig.from_hf(config, features_dim=features_dim, max_feats=max_feats,
                                    ds_factor_attn=ds_factor_attn, ds_factor_ff=ds_factor_ff,

@@ -9,6 +9,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from frozenbilm_b200 import lib
+
+lib.use_debug_library()   # test-only build with the probe / phase-stamp hooks
 from frozenbilm_b200.relpos import bucket_of_rel
 
 B, L, h = 32, 352, 24
@@ -27,7 +29,7 @@ PQrel, PKrel = lib.build_rel_tables(pqk, bor, L, h, out_pk_rev=PKrev)
 Q, K, V = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
 ctx = torch.zeros(B * L, H, device=dev, dtype=torch.bfloat16)
 lse = torch.empty(B, h, L, device=dev)
-s2 = torch.empty(B, h, L, lp, device=dev)
+s2 = torch.empty(B, h, L, lp, device=dev, dtype=lib.SCORE_DTYPE)
 lib.attn_fwd(Q, K, V, PKrel, PQrel, mask, ctx, lse, B=B, L=L, h=h, scale=scale, dropout_p=0.1, seed=3, offset=5, s_out=s2)
 dqkv = torch.empty(B * L, 3 * H, device=dev, dtype=torch.bfloat16)
 ds = torch.empty(B, h, L, lp, device=dev, dtype=torch.bfloat16)
@@ -49,7 +51,7 @@ e1.record()
 torch.cuda.synchronize()
 print(f"fb_attn_bwd: {e0.elapsed_time(e1) / 5 * 1e3:.1f} us per launch (no stamps)")
 stamps = torch.zeros(16 * 32, dtype=torch.int64, device=dev)
-fn = lib.load().fb_attn_bwd_set_debug
+fn = lib.use_debug_library().fb_attn_bwd_set_debug
 fn.argtypes = [C.c_void_p]
 fn(C.c_void_p(stamps.data_ptr()))
 bwd()

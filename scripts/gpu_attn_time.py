@@ -22,7 +22,7 @@ ctx = torch.empty(B * L, H, device=dev, dtype=torch.bfloat16)
 dctx = (torch.randn(B * L, H, device=dev) * 0.1).bfloat16()
 dqkv = torch.empty(B * L, 3 * H, device=dev, dtype=torch.bfloat16)
 lse = torch.empty(B, h, L, device=dev)
-s2 = torch.empty(B, h, L, lp, device=dev)
+s2 = torch.empty(B, h, L, lp, device=dev, dtype=lib.SCORE_DTYPE)
 ds = torch.empty(B, h, L, lp, device=dev, dtype=torch.bfloat16)
 gpk = torch.empty(h, rel_rows, 64, device=dev)
 gpq = torch.empty(h, rel_rows, 64, device=dev)

@@ -10,6 +10,8 @@ import numpy as np
 import torch
 
 from frozenbilm_b200 import lib
+
+lib.use_debug_library()   # test-only build with the probe / phase-stamp hooks
 from gpu_umma_probe import b_image_mn_sw128, bf16_bytes, desc, idesc
 
 for Mm, Nn in ((64, 64),):

@@ -11,6 +11,8 @@ import torch
 
 from frozenbilm_b200 import lib
 
+lib.use_debug_library()   # test-only build with the probe / phase-stamp hooks
+
 M, N = 128, 64
 
 

@@ -8,6 +8,8 @@ import torch
 
 from frozenbilm_b200 import lib
 
+lib.use_debug_library()   # test-only build with the probe / phase-stamp hooks
+
 
 def desc(lbo, sbo, layout):
     return ((lbo >> 4) & 0x3FFF) << 16 | ((sbo >> 4) & 0x3FFF) << 32 | 1 << 46 | layout << 61

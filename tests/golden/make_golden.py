@@ -47,7 +47,7 @@ def logit_slice(logits):
     return logits[..., cols], cols
 
 
-def run_case(name, cfg, B, Lt, F, ragged, mode, seed=1234):
+def run_case(name, cfg, B, Lt, F, ragged, mode, seed=1234, out_dir=HERE):
     torch.manual_seed(0)
     P = synth_params(cfg, seed)
     batch = synth_batch(cfg, B, Lt, seed + 1, n_frames=F, ragged=ragged)
@@ -68,8 +68,11 @@ def run_case(name, cfg, B, Lt, F, ragged, mode, seed=1234):
     kw = dict(video=batch["video"], video_mask=batch["video_mask"], input_ids=batch["input_ids"],
               attention_mask=batch["attention_mask"])
     fx = {}
+    # DebertaV2ForMaskedLM.forward (deberta.py:1414-1427) has no output_hidden_states argument: it always asks the
+    # encoder for them (the enhanced mask decoder needs them) and returns them; BertForMaskedLM.forward takes the flag.
+    hs_kw = dict(output_hidden_states=True) if cfg.arch == "bert" else {}
     if mode == "mlm":
-        out = model(labels=batch["labels"], output_hidden_states=True, **kw)
+        out = model(labels=batch["labels"], **hs_kw, **kw)
         out.loss.backward()
         fx["loss"] = np.float64(out.loss.item())
         for n, p in model.named_parameters():
@@ -79,7 +82,7 @@ def run_case(name, cfg, B, Lt, F, ragged, mode, seed=1234):
                 fx["gslice/" + n] = g[::GRAD_STRIDE].numpy().copy()
     else:
         with torch.no_grad():
-            out = model(output_hidden_states=True, **kw)
+            out = model(**hs_kw, **kw)
     lg = out.logits.detach().numpy()
     sl, cols = logit_slice(lg)
     fx["logits_slice"] = sl.copy()
@@ -89,8 +92,9 @@ def run_case(name, cfg, B, Lt, F, ragged, mode, seed=1234):
     hs = out.hidden_states
     fx["hidden_abs_mean"] = np.array([h.detach().abs().double().mean().item() for h in hs])
     fx["hidden_slice"] = np.stack([h.detach()[:, :, ::37].numpy() for h in hs])
-    np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
+    np.savez_compressed(os.path.join(out_dir, name + ".npz"), **fx)
     print(name, "loss", fx.get("loss"), "logits", lg.shape, "abs-mean", np.abs(lg).mean())
+    return fx
 
 
 if __name__ == "__main__":

@@ -25,7 +25,16 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(dll, name), f"{name} declared in include/frozenbilm_b200.h but not exported"
     assert sorted(lib.EXPORTS) == declared
     dll.fb_abi_version.restype = ctypes.c_int
-    assert dll.fb_abi_version() == 1
+    assert dll.fb_abi_version() == 2
+    # the hardware probe / phase-stamp hooks live only in the test-only debug library
+    for name in lib.DEBUG_EXPORTS:
+        assert not hasattr(dll, name), f"{name} must not be exported by the product library"
+    dbg = ctypes.CDLL(lib.LIB_DBG_PATH)
+    dbg_hdr = open(os.path.join(ROOT, "include", "frozenbilm_b200_debug.h")).read()
+    dbg_hdr = re.sub(r"/\*.*?\*/", "", dbg_hdr, flags=re.S)
+    assert sorted(set(re.findall(r"\b(fb_[a-z0-9_]+)\s*\(", dbg_hdr))) == sorted(lib.DEBUG_EXPORTS)
+    for name in declared + lib.DEBUG_EXPORTS:
+        assert hasattr(dbg, name)
 
 
 def test_compute_fails_loudly_without_gpu():

@@ -62,7 +62,7 @@ def run_case(B, L, h, rel, dropout_p=0.0, seed=0):
     Q, K, V = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
     ctx = torch.zeros(B * L, H, device=dev, dtype=torch.bfloat16)
     lse = torch.empty(B, h, L, device=dev)
-    s2 = torch.full((B, h, L, lp), float("nan"), device=dev)
+    s2 = torch.full((B, h, L, lp), float("nan"), device=dev, dtype=lib.SCORE_DTYPE)
     lib.attn_fwd(Q, K, V, PKrel, PQrel, mask, ctx, lse, B=B, L=L, h=h, scale=scale, dropout_p=dropout_p, seed=seed,
                  offset=5, s_out=s2, key_mask_only=not rel)
     dqkv = torch.full((B * L, 3 * H), float("nan"), device=dev, dtype=torch.bfloat16)

@@ -1,14 +1,15 @@
-"""End-to-end parity of the drop-in model (CUDA path through the C-ABI) on a real B200.
+"""End-to-end parity of the drop-in model in its bf16 TRAINING precision (CUDA path through the C-ABI) on a B200.
 
-Tolerances (the reference is fp32; this path feeds bf16 operands to the tensor cores with fp32
-accumulation, fp32 residual stream / LayerNorm / softmax statistics):
+north_star's rtol 1e-3 / atol 1e-4 against the fp32 reference is gated in tests/test_precise_gpu.py on the
+fp32-class instantiation of the same schedule (FB_PRECISION=fp32x3).  This file holds the bf16 path, whose operand
+rounding (2^-9 per GEMM input) cannot meet that bound, to what bf16 can deliver:
   * vs the golden vectors of the UNMODIFIED fp32 reference: logits max-abs-err <= 0.06 x mean|logit|
     (measured 0.012 on the tiny cases, 0.042 on BASELINE configs[0]); loss rel-err <= 1e-3;
-    every trainable gradient: L2-norm rel-err <= 3e-2.
+    every trainable gradient: L2-norm rel-err <= 3e-2 AND its strided slice within 8e-2 (adapter.down 1.5e-1)
+    relative L2 of the reference slice.
   * vs the oracle run with bf16-rounded contraction operands (same rounding points): logits
-    max-abs-err <= 0.02 x mean|logit|, gradient cosine >= 0.999.
-north_star's rtol=1e-3/atol=1e-4 is not reachable with bf16 operands (one bf16 rounding of the final
-vocabulary GEMM alone is ~2e-3 absolute); see DESIGN.md "Numerics".
+    max-abs-err <= 0.02 x mean|logit|, gradient cosine >= 0.999 -- also at the full XL tile shapes
+    (H = 1536, 24 heads, L = 352, B = 4).
 """
 import math
 
@@ -70,6 +71,11 @@ def test_golden_logits_and_grads(name):
         ref_norm = float(fx["gnorm/" + n])
         rel = abs(g.double().norm().item() - ref_norm) / max(ref_norm, 1e-12)
         assert rel <= 3e-2, f"{n}: grad-norm rel-err {rel}"
+        # direction, not just length: the committed strided slice of the reference gradient
+        sl, rs = g[::GRAD_STRIDE].double().numpy(), fx["gslice/" + n].astype(np.float64)
+        if np.linalg.norm(rs) > 1e-3 * ref_norm:     # a slice that happens to be ~0 carries no direction
+            srel = np.linalg.norm(sl - rs) / np.linalg.norm(rs)
+            assert srel <= (1.5e-1 if "adapter.down" in n else 8e-2), f"{n}: gradient-slice rel-err {srel}"
         n_checked += 1
     assert n_checked == sum(is_trainable(k, cfg) for k in P)
     # lazily materialised full logits of the training forward agree with the eval logits
@@ -183,29 +189,114 @@ def test_train_mode_dropout_is_sane_and_reproducible_in_backward():
     assert abs(out["loss"].item() - l0) <= 0.1 * l0
 
 
-def test_full_width_properties_xl_dims():
-    """BASELINE configs[1] dimensions (H=1536, 24 heads, L=352) with 2 layers: batch-permutation equivariance and
-    gradient linearity in the loss scale -- size-independent properties at the full tile shapes."""
+def test_full_width_against_oracle_xl_dims():
+    """BASELINE configs[1] tile shapes (H = 1536, 24 heads, L = 352, B = 4; 2 layers = 1 ordinary + 2 EMD passes,
+    conv, head) against the oracle with bf16-rounded contraction operands: loss, logits and the direction of every
+    trainable gradient.  (Round 1 only checked size-independent self-consistency at these shapes.)"""
+    from oracle import frozenbilm_oracle as orc
     cfg = CONFIG_XL.replace(num_hidden_layers=2, vocab_size=4096, hidden_dropout_prob=0.0,
                             attention_probs_dropout_prob=0.0, adapter_dropout=0.0)
     P = synth_params(cfg, 3)
     b = synth_batch(cfg, 4, 342, 4)
+    names_t = [n for n in P if is_trainable(n, cfg)]
+    kw = {k: b[k] for k in ("video", "video_mask", "input_ids", "attention_mask")}
+    ref, rgrads = orc.forward_backward(P, cfg, names_t, labels=b["labels"], bf16_gemm_inputs=True, **kw)
     model = build(cfg, P).train()
-    kw = to_dev(b)
-    lab = b["labels"].to(DEV)
-    out = model(labels=lab, **kw)
+    out = model(labels=b["labels"].to(DEV), **to_dev(b))
     out["loss"].backward()
+    assert abs(out["loss"].item() - ref["loss"].item()) <= 5e-4 * ref["loss"].item()
+    lg = out["logits"].float().cpu()
+    scale = ref["logits"].abs().mean().item()
+    assert (lg - ref["logits"].detach()).abs().max().item() <= 0.03 * scale
+    g = dict(model.named_parameters())
+    for n in names_t:
+        a_, b_ = g[n].grad.float().cpu().reshape(-1).double(), rgrads[n].reshape(-1).double()
+        cos = (a_ @ b_ / (a_.norm() * b_.norm() + 1e-30)).item()
+        assert cos >= (0.995 if "adapter.down" in n else 0.999), f"{n}: cosine {cos}"
+        assert abs(a_.norm().item() / b_.norm().item() - 1) <= 2e-2, n
+    # size-independent properties at the same shapes: batch-permutation equivariance, linearity in the loss scale
     g1 = torch.cat([p.grad.reshape(-1).clone() for p in model.parameters() if p.requires_grad])
-    lg = out["logits"].clone()
+    lgd = out["logits"].clone()
+    lab = b["labels"].to(DEV)
     perm = torch.tensor([2, 0, 3, 1], device=DEV)
     model.zero_grad(set_to_none=True)
-    out2 = model(labels=lab[perm], **{k: v[perm] for k, v in kw.items()})
+    out2 = model(labels=lab[perm], **{k: v[perm] for k, v in to_dev(b).items()})
     (4.0 * out2["loss"]).backward()   # power of two: scaled bf16 operands round identically
     g2 = torch.cat([p.grad.reshape(-1).clone() for p in model.parameters() if p.requires_grad])
-    assert (out2["logits"] - lg[perm]).abs().max().item() <= 1e-3
+    assert (out2["logits"] - lgd[perm]).abs().max().item() <= 1e-3
     assert abs(out2["loss"].item() - out["loss"].item()) <= 1e-4
     rel = ((g2 - 4.0 * g1).norm() / (4.0 * g1).norm()).item()
     assert rel <= 2e-3, rel   # fp32 atomics in split-K dW / LayerNorm gradients make this order-dependent
+
+
+def test_several_forwards_then_one_backward():
+    """The multiple-choice loop of the reference (mc.py:150-172 in train mode) runs one forward per answer candidate
+    and a single loss.backward(): every forward keeps its own saved state, gradients add up."""
+    cfg = CONFIG_TINY.replace(n_ans=2)
+    P = synth_params(cfg, 31)
+    model = build(cfg, P).train()
+    batches = [synth_batch(cfg, 2, 20 + 7 * i, 40 + i) for i in range(3)]
+    ws = [torch.randn(2, b["input_ids"].shape[1] + 10, 2, generator=torch.Generator().manual_seed(i)).to(DEV)
+          for i, b in enumerate(batches)]
+    ref = None
+    for b, w in zip(batches, ws):      # one backward per forward (the pattern round 1 supported)
+        model.zero_grad(set_to_none=True)
+        (model(**to_dev(b))["logits"] * w).sum().backward()
+        gcat = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.requires_grad]).clone()
+        ref = gcat if ref is None else ref + gcat
+    model.zero_grad(set_to_none=True)
+    total = sum((model(**to_dev(b))["logits"] * w).sum() for b, w in zip(batches, ws))
+    total.backward()
+    got = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.requires_grad])
+    assert (got - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    assert len(model._engine_obj._free_slots) == model._engine_obj._n_slots == 3   # every slot was returned
+    # MLM losses summed over two forwards
+    cfg2 = CONFIG_TINY
+    m2 = build(cfg2, synth_params(cfg2, 5)).train()
+    b1, b2 = synth_batch(cfg2, 2, 30, 1), synth_batch(cfg2, 3, 44, 2)
+    l1 = m2(labels=b1["labels"].to(DEV), **to_dev(b1))["loss"]
+    l2 = m2(labels=b2["labels"].to(DEV), **to_dev(b2))["loss"]
+    l1_val = l1.item()
+    (l1 + l2).backward()
+    assert l1.item() == l1_val          # a kept loss is not a view of reused workspace memory
+    assert all(torch.isfinite(p.grad).all() for p in m2.parameters() if p.requires_grad)
+
+
+def test_load_state_dict_after_forward_refreshes_frozen_operands():
+    """the bf16 operand copies of the frozen matrices must follow load_state_dict / in-place edits."""
+    cfg = CONFIG_TINY
+    Pa, Pb = synth_params(cfg, 5), synth_params(cfg, 6)
+    b = synth_batch(cfg, 2, 30, 7)
+    ma = build(cfg, Pa).eval()
+    with torch.no_grad():
+        la = ma(**to_dev(b))["logits"].clone()
+        ma.load_state_dict(Pb, strict=False)
+        lab = ma(**to_dev(b))["logits"].clone()
+        lb = build(cfg, Pb).eval()(**to_dev(b))["logits"]
+    assert (la - lb).abs().max().item() > 1e-2          # the two weight sets really differ
+    assert torch.equal(lab, lb)
+    with torch.no_grad():                               # in-place edit of one frozen matrix
+        ma.deberta.encoder.layer[0].intermediate.dense.weight.mul_(0.5)
+        lc = ma(**to_dev(b))["logits"]
+    assert (lc - lb).abs().max().item() > 1e-4
+
+
+def test_workspace_does_not_grow_with_distinct_shapes():
+    """padding='longest' gives a new (B, L) almost every batch; buffers are keyed by name and sized for
+    the largest batch seen, so smaller shapes allocate nothing new."""
+    cfg = CONFIG_TINY
+    model = build(cfg, synth_params(cfg, 5)).train()
+
+    def step(B, Lt, seed):
+        b = synth_batch(cfg, B, Lt, seed)
+        model.zero_grad(set_to_none=True)
+        model(labels=b["labels"].to(DEV), **to_dev(b))["loss"].backward()
+        eng = model._engine_obj
+        return eng.ws.nbytes() + sum(w.nbytes() for w in eng._free_slots)
+
+    big = step(4, 120, 1)
+    for i, (B, Lt) in enumerate([(4, 100), (3, 77), (2, 118), (4, 64), (1, 33)]):
+        assert step(B, Lt, 10 + i) == big
 
 
 def test_fused_optimizer_matches_torch_adam():
