@@ -538,6 +538,71 @@ __global__ void cast_kernel(const float* __restrict__ x, long long n, __nv_bfloa
     out[i] = __float2bfloat16_rn(x[i]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// softmax over the answer vocabulary + top-k at the [MASK] rows (videoqa.py:164-170: logits.softmax(-1),
+// torch.topk(logits, k); mc.py:168-172: softmax(-1)[:, 0]).  One CTA per row; V up to a few thousand answers.
+// probs_out (nullable): full softmax [P, V].  top_p / top_i: the k largest probabilities (descending; ties -> the
+// lower index, like torch.topk on a strictly ordered input) and their answer ids.
+// ---------------------------------------------------------------------------------------------
+static constexpr int STK_THREADS = 256;
+__global__ void __launch_bounds__(STK_THREADS)
+softmax_topk_kernel(const float* __restrict__ logits, long long ld, int V, int k, float* __restrict__ probs_out,
+                    long long ldp, float* __restrict__ top_p, long long* __restrict__ top_i) {
+  extern __shared__ float srow[];                 // V probabilities
+  __shared__ float rv[STK_THREADS / 32];
+  __shared__ int ri[STK_THREADS / 32];
+  __shared__ float bc;
+  const int row = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* lr = logits + (long long)row * ld;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < V; c += STK_THREADS) { const float x = lr[c]; srow[c] = x; m = fmaxf(m, x); }
+  m = warp_max(m);
+  if (lane == 0) rv[warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = rv[0]; for (int w = 1; w < STK_THREADS / 32; ++w) t = fmaxf(t, rv[w]); bc = t; }
+  __syncthreads();
+  m = bc;
+  float s = 0.0f;
+  for (int c = threadIdx.x; c < V; c += STK_THREADS) { const float e = expf(srow[c] - m); srow[c] = e; s += e; }
+  s = warp_sum(s);
+  __syncthreads();
+  if (lane == 0) rv[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.0f; for (int w = 0; w < STK_THREADS / 32; ++w) t += rv[w]; bc = 1.0f / t; }
+  __syncthreads();
+  const float inv = bc;
+  for (int c = threadIdx.x; c < V; c += STK_THREADS) {
+    const float pr = srow[c] * inv;
+    srow[c] = pr;
+    if (probs_out) probs_out[(long long)row * ldp + c] = pr;
+  }
+  __syncthreads();
+  for (int t = 0; t < k; ++t) {
+    float bv = -1.0f; int bi = 0x7fffffff;
+    for (int c = threadIdx.x; c < V; c += STK_THREADS) {
+      const float x = srow[c];
+      if (x > bv) { bv = x; bi = c; }              // strided scan: lower index wins inside a thread
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { rv[warp] = bv; ri[warp] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float fv = rv[0]; int fi = ri[0];
+      for (int w = 1; w < STK_THREADS / 32; ++w)
+        if (rv[w] > fv || (rv[w] == fv && ri[w] < fi)) { fv = rv[w]; fi = ri[w]; }
+      top_p[(long long)row * k + t] = fv;
+      top_i[(long long)row * k + t] = fi;
+      srow[fi] = -1.0f;                            // remove it from the next round
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace fb
 
 using namespace fb;
@@ -634,6 +699,18 @@ int fb_cross_entropy_f32(const float* logits, long long ld, int P, int V, const 
   }
   fb::ce_kernel<float><<<P, fb::CE_THREADS, fb::CE_SMEM, ST(stream)>>>(logits, ld, V, labels, loss_sum, loss_scale,
                                                                        dlogits_f32, ldd, grad_scale);
+  count_launch();
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int fb_softmax_topk(const float* logits, long long ld, int P, int V, int k, float* probs, long long ldp, float* top_p,
+                    long long* top_i, void* stream) {
+  FB_REQUIRE(logits && P > 0 && V > 0 && k >= 0 && k <= V && (k == 0 || (top_p && top_i)), "fb_softmax_topk: bad args");
+  FB_REQUIRE((size_t)V * 4 <= 200 * 1024, "fb_softmax_topk: answer vocabulary too large for one CTA (V = %d)", V);
+  const size_t smem = (size_t)V * sizeof(float);
+  if (smem > 48 * 1024)
+    FB_CHECK_CUDA(cudaFuncSetAttribute(fb::softmax_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fb::softmax_topk_kernel<<<P, fb::STK_THREADS, smem, ST(stream)>>>(logits, ld, V, k, probs, ldp, top_p, top_i);
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;

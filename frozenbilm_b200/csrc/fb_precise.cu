@@ -2,12 +2,14 @@
 //
 // north_star asks for MLM logits within rtol 1e-3 / atol 1e-4 of the fp32 reference.  One bf16 rounding of a GEMM
 // operand is 2^-9 relative, so the bf16 training path cannot meet that bound; this file supplies what the SAME kernel
-// schedule needs to run every contraction at ~2^-17 relative precision instead:
+// schedule needs to run every contraction at fp32-class (~2^-24 relative) precision instead:
 //
-//   * fb_split3:       x (fp32) -> [hi | hi | lo] (A side) or [hi | lo | hi] (B side) bf16 blocks along K, with
-//                      hi = bf16(x), lo = bf16(x - hi).  The ordinary tcgen05 GEMM (fb_gemm) over the tripled K then
-//                      accumulates  hi.hi + hi.lo + lo.hi  in fp32 TMEM: a 3-pass split-bf16 product, the dropped
-//                      lo.lo term is 2^-18 relative.  No new tensor-core kernel, the product GEMM is the one measured.
+//   * fb_split3:       x (fp32) -> three bf16 pieces p0 + p1 + p2 (24 mantissa bits), laid out as six blocks along K
+//                      (A side: p0 p0 p1 p1 p0 p2, B side: p0 p1 p0 p1 p2 p0).  The ordinary tcgen05 GEMM (fb_gemm) over
+//                      the 6x longer K then accumulates the six products larger than 2^-24 |a||b| in fp32 TMEM: an
+//                      fp32-class product on the bf16 tensor pipe.  No new tensor-core kernel: the product GEMM is the
+//                      one measured.  (Two pieces / three products leave 2^-17 per operand: measured 1.1e-4 on the
+//                      configs[0] logits after 12 layers, just over north_star's atol.)
 //   * fb_epilogue_f32: the GEMM epilogue (alpha, bias, row mask, dropout, pre-activation copy, GELU/ReLU, aux op,
 //                      residual, accumulate) with every operand in fp32 (the bf16 path rounds aux / D_pre).
 //   * fb_attn_fwd_f32 / fb_attn_bwd_f32: disentangled attention (deberta.py:717-947) in fp32 on the CUDA cores,
@@ -30,17 +32,18 @@ __global__ void split3_kernel(const float* __restrict__ x, long long ld, int row
   if (idx >= (long long)rows * cols) return;
   const int r = (int)(idx / cols), c = (int)(idx % cols);
   const float v = x[(long long)r * ld + c];
-  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-  const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-  // A side: (hi, hi, lo)   B side: (hi, lo, hi)   ->  sum over blocks = hi.hi + hi.lo + lo.hi
-  const __nv_bfloat16 b0 = hi, b1 = b_mode ? lo : hi, b2 = b_mode ? hi : lo;
-  if (along_rows) {
-    out[((long long)r) * ld_out + c] = b0;
-    out[(block_stride + r) * ld_out + c] = b1;
-    out[(2 * block_stride + r) * ld_out + c] = b2;
-  } else {
-    __nv_bfloat16* o = out + (long long)r * ld_out + c;
-    o[0] = b0; o[block_stride] = b1; o[2 * block_stride] = b2;
+  // three bf16 pieces, 24 mantissa bits in total: v = p0 + p1 + p2 (+ <= 2^-25 |v|)
+  const __nv_bfloat16 p0 = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(p0);
+  const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 p2 = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+  // the six products larger than 2^-24 |a||b|:  a0 b0 + a0 b1 + a1 b0 + a1 b1 + a0 b2 + a2 b0
+  //   A side blocks: a0 a0 a1 a1 a0 a2      B side blocks: b0 b1 b0 b1 b2 b0
+  const __nv_bfloat16 blk[6] = {p0, b_mode ? p1 : p0, b_mode ? p0 : p1, p1, b_mode ? p2 : p0, b_mode ? p0 : p2};
+#pragma unroll
+  for (int t = 0; t < 6; ++t) {
+    if (along_rows) out[(t * block_stride + r) * ld_out + c] = blk[t];
+    else out[(long long)r * ld_out + t * block_stride + c] = blk[t];
   }
 }
 

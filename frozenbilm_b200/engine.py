@@ -238,22 +238,28 @@ class DebertaEngine:
         self.head_saved = None
         return st
 
-    def _video_prefix(self, video, B, F, L, e32, wname, bname):
-        """linear_video(video) into the F visual rows of every sample of e32 [B*L, H] (deberta.py:993-1010)."""
+    def _video_prefix(self, video, B, F, L, e32, wname, bname, repeat=1):
+        """linear_video(video) into the F visual rows of every sample of e32 [B*L, H] (deberta.py:993-1010).
+        ``repeat`` = C: one clip serves C consecutive samples and is projected once."""
         cfg, ws, dev = self.cfg, self.ws, self.device
         Dv, H = cfg.features_dim, cfg.hidden_size
-        v16 = self.sws.get("video16", (B * F, _ceil8(Dv)), self.AD)
-        vin = video.to(dev, F32).reshape(B * F, Dv).contiguous()
+        Bv = B // repeat
+        if repeat > 1 and self.training:
+            raise NotImplementedError("video_repeat > 1 is an inference path (the candidates share one projection)")
+        v16 = self.sws.get("video16", (Bv * F, _ceil8(Dv)), self.AD)
+        vin = video.to(dev, F32).reshape(Bv * F, Dv).contiguous()
         if _ceil8(Dv) != Dv:
             v16.zero_()
             v16[:, :Dv] = vin.to(self.AD)
         else:
             lib.cast_bf16(vin, v16)
         ar = torch.arange(B, device=dev)[:, None] * L
-        if self.precise:
-            pv32 = ws.get("video.proj", (B * F, H), F32)
+        if self.precise or repeat > 1:
+            pv32 = ws.get("video.proj", (Bv * F, H), F32)
             lib.gemm(v16, self.t16(wname), pv32, bias=self.P[bname], N=H, K=Dv)
-            lib.move_rows(pv32, e32, idx_out=(ar + torch.arange(F, device=dev)[None, :]).reshape(-1).contiguous())
+            fr = torch.arange(F, device=dev)[None, :]
+            idx_in = ((torch.arange(B, device=dev) // repeat)[:, None] * F + fr).reshape(-1).contiguous()
+            lib.move_rows(pv32, e32, idx_in=idx_in, idx_out=(ar + fr).reshape(-1).contiguous())
         else:
             lib.gemm(v16, self.t16(wname), e32, bias=self.P[bname], M=F, N=H, K=Dv,
                      batch={"outer": (B, F * v16.stride(0), 0, L * H)})
@@ -261,7 +267,9 @@ class DebertaEngine:
         return v16, idx_out
 
     # ------------------------------------------------------------------ forward
-    def forward_encoder(self, video, video_mask, input_ids, attention_mask, training):
+    def forward_encoder(self, video, video_mask, input_ids, attention_mask, training, video_repeat=1):
+        """``video_repeat`` = C > 1: ``video`` holds one clip per C consecutive rows of ``input_ids`` (the answer
+        candidates of one question, mc.py:150-172); the visual prefix is projected once per clip."""
         cfg, P, W, ws = self.cfg, self.P, self.W, self.ws
         st = self.begin_forward(training)
         sws, AD = self.sws, self.AD
@@ -284,7 +292,11 @@ class DebertaEngine:
             attention_mask = torch.ones(B, Lt, device=dev, dtype=torch.long)
         if use_video:
             if video_mask is None:
-                video_mask = torch.ones(B, F, device=dev, dtype=torch.long)
+                video_mask = torch.ones(video.shape[0], F, device=dev, dtype=torch.long)
+            if video_repeat > 1:
+                if video.shape[0] * video_repeat != B:
+                    raise ValueError(f"video_repeat={video_repeat}: {video.shape[0]} clips for {B} text rows")
+                video_mask = video_mask.to(dev).repeat_interleave(video_repeat, 0)
             m = torch.cat([video_mask.to(dev), attention_mask.to(dev)], 1)
         else:
             m = attention_mask.to(dev)
@@ -295,7 +307,8 @@ class DebertaEngine:
         e32 = sws.get("e32", (T, H), F32)
         v16, idx_out = None, None
         if use_video:
-            v16, idx_out = self._video_prefix(video, B, F, L, e32, e + "linear_video.weight", e + "linear_video.bias")
+            v16, idx_out = self._video_prefix(video, B, F, L, e32, e + "linear_video.weight", e + "linear_video.bias",
+                                              video_repeat)
         ids = input_ids.to(dev).reshape(-1).contiguous()
         lib.move_rows(P[e + "word_embeddings.weight"], e32, idx_in=ids, idx_out=idx_out)
         x32 = ws.get("x32.0", (T, H), F32)
@@ -882,7 +895,7 @@ class BertEngine(DebertaEngine):
             if cfg.n_ans:
                 self.refresh_answer_embeddings()
 
-    def forward_encoder(self, video, video_mask, input_ids, attention_mask, training):
+    def forward_encoder(self, video, video_mask, input_ids, attention_mask, training, video_repeat=1):
         cfg, P, W, ws = self.cfg, self.P, self.W, self.ws
         st = self.begin_forward(training)
         sws, AD = self.sws, self.AD
@@ -902,7 +915,11 @@ class BertEngine(DebertaEngine):
             attention_mask = torch.ones(B, Lt, device=dev, dtype=torch.long)
         if use_video:
             if video_mask is None:
-                video_mask = torch.ones(B, F, device=dev, dtype=torch.long)
+                video_mask = torch.ones(video.shape[0], F, device=dev, dtype=torch.long)
+            if video_repeat > 1:
+                if video.shape[0] * video_repeat != B:
+                    raise ValueError(f"video_repeat={video_repeat}: {video.shape[0]} clips for {B} text rows")
+                video_mask = video_mask.to(dev).repeat_interleave(video_repeat, 0)
             m = torch.cat([video_mask.to(dev), attention_mask.to(dev)], 1)
         else:
             m = attention_mask.to(dev)
@@ -911,7 +928,8 @@ class BertEngine(DebertaEngine):
         g32 = ws.get("g32", (T, H), F32)
         v16, idx_out = None, None
         if use_video:
-            v16, idx_out = self._video_prefix(video, B, F, L, g32, e + "linear_video.weight", e + "linear_video.bias")
+            v16, idx_out = self._video_prefix(video, B, F, L, g32, e + "linear_video.weight", e + "linear_video.bias",
+                                              video_repeat)
         lib.move_rows(P[e + "word_embeddings.weight"], g32, idx_in=input_ids.to(dev).reshape(-1).contiguous(),
                       idx_out=idx_out)
         pos_type = (P[e + "position_embeddings.weight"][:L] + P[e + "token_type_embeddings.weight"][0]).contiguous()

@@ -207,6 +207,7 @@ def _load(path, exports) -> C.CDLL:
     lib.fb_rel_to_bucket.argtypes = [vp, vp, i, i, vp, i, i, i, vp, ll, vp]
     lib.fb_mlm_corrupt.argtypes = [vp, vp, ll, ll, ll, ll, f, C.c_ulonglong, vp, vp, vp]
     lib.fb_gather_frames.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp]
+    lib.fb_softmax_topk.argtypes = [vp, ll, i, i, i, vp, ll, vp, vp, vp]
     lib.fb_split3.argtypes = [vp, ll, i, i, i, i, ll, vp, ll, vp]
     lib.fb_colsum_f32.argtypes = [vp, ll, i, i, vp, vp]
     lib.fb_conv_im2col_f32.argtypes = [vp, i, i, i, vp, vp]
@@ -223,7 +224,7 @@ EXPORTS = [
     "fb_cast_f32_bf16", "fb_attn_bwd_prep", "fb_rel_to_bucket", "fb_attn_bwd", "fb_attn_bwd_rel",
     "fb_mlm_corrupt", "fb_gather_frames", "fb_gemm_cluster_capacity",
     "fb_split3", "fb_epilogue_f32", "fb_colsum_f32", "fb_conv_im2col_f32", "fb_conv_col2im_f32",
-    "fb_cross_entropy_f32", "fb_attn_fwd_f32", "fb_attn_bwd_f32",
+    "fb_cross_entropy_f32", "fb_attn_fwd_f32", "fb_attn_bwd_f32", "fb_softmax_topk",
 ]
 # include/frozenbilm_b200_debug.h: only in libfrozenbilm_sm100_dbg.so
 DEBUG_EXPORTS = ["fb_umma_probe", "fb_attn_bwd_set_debug"]
@@ -325,14 +326,14 @@ def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, a_mn_major=False,
 # sites; only the operand precision differs.  Not tuned (temporaries are allocated per call).
 # --------------------------------------------------------------------------------------------------------------
 def split3(x: torch.Tensor, rows: int, cols: int, *, along_rows: bool, b_mode: bool):
-    """fp32 2-D view [>= rows, >= cols] -> bf16 [rows, 3 Kp] (K = columns) or [3 Kp, ceil8(cols)] (K = rows)."""
+    """fp32 2-D view [>= rows, >= cols] -> bf16 [rows, 6 Kp] (K = columns) or [6 Kp, ceil8(cols)] (K = rows)."""
     assert x.dtype == torch.float32 and x.stride(-1) == 1
     if along_rows:
         kp = (rows + 7) // 8 * 8
-        out = torch.zeros(3 * kp, (cols + 7) // 8 * 8, device=x.device, dtype=torch.bfloat16)
+        out = torch.zeros(6 * kp, (cols + 7) // 8 * 8, device=x.device, dtype=torch.bfloat16)
     else:
         kp = (cols + 7) // 8 * 8
-        out = torch.zeros(rows, 3 * kp, device=x.device, dtype=torch.bfloat16)
+        out = torch.zeros(rows, 6 * kp, device=x.device, dtype=torch.bfloat16)
     check(load().fb_split3(_ptr(x), x.stride(0), rows, cols, int(along_rows), int(b_mode), kp, _ptr(out),
                            out.stride(0), stream_ptr()), "fb_split3")
     return out, kp
@@ -363,8 +364,8 @@ def epilogue_f32(inp, D, *, alpha=1.0, bias=None, rowmask=None, dropout=None, dr
 
 def _gemm_split3(A, B, D, *, a_mn_major, b_mn_major, bias, act, D_pre, aux, aux_op, resid, alpha, accumulate, M, N, K,
                  rowmask, dropout, drop_pos, batch):
-    """fb_gemm at fp32-class precision: operands split into bf16 (hi, lo) blocks along K, ONE tcgen05 GEMM over the
-    tripled K (hi.hi + hi.lo + lo.hi, fp32 accumulation), then the fp32 epilogue."""
+    """fb_gemm at fp32-class precision: each operand split into three bf16 pieces laid out as six blocks along K, ONE
+    tcgen05 GEMM over the 6x longer K (all products above 2^-24, fp32 accumulation), then the fp32 epilogue."""
     if batch is not None or A.dim() != 2:
         raise NotImplementedError("split-bf16 GEMM: batched mode is not part of the fp32-class instantiation")
     assert B.dtype == torch.float32 and D.dtype == torch.float32
@@ -379,8 +380,13 @@ def _gemm_split3(A, B, D, *, a_mn_major, b_mn_major, bias, act, D_pre, aux, aux_
     B3, kp2 = split3(B, K, N, along_rows=True, b_mode=True) if b_mn_major else \
         split3(B, N, K, along_rows=False, b_mode=True)
     assert kp == kp2
-    raw = torch.empty(M, (N + 7) // 8 * 8, device=A.device, dtype=torch.float32)
-    gemm(A3, B3, raw, a_mn_major=a_mn_major, b_mn_major=b_mn_major, M=M, N=N, K=3 * kp)
+    # TMEM accumulation is not round-to-nearest: every tcgen05.mma added into a live accumulator truncates (measured:
+    # relative error ~ 2^-24 x the number of accumulating instructions: 1.5e-5 after 414 of them, worse than the split
+    # itself).  So each CTA accumulates ONE 64-wide K block (4 instructions) and the partial tiles are summed by
+    # fp32 reductions in L2 (split-K with cp.reduce.async.bulk / red.global.add.f32, both round-to-nearest).
+    raw = torch.zeros(M, (N + 7) // 8 * 8, device=A.device, dtype=torch.float32)
+    gemm(A3, B3, raw, a_mn_major=a_mn_major, b_mn_major=b_mn_major, M=M, N=N, K=6 * kp,
+         split_k=(6 * kp + 63) // 64)
     return epilogue_f32(raw, D, alpha=alpha, bias=bias, rowmask=rowmask, dropout=dropout, drop_pos=drop_pos,
                         D_pre=D_pre, act=act, aux=aux, aux_op=aux_op, resid=resid, accumulate=accumulate, M=M, N=N)
 
@@ -570,6 +576,18 @@ def cross_entropy(logits32, V, labels, loss_sum, loss_scale, dlogits16=None, gra
                                   float(loss_scale), _ptr(dlogits16),
                                   dlogits16.stride(0) if dlogits16 is not None else 0, float(grad_scale),
                                   stream_ptr()), "fb_cross_entropy")
+
+
+def softmax_topk(logits32, V, k, want_probs=False):
+    """fb_softmax_topk: logits fp32 [P, >= V] -> (probs [P, V] or None, top_p [P, k], top_i [P, k])."""
+    assert logits32.dtype == torch.float32 and logits32.stride(-1) == 1
+    P = logits32.shape[0]
+    probs = torch.empty(P, V, device=logits32.device, dtype=torch.float32) if want_probs else None
+    top_p = torch.empty(P, k, device=logits32.device, dtype=torch.float32)
+    top_i = torch.empty(P, k, device=logits32.device, dtype=torch.int64)
+    check(load().fb_softmax_topk(_ptr(logits32), logits32.stride(0), P, V, k, _ptr(probs), V, _ptr(top_p), _ptr(top_i),
+                                 stream_ptr()), "fb_softmax_topk")
+    return probs, top_p, top_i
 
 
 def dropout_apply(x32, dropout, *, out32=None, accumulate=False, out16=None):

@@ -274,6 +274,41 @@ class FrozenBiLMBase(nn.Module):
             logits = _LogitsFn.apply(self._anchor, self, state, logits)
         return FBMaskedLMOutput(logits=logits)
 
+    @torch.no_grad()
+    def answer_scores(self, input_ids, attention_mask=None, video=None, video_mask=None, *, mask_token_id, topk=1,
+                      candidates=1, return_probs=False):
+        """Inference fast path of the downstream scripts: what videoqa.py:157-170 and mc.py:150-172
+        compute from ``forward()["logits"]`` -- the answer distribution AT THE [MASK] TOKEN -- without materialising
+        the [B, L, n_ans] logits: the head GEMM runs on the [MASK] rows only and softmax + top-k are one kernel.
+
+        candidates = C > 1 (multiple choice): ``input_ids`` / ``attention_mask`` are [B*C, Lt] with the C candidates
+        of a question in consecutive rows, ``video`` / ``video_mask`` are [B, ...]; the visual prefix is projected
+        once per clip and all B*C rows go through the encoder as one batch (mc.py runs C forwards of [B, Lt]).
+
+        Returns dict(top_p [n, k], top_i [n, k], rows [n] (flat index of each [MASK] position in [B*C, Lt]),
+        probs [n, n_ans] when return_probs).  mc.py's score of candidate c is ``probs[:, 0]`` (mc.py:172)."""
+        if not self.fb.n_ans:
+            raise ValueError("answer_scores needs the answer head (n_ans > 0)")
+        eng = self._ensure_engine()
+        dev = self.device
+        input_ids = input_ids.to(dev)
+        Bt, Lt = input_ids.shape
+        use_video = bool(self.features_dim) and video is not None
+        F = video.shape[1] if use_video else 0
+        eng.forward_encoder(video, video_mask, input_ids, attention_mask, False, video_repeat=candidates)
+        pos = torch.nonzero(input_ids.reshape(-1) == mask_token_id).reshape(-1)     # like the reference's boolean index
+        n = int(pos.numel())
+        rows = (pos // Lt) * (F + Lt) + F + pos % Lt
+        rows16 = eng.ws.rows("ans.rows16", n, self.fb.hidden_size, eng.AD)
+        lib.move_rows(eng.cur.o2[1], rows16, idx_in=rows.contiguous())
+        logits, V = eng.head_logits(rows16, n, mlm=False, scratch=True)
+        k = min(int(topk), V)
+        probs, top_p, top_i = lib.softmax_topk(logits, V, k, want_probs=return_probs)
+        out = dict(top_p=top_p, top_i=top_i, rows=pos)
+        if return_probs:
+            out["probs"] = probs
+        return out
+
     def _full_logits(self, eng, state, B, L, mlm, scratch=False):
         if eng.cur is not state:
             raise lib.FbError("the lazily materialised logits of an earlier forward are gone: read out['logits'] "

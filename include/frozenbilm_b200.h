@@ -215,6 +215,11 @@ int fb_colsum_bf16(const void* x, long long ld, int M, int N, float* out, void* 
  * dlogits (bf16, nullable) = (softmax - onehot) * grad_scale. */
 int fb_cross_entropy(const float* logits, long long ld, int P, int V, const long long* labels, float* loss_sum,
                      float loss_scale, void* dlogits_bf16, long long ldd, float grad_scale, void* stream);
+/* Answer scoring at the [MASK] rows: softmax over the answer vocabulary + top-k
+ * (videoqa.py:164-170 logits.softmax(-1) / torch.topk; mc.py:168-172 softmax(-1)[:, 0]).  logits fp32 [P, V] (pitch
+ * ld); probs (nullable) fp32 [P, V] (pitch ldp); top_p fp32 [P, k] descending, top_i int64 [P, k] (ties -> lower id). */
+int fb_softmax_topk(const float* logits, long long ld, int P, int V, int k, float* probs, long long ldp, float* top_p,
+                    long long* top_i, void* stream);
 /* out = dropout(x) as fp32 (optionally accumulating) and/or bf16: relative-embedding dropout, deberta.py:779. */
 int fb_dropout_apply(const float* x, int M, int N, const fb_dropout* drop, float* out_f32, int accumulate,
                      void* out_bf16, void* stream);
@@ -232,12 +237,12 @@ int fb_cast_f32_bf16(const float* x, long long n, void* out, void* stream);
  * model.set_precision("fp32x3"): the parity gate of BASELINE.json configs[0] (north_star: logits within
  * rtol 1e-3 / atol 1e-4 of the fp32 reference), which bf16 tensor-core operands cannot meet.
  * ------------------------------------------------------------------------------------------ */
-/* x fp32 [rows, cols] (pitch ld) -> three bf16 blocks hi = bf16(x), lo = bf16(x - hi) laid out along the GEMM K
- * axis: A side (b_mode = 0): hi | hi | lo,  B side (b_mode = 1): hi | lo | hi, so that fb_gemm over the tripled K
- * accumulates hi.hi + hi.lo + lo.hi in fp32 (3-pass split-bf16 product of nn.Linear / bmm, same call sites as
- * fb_gemm).  along_rows = 0: K = columns, block b starts at column b * block_stride of out [rows, >= 3 block_stride];
- * along_rows = 1: K = rows (MN-major operand), block b starts at row b * block_stride.  Padding must be zeroed by
- * the caller. */
+/* x fp32 [rows, cols] (pitch ld) -> three bf16 pieces p0 = bf16(x), p1 = bf16(x - p0), p2 = bf16(x - p0 - p1) laid
+ * out as SIX blocks along the GEMM K axis: A side (b_mode = 0): p0 p0 p1 p1 p0 p2,  B side (b_mode = 1): p0 p1 p0 p1
+ * p2 p0, so that fb_gemm over the 6x longer K accumulates a0b0 + a0b1 + a1b0 + a1b1 + a0b2 + a2b0 in fp32: every
+ * product above 2^-24 |a||b| (fp32-class nn.Linear / bmm, same call sites as fb_gemm).  along_rows = 0: K = columns,
+ * block t starts at column t * block_stride of out [rows, >= 6 block_stride]; along_rows = 1: K = rows (MN-major
+ * operand), block t starts at row t * block_stride.  Padding must be zeroed by the caller. */
 int fb_split3(const float* x, long long ld, int rows, int cols, int along_rows, int b_mode, long long block_stride,
               void* out_bf16, long long ld_out, void* stream);
 /* fb_gemm's epilogue with every operand in fp32 (same order: alpha, bias, rowmask, dropout pos 1, D_pre, act, aux,

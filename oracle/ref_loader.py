@@ -1,9 +1,9 @@
-"""Load the UNMODIFIED reference model files from /root/reference by path.
+"""Load the UNMODIFIED reference model files by path: from /root/reference (container) or from the byte-identical
+copies baseline/install_ref.py stages under baseline/_ref (git-ignored; travels to the GPU box).
 
-TEST INFRASTRUCTURE ONLY (container-side): used by tests/golden/make_golden.py to
-generate golden vectors and by the CPU test that pins the oracle restatement
-against the real reference.  /root/reference does not exist on the GPU box, so
-nothing on the GPU path may import this module.
+TEST / BENCH INFRASTRUCTURE ONLY: used by tests/golden/*.py to generate golden vectors, by the CPU tests that pin the
+oracle restatement against the real reference, and by bench.py's CPU legs (--impl reference, cpu_baseline) to time the
+reference's own implementation.  The product path (frozenbilm_b200/) never imports this module.
 
 The shims below are version-compat only (transformers 5.5 / torch 2.11 vs the
 reference's pinned transformers 4.17 / torch 1.8.1); none changes arithmetic.
@@ -18,10 +18,27 @@ import types
 import numpy as np
 import torch
 
-REF_ROOT = os.environ.get("FROZENBILM_REFERENCE", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")   # baseline/install_ref.py
+
+
+def _pick_root():
+    for cand in (os.environ.get("FROZENBILM_REFERENCE"), "/root/reference", _STAGED):
+        if cand and os.path.isfile(os.path.join(cand, "model", "deberta.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _pick_root()
 
 
 def reference_available() -> bool:
+    """The reference checkout itself (container) -- what the golden generators need."""
+    return os.path.isfile(os.path.join("/root/reference", "model", "deberta.py")) or \
+        bool(os.environ.get("FROZENBILM_REFERENCE"))
+
+
+def reference_model_files_available() -> bool:
+    """The reference's model files, from the checkout or staged by baseline/install_ref.py (enough to run its path)."""
     return os.path.isfile(os.path.join(REF_ROOT, "model", "deberta.py"))
 
 
