@@ -118,6 +118,8 @@ class ForwardState:
 
 
 class DebertaEngine:
+    LAYER_PREFIX = "deberta.encoder.layer."
+
     def __init__(self, cfg: FBConfig, params: dict, device, precision: str = "bf16"):
         """params: name -> fp32 CUDA tensor (the module's parameters; reference names).
         precision: "bf16" (training path: bf16 tensor-core operands, fp32 accumulation) or "fp32x3" (fp32-class
@@ -141,6 +143,7 @@ class DebertaEngine:
         self.cur = None
         self.saved = None
         self.head_saved = None
+        self._on_grads_ready = None
         self.step_seed = 0x5EED0000
         self.cur_seed = self.step_seed
         if cfg.head_dim != 64:
@@ -157,7 +160,7 @@ class DebertaEngine:
         self.rel_side_stream = self.dw_side_stream and os.environ.get("FB_REL_STREAM", "1") != "0"
         self.rel_side_units = int(os.environ.get("FB_REL_UNITS", "0"))
         self.attn_scale = 1.0 / math.sqrt(3 * 64)             # deberta.py:769-777
-        self.layer_prefix = "deberta.encoder.layer."
+        self.layer_prefix = self.LAYER_PREFIX
         if cfg.hidden_size % 128 != 0:
             raise NotImplementedError("hidden_size must be a multiple of 128")
         self.bucket_of_rel = torch.from_numpy(bucket_of_rel(cfg.position_buckets, cfg.max_position_embeddings)).to(device) \
@@ -529,9 +532,27 @@ class DebertaEngine:
         return loss_sum[0].clone()   # never a view of the reused workspace (a kept loss must not change later)
 
     # ------------------------------------------------------------------ backward
-    def backward(self, gviews, scale=None, dlogits=None, state=None):
+    def pending_forwards(self):
+        """Train-mode forwards whose backward has not run yet."""
+        return self._n_slots - len(self._free_slots)
+
+    def _grads_ready(self, group):
+        """Every gradient of ``group`` (a layer index) has been ISSUED: hands the data-parallel hook one event per
+        stream that contributes to them, so the layer's slice of the flat bucket can be all-reduced while the
+        backward of the earlier layers is still running."""
+        cb = self._on_grads_ready
+        if cb is None:
+            return
+        evs = [torch.cuda.current_stream().record_event()]
+        if self._side is not None:
+            evs.append(self._side.record_event())
+        cb(group, evs)
+
+    def backward(self, gviews, scale=None, dlogits=None, state=None, on_grads_ready=None):
         """Selective backward of ONE forward (``state``; default: the latest): accumulates into ``gviews``
-        (name -> fp32 view of the flat gradient bucket)."""
+        (name -> fp32 view of the flat gradient bucket).  ``on_grads_ready(layer, events)`` is called as soon as the
+        gradients of an encoder layer are complete on the device timeline described by ``events``."""
+        self._on_grads_ready = on_grads_ready
         st = state if state is not None else self.cur
         if st is None or st.sv is None or st.released:
             raise lib.FbError("backward() without a training-mode forward (or its state was already consumed)")
@@ -543,6 +564,7 @@ class DebertaEngine:
             self._backward_impl(scale, dlogits)
         finally:
             self.saved = self.head_saved = None
+            self._on_grads_ready = None
             st.release()
 
     def _backward_impl(self, scale, dlogits):
@@ -611,6 +633,7 @@ class DebertaEngine:
         # ---- enhanced mask decoder passes (reverse): shared K/V projection of h[-2]
         dq32, dkv_b = self._bwd_pass(passes[-1], dy32, emd=True, slot=0)
         dz32, dkv_a = self._bwd_pass(passes[-2], dq32, emd=True, slot=1)
+        self._grads_ready(last)
         dx32 = ws.get("bw.dx32.e", (T, H), F32)
         wkv = W[f"qkv.w.{last}"][H:]
         lib.gemm(dkv_b, wkv, dx32, b_mn_major=True, resid=dz32)
@@ -632,6 +655,7 @@ class DebertaEngine:
                 lib.gemm(dconv16, W["conv.w"], dcol16, b_mn_major=True)
                 dx32 = ds_c
             dx32 = self._bwd_pass(rec, dx32, emd=False, slot=rec["pass_id"] % 2)
+            self._grads_ready(rec["layer"])
         if dcol16 is not None:
             lib.conv_col2im(dcol16, B, L, H, dx32, accumulate=True)
         self._bwd_embeddings(dx32, "deberta.embeddings.", rowmask=self.mask_u8)
@@ -868,11 +892,13 @@ class BertEngine(DebertaEngine):
     blocks without adapters (:281-292, 349-360), MLM head on ``cls.predictions.decoder`` (:74-96).  Same kernels
     as the DeBERTa path: fb_attn_fwd in plain mode (no relative tables), the same GEMM / LayerNorm schedule."""
 
+    LAYER_PREFIX = "bert.encoder.layer."
+
     def __init__(self, cfg, params, device, precision="bf16"):
         super().__init__(cfg, params, device, precision)
         self.use_rel = False
         self.attn_scale = 1.0 / math.sqrt(64)
-        self.layer_prefix = "bert.encoder.layer."
+        self.layer_prefix = self.LAYER_PREFIX
         self.hn = dict(dense_b="cls.predictions.transform.dense.bias", ln_w="cls.predictions.transform.LayerNorm.weight",
                        ln_b="cls.predictions.transform.LayerNorm.bias", bias="cls.predictions.bias")
 
@@ -959,4 +985,5 @@ class BertEngine(DebertaEngine):
         dx32 = dy32
         for rec in reversed(sv["passes"]):
             dx32 = self._bwd_pass(rec, dx32, emd=False, slot=rec["pass_id"] % 2)
+            self._grads_ready(rec["layer"])
         self._bwd_embeddings(dx32, "bert.embeddings.", rowmask=None)

@@ -109,6 +109,10 @@ class FrozenBiLMBase(nn.Module):
         self._flat = None
         self._anchor = None
         self._frozen_sig = None
+        # data-parallel gradient synchronisation inside backward() (the reference has none): on by default
+        # when torch.distributed is initialised with world_size > 1; FB_DP_SYNC=0 / model.dp_sync = False disables it
+        self.dp_sync = os.environ.get("FB_DP_SYNC", "1") != "0"
+        self._dp = None
         # "bf16" (training path) | "fp32x3" (fp32-class instantiation, the configs[0] parity gate)
         self.precision = os.environ.get("FB_PRECISION", "bf16")
 
@@ -150,16 +154,13 @@ class FrozenBiLMBase(nn.Module):
     def _engine_params(self, named):
         return {n: p.data for n, p in named.items()}
 
-    def _ensure_engine(self):
-        dev = self.device
-        if dev.type != "cuda":
-            raise lib.FbError("frozenbilm_b200 has no CPU path: call model.to('cuda') before forward()")
-        named = self._param_dict()
+    def _ensure_flat(self, dev, named=None):
+        """(Re)builds the flat fp32 bucket of the trainable set: parameters become views of it, so that one NCCL
+        all-reduce per contiguous range / one fused Adam kernel covers everything that trains."""
+        named = named if named is not None else self._param_dict()
         train = [(n, p) for n, p in named.items() if p.requires_grad]
         sig = tuple((n, p.data_ptr()) for n, p in train)
         if self._flat is None or self._flat["sig"] != sig or self._flat["flat32"].device != dev:
-            # (re)build the flat fp32 bucket; parameters become views so that one NCCL all-reduce / one
-            # fused Adam kernel covers the whole trainable set
             total = sum(p.numel() for _, p in train)
             total_pad = (total + 7) // 8 * 8
             flat32 = torch.zeros(total_pad, device=dev, dtype=torch.float32)
@@ -174,6 +175,14 @@ class FrozenBiLMBase(nn.Module):
                               grad32=torch.zeros(total_pad, device=dev, dtype=torch.float32), slices=slices,
                               sig=tuple((n, p.data_ptr()) for n, p in train), version=-1, total=total)
             self._engine_obj = None
+        return train
+
+    def _ensure_engine(self):
+        dev = self.device
+        if dev.type != "cuda":
+            raise lib.FbError("frozenbilm_b200 has no CPU path: call model.to('cuda') before forward()")
+        named = self._param_dict()
+        train = self._ensure_flat(dev, named)
         # frozen tensors: version counters of the PARAMETERS (p.data has its own, which load_state_dict never bumps)
         fsig = tuple((n, p._version, p.data_ptr()) for n, p in named.items() if not p.requires_grad)
         if self._engine_obj is None:
@@ -320,6 +329,76 @@ class FrozenBiLMBase(nn.Module):
             eng.head_logits(state.o2[1], T, mlm=(mlm or not self.fb.n_ans), out=out, scratch=scratch)
         return out.view(B, L, n)
 
+    # ------------------------------------------------------------------ data-parallel gradient all-reduce
+    @staticmethod
+    def _dp_world():
+        import torch.distributed as dist
+        return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    def _layer_ranges(self):
+        """flat-bucket range [a, b) of every encoder layer's trainable tensors (contiguous: named_parameters order)
+        and the ranges in front of / behind the layers."""
+        fl = self._flat
+        if "layer_ranges" not in fl:
+            pfx = self.engine_cls.LAYER_PREFIX
+            rng = {}
+            for n, (a, b, _) in fl["slices"].items():
+                if n.startswith(pfx):
+                    i = int(n[len(pfx):].split(".")[0])
+                    lo, hi = rng.get(i, (a, b))
+                    rng[i] = (min(lo, a), max(hi, b))
+            spans = sorted(rng.values())
+            ok = all(spans[k][1] == spans[k + 1][0] for k in range(len(spans) - 1)) if spans else False
+            fl["layer_ranges"] = rng if ok else {}
+            fl["rest_ranges"] = [(0, spans[0][0]), (spans[-1][1], fl["total"])] if ok else [(0, fl["total"])]
+        return fl["layer_ranges"], fl["rest_ranges"]
+
+    def _allreduce_range(self, a, b, async_op):
+        import torch.distributed as dist
+        if b <= a:
+            return None
+        t = self._flat["grad32"][a:b]
+        if dist.get_backend() == "nccl":
+            return dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op)
+        w = dist.all_reduce(t, async_op=False)          # gloo (CPU tests): SUM, then the 1/world factor
+        t.mul_(1.0 / dist.get_world_size())
+        return None
+
+    def _dp_layer_ready(self, layer, events):
+        """Called by the engine as a layer's gradients complete: all-reduce that layer's slice of the flat bucket on a
+        communication stream, overlapped with the backward of the earlier layers."""
+        dp = self._dp
+        rng = dp["layers"].get(layer)
+        if rng is None or layer in dp["done"]:
+            return
+        comm = dp["stream"]
+        if comm is None:                                    # host-logic tests on CPU (gloo): reduce in place
+            w = self._allreduce_range(rng[0], rng[1], async_op=False)
+        else:
+            for ev in events:
+                comm.wait_event(ev)
+            with torch.cuda.stream(comm):
+                w = self._allreduce_range(rng[0], rng[1], async_op=True)
+        dp["done"].add(layer)
+        dp["works"].append(w)
+
+    def _finalize_backward(self):
+        """End of the autograd pass (queued like DistributedDataParallel's finalizer): reduce what the overlapped path
+        did not cover -- everything, when several forwards shared this backward -- and join the communication."""
+        dp, self._dp = self._dp, None
+        if dp is None:
+            return
+        layers, rest = dp["layers"], dp["rest"]
+        todo = list(rest) if dp["done"] else [(0, self._flat["total"])]
+        if dp["done"]:
+            todo += [layers[i] for i in layers if i not in dp["done"]]
+        for w in dp["works"]:
+            if w is not None:
+                w.wait()
+        for a, b in todo:
+            self._allreduce_range(a, b, async_op=False)
+        self._flat["synced"] = True
+
     # ------------------------------------------------------------------ backward bridge
     def _run_backward(self, state, scale=None, dlogits=None):
         eng = self._engine_obj
@@ -334,7 +413,22 @@ class FrozenBiLMBase(nn.Module):
             fl["grad32"].zero_()
         else:
             foreign = {}
-        eng.backward(views, scale=scale, dlogits=dlogits, state=state)
+        hook = None
+        if self.dp_sync and self._dp_world() > 1:
+            if self._dp is None:
+                # first backward node of this autograd pass: the finalizer runs when the whole pass is done
+                layers, rest = self._layer_ranges()
+                self._dp = dict(layers=layers, rest=rest, done=set(), works=[], stream=None)
+                torch.autograd.Variable._execution_engine.queue_callback(self._finalize_backward)
+                # overlap per layer only when this is the ONLY forward feeding this backward pass (several pending
+                # forwards -- mc.py's candidate loop -- accumulate into the same slices until the pass ends)
+                if layers and not foreign and eng.pending_forwards() == 1 and self._flat["grad32"].is_cuda:
+                    if "comm_stream" not in self._flat:
+                        self._flat["comm_stream"] = torch.cuda.Stream(device=self.device)
+                    self._dp["stream"] = self._flat["comm_stream"]
+                    hook = self._dp_layer_ready
+            self._flat["synced"] = False
+        eng.backward(views, scale=scale, dlogits=dlogits, state=state, on_grads_ready=hook)
         for n, p in train:
             if n in foreign:
                 views[n].add_(foreign[n])

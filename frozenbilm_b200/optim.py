@@ -53,7 +53,14 @@ class FusedClipAdam:
     def step(self):
         """all-reduce (if a process group is up) -> global-norm clip -> Adam -> refresh bf16 operand copies."""
         p32, g32, p16 = self._state()
-        scale = allreduce_sum_and_scale(g32)
+        # the module's backward already averaged the gradients over the ranks (overlapped with the backward itself);
+        # only when that is switched off (model.dp_sync = False) is the bucket reduced here
+        fl = self.model._flat
+        if fl.get("synced"):
+            scale = 1.0
+            fl["synced"] = False
+        else:
+            scale = allreduce_sum_and_scale(g32)
         self.step_count += 1
         self.norm_sq.zero_()
         lib.sumsq(g32, self.norm_sq)

@@ -29,7 +29,34 @@ def _worker(rank, world, port, q):
     p = torch.arange(17, dtype=torch.float32) + 100 * rank
     broadcast_flat(p, 0)
     b = synth_batch(CONFIG_TINY, 2, 16, shard_seed(1234, rank, 0))
-    q.put((rank, float(mean[0]), float(mean[-1]), scale, p.tolist(), int(b["input_ids"].sum())))
+    # the module's own data-parallel hook (host logic, on CPU tensors): per-layer ranges of the flat bucket reduced as
+    # the backward reaches them, the rest in the finalizer; result = mean over ranks, identical on every rank
+    from frozenbilm_b200.model import DebertaV2ForMaskedLM
+    cfg = CONFIG_TINY
+    torch.manual_seed(0)
+    m = DebertaV2ForMaskedLM(cfg.to_hf(), max_feats=cfg.max_feats)
+    m._ensure_flat(torch.device("cpu"))
+    layers, rest = m._layer_ranges()
+    fl = m._flat
+    total = fl["total"]
+    gen = torch.Generator().manual_seed(100 + rank)
+    fl["grad32"][:total] = torch.randn(total, generator=gen)
+    local = fl["grad32"][:total].clone()
+    m._dp = dict(layers=layers, rest=rest, done=set(), works=[], stream=None)
+    for i in sorted(layers, reverse=True)[:-1]:          # every layer but layer 0 arrives through the overlap hook
+        m._dp_layer_ready(i, [])
+    m._finalize_backward()
+    covered = sum(b_ - a_ for a_, b_ in layers.values()) + sum(b_ - a_ for a_, b_ in rest)
+    gens = [torch.randn(total, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
+    want = sum(gens) / world
+    ok_overlap = bool(torch.allclose(fl["grad32"][:total], want, atol=1e-6)) and covered == total and fl["synced"]
+    # several forwards -> one backward: nothing through the hook, the finalizer reduces the whole bucket
+    fl["grad32"][:total] = local
+    m._dp = dict(layers=layers, rest=rest, done=set(), works=[], stream=None)
+    m._finalize_backward()
+    ok_whole = bool(torch.allclose(fl["grad32"][:total], want, atol=1e-6))
+    q.put((rank, float(mean[0]), float(mean[-1]), scale, p.tolist(), int(b["input_ids"].sum()), ok_overlap, ok_whole,
+           len(layers), float(fl["grad32"][:total].double().sum())))
     dist.destroy_process_group()
 
 
@@ -45,11 +72,13 @@ def test_flat_bucket_allreduce_broadcast_and_shards():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, m0, m1, scale, plist, ids_sum in res:
+    for rank, m0, m1, scale, plist, ids_sum, ok_overlap, ok_whole, n_layers, gsum in res:
         assert scale == 0.5
         assert m0 == m1 == 1.5           # mean of rank+1 over 2 ranks
         assert plist == list(range(17))   # every rank holds rank 0's parameters after the broadcast
+        assert ok_overlap and ok_whole and n_layers > 0
     assert res[0][5] != res[1][5]         # different data shard per rank
+    assert res[0][9] == res[1][9]         # bit-identical reduced gradients on both ranks
 
 
 def test_single_process_is_a_noop():
