@@ -3,8 +3,8 @@
     python baseline/install_ref.py          # also run by __graft_entry__.build() when /root/reference is present
 
 The reference is pure Python (no FFI, nothing to compile), and /root/reference does not exist on the GPU box.  This
-copies the files of the masked-LM path -- model/deberta.py, model/adapter.py, model/bert.py, util/misc.py -- byte for
-byte into baseline/_ref/ (git-ignored, so never part of the repo's history; NOT gpurun-ignored, so it travels with the
+copies the files of the masked-LM path -- model/{deberta,adapter,bert}.py, util/*.py and the main.py / mc.py loops --
+byte for byte into baseline/_ref/ (git-ignored, so never part of the repo's history; NOT gpurun-ignored, so it travels with the
 snapshot like a built .so).  oracle/ref_loader.py loads them by path under the version shims of SURVEY.md 8(c), which
 lets ``bench.py --impl reference`` and ``cpu_baseline`` time the REAL reference implementation (kind "reference") on
 the box's host cores; without baseline/_ref they fall back to the oracle port (kind "port").
@@ -18,7 +18,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 DEST = os.path.join(HERE, "_ref")   # baseline/_ref: the sanctioned, git-ignored home of the reference install
 SRC = os.environ.get("FROZENBILM_REFERENCE_SRC", "/root/reference")
-FILES = ["model/deberta.py", "model/adapter.py", "model/bert.py", "util/misc.py"]
+FILES = ["model/deberta.py", "model/adapter.py", "model/bert.py", "util/misc.py",
+         # the training / evaluation loops that tests/test_dropin_gpu.py drives UNMODIFIED against this build
+         "main.py", "mc.py", "args.py", "util/__init__.py", "util/dist.py", "util/metrics.py"]
 
 
 def install(src=SRC, dest=DEST, quiet=False):

@@ -513,6 +513,37 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __
     atomicAdd(out, t);
   }
 }
+// Deterministic variant: every CTA writes its partial to scratch[blockIdx.x]; the LAST CTA to finish (ticket counter
+// at scratch[gridDim.x], reset for the next launch) adds them in index order.  Identical gradients therefore give a
+// bit-identical norm on every data-parallel rank, so the clip factor -- and with it every parameter -- stays
+// bit-identical across replicas (float atomics would add the partials in arrival order).
+__global__ void sumsq_det_kernel(const float* __restrict__ g, long long n, float* __restrict__ out,
+                                 float* __restrict__ scratch) {
+  __shared__ float sred[8];
+  __shared__ bool last;
+  float s = 0.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    s += g[i] * g[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sred[w];
+    scratch[blockIdx.x] = t;
+    __threadfence();
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + gridDim.x);
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float t = 0.0f;
+    for (unsigned int b = 0; b < gridDim.x; ++b) t += __ldcg(scratch + b);
+    *out = t;
+    *reinterpret_cast<unsigned int*>(scratch + gridDim.x) = 0u;
+  }
+}
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float bc1,
                             float bc2, const float* __restrict__ gnorm_sq, float max_norm, float grad_scale,
@@ -729,6 +760,15 @@ int fb_sumsq(const float* g, long long n, float* out, void* stream) {
   FB_REQUIRE(g && out && n > 0, "fb_sumsq: bad args");
   const int grid = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 4LL * num_sms()));
   sumsq_kernel<<<grid, 256, 0, ST(stream)>>>(g, n, out);
+  count_launch();
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int fb_sumsq_det(const float* g, long long n, float* out, float* scratch, int scratch_len, void* stream) {
+  FB_REQUIRE(g && out && scratch && n > 0 && scratch_len >= 2, "fb_sumsq_det: bad args");
+  const int grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>((n + 255) / 256, 4LL * num_sms()),
+                                                                   scratch_len - 1));
+  sumsq_det_kernel<<<grid, 256, 0, ST(stream)>>>(g, n, out, scratch);
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -201,6 +201,7 @@ def _load(path, exports) -> C.CDLL:
     lib.fb_cross_entropy.argtypes = [vp, ll, i, i, vp, vp, f, vp, ll, f, vp]
     lib.fb_dropout_apply.argtypes = [vp, i, i, dp, vp, i, vp, vp]
     lib.fb_sumsq.argtypes = [vp, ll, vp, vp]
+    lib.fb_sumsq_det.argtypes = [vp, ll, vp, vp, i, vp]
     lib.fb_adam_step.argtypes = [vp, vp, vp, vp, ll, f, f, f, f, i, vp, f, f, vp, vp]
     lib.fb_cast_f32_bf16.argtypes = [vp, ll, vp, vp]
     lib.fb_build_rel_tables.argtypes = [vp, ll, i, i, vp, i, i, i, vp, vp, vp, vp]
@@ -224,7 +225,7 @@ EXPORTS = [
     "fb_cast_f32_bf16", "fb_attn_bwd_prep", "fb_rel_to_bucket", "fb_attn_bwd", "fb_attn_bwd_rel",
     "fb_mlm_corrupt", "fb_gather_frames", "fb_gemm_cluster_capacity",
     "fb_split3", "fb_epilogue_f32", "fb_colsum_f32", "fb_conv_im2col_f32", "fb_conv_col2im_f32",
-    "fb_cross_entropy_f32", "fb_attn_fwd_f32", "fb_attn_bwd_f32", "fb_softmax_topk",
+    "fb_cross_entropy_f32", "fb_attn_fwd_f32", "fb_attn_bwd_f32", "fb_softmax_topk", "fb_sumsq_det",
 ]
 # include/frozenbilm_b200_debug.h: only in libfrozenbilm_sm100_dbg.so
 DEBUG_EXPORTS = ["fb_umma_probe", "fb_attn_bwd_set_debug"]
@@ -601,6 +602,12 @@ def dropout_apply(x32, dropout, *, out32=None, accumulate=False, out16=None):
 
 def sumsq(g, out):
     check(load().fb_sumsq(_ptr(g), g.numel(), _ptr(out), stream_ptr()), "fb_sumsq")
+
+
+def sumsq_det(g, out, scratch):
+    """Deterministic sum of squares (overwrites out[0]); scratch: fp32 [>= 2], zeroed once by the caller."""
+    check(load().fb_sumsq_det(_ptr(g), g.numel(), _ptr(out), _ptr(scratch), scratch.numel(), stream_ptr()),
+          "fb_sumsq_det")
 
 
 def adam_step(p, g, m, v, *, lr, beta1, beta2, eps, step, gnorm_sq=None, max_norm=0.0, grad_scale=1.0, p16=None):

@@ -112,6 +112,11 @@ class FrozenBiLMBase(nn.Module):
         # data-parallel gradient synchronisation inside backward() (the reference has none): on by default
         # when torch.distributed is initialised with world_size > 1; FB_DP_SYNC=0 / model.dp_sync = False disables it
         self.dp_sync = os.environ.get("FB_DP_SYNC", "1") != "0"
+        # FB_DP_OVERLAP=1: all-reduce every layer's slice as soon as its gradients are complete, on a communication
+        # stream.  Measured on 2xB200 (profiles/r2_dp_overlap.md): 72.4 ms/step vs 71.9 ms with ONE all-reduce at the end
+        # of the backward -- the NCCL kernels take SMs away from the persistent one-CTA-per-SM GEMM / attention kernels,
+        # which costs more than the 0.5 ms the single collective leaves exposed.  Off by default.
+        self.dp_overlap = os.environ.get("FB_DP_OVERLAP", "0") == "1"
         self._dp = None
         # "bf16" (training path) | "fp32x3" (fp32-class instantiation, the configs[0] parity gate)
         self.precision = os.environ.get("FB_PRECISION", "bf16")
@@ -422,7 +427,8 @@ class FrozenBiLMBase(nn.Module):
                 torch.autograd.Variable._execution_engine.queue_callback(self._finalize_backward)
                 # overlap per layer only when this is the ONLY forward feeding this backward pass (several pending
                 # forwards -- mc.py's candidate loop -- accumulate into the same slices until the pass ends)
-                if layers and not foreign and eng.pending_forwards() == 1 and self._flat["grad32"].is_cuda:
+                if self.dp_overlap and layers and not foreign and eng.pending_forwards() == 1 and \
+                        self._flat["grad32"].is_cuda:
                     if "comm_stream" not in self._flat:
                         self._flat["comm_stream"] = torch.cuda.Stream(device=self.device)
                     self._dp["stream"] = self._flat["comm_stream"]

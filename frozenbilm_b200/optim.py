@@ -44,6 +44,7 @@ class FusedClipAdam:
             self.m = torch.zeros_like(p32)
             self.v = torch.zeros_like(p32)
             self.norm_sq = torch.zeros(1, device=p32.device)
+            self.norm_scratch = torch.zeros(1025, device=p32.device)   # partials + ticket of fb_sumsq_det
         return p32, g32, p16
 
     def zero_grad(self):
@@ -62,8 +63,8 @@ class FusedClipAdam:
         else:
             scale = allreduce_sum_and_scale(g32)
         self.step_count += 1
-        self.norm_sq.zero_()
-        lib.sumsq(g32, self.norm_sq)
+        # fixed summation order: identical (all-reduced) gradients give a bit-identical clip factor on every rank
+        lib.sumsq_det(g32, self.norm_sq, self.norm_scratch)
         lib.adam_step(p32, g32, self.m, self.v, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
                       step=self.step_count, gnorm_sq=self.norm_sq, max_norm=self.max_norm, grad_scale=scale, p16=p16)
         self.model._mark_trainable_fresh()

@@ -225,6 +225,10 @@ int fb_dropout_apply(const float* x, int M, int N, const fb_dropout* drop, float
                      void* out_bf16, void* stream);
 /* clip_grad_norm_ + Adam over a flat fp32 bucket (main.py:82-84, args.py:246-275), refreshing the bf16 copy. */
 int fb_sumsq(const float* g, long long n, float* out, void* stream);
+/* Same sum of squares, OVERWRITING *out, with a fixed summation order (bit-identical on every data-parallel rank for
+ * identical gradients).  scratch: fp32 [scratch_len >= 2], zero-initialised ONCE by the caller and then owned by this
+ * function (per-CTA partials + a ticket counter that the kernel resets itself). */
+int fb_sumsq_det(const float* g, long long n, float* out, float* scratch, int scratch_len, void* stream);
 int fb_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                  float eps, int step, const float* gnorm_sq, float max_norm, float grad_scale, void* p_bf16,
                  void* stream);
