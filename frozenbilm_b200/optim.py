@@ -77,4 +77,7 @@ def broadcast_trainable(model, src=0):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         p32, _, _ = model.flat_buffers()
         broadcast_flat(p32, src)
+        # a c10d collective writes the tensor without bumping its autograd version counter: force the refresh of the
+        # bf16 operand copies of the trainable tensors (ranks other than ``src`` would keep computing with their own)
+        model._flat["version"] = -1
         model._ensure_engine()
