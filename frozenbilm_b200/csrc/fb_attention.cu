@@ -17,6 +17,7 @@
 // bf16 operands that produced them) because the skew needs a per-lane column shift that TMEM
 // loads cannot express; scores, softmax statistics and the output accumulate in fp32.
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/frozenbilm_b200.h"
@@ -480,6 +481,473 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
   }
 }
 
+// =============================================================================================
+// Forward, second generation (default; FB_ATTN_FWD=1 selects the kernel above).
+//
+// The first kernel regroups the two positional terms through fp16 staging buffers that the softmax threads then
+// READ BACK and add to S (per 128 x 128 block and row: 352 two-byte scatter stores with 2-way bank conflicts, 32
+// 16-byte loads, ~190 ALU instructions).  Here the staging buffers are MMA OPERANDS and the tensor core does the
+// regrouped addition itself:
+//
+//   Wc[a][k] = X1[a][a + 127 - k]        (thread = query row a stores its own row, k = key index inside the block)
+//   Wp[b][x] = X2[b][x - b + 127]        (thread = key row b stores its own row, x = query index inside the tile)
+//   S += Wc . I            8 x tcgen05.mma 128x16x16, A = Wc K-major   (adds the c2p term,  Q_a . PK[a - b])
+//   S += Wp^T . I          8 x tcgen05.mma 128x16x16, A = Wp MN-major  (adds the p2c term,  K_b . PQ[a - b], transposed
+//                                                                       by the operand view: no transposition in smem)
+//
+// with I the 16 x 16 identity (the trick fb_attn_bwd uses to transpose dS').  Wc / Wp are dense 128 x 128 fp16
+// matrices in the SWIZZLE_NONE core-matrix layout with LB = 128 (column groups) and SB = 2080 (row groups): for every
+// store instruction the 32 lanes write (row r0 + lane, column x0 + lane), and with these strides the 32 two-byte
+// stores fall into 32 different banks (simulated for every (warp, x0): 1.0 wavefronts; the dense SB = 2048 gives
+// 3.4, a 128B-swizzled tile 1.8).  Per row and block that leaves 256 conflict-free stores, no loads, no adds; the 16
+// extra MMAs cost ~0.8 K tensor-pipe cycles of the ~2.7 K the block needs, on a pipe that was idle 90 % of the time.
+// fp16 operands x 1.0 with fp32 accumulation: the positional terms reach S with the same precision as before.
+// =============================================================================================
+static constexpr uint32_t W_LB = 128, W_SB = 2080, W_BYTES = 15 * W_SB + 16 * W_LB;   // 33248 B per staging matrix
+static constexpr uint32_t F2_OFF_WC = OFF_T1, F2_OFF_WP = F2_OFF_WC + 33280, F2_OFF_KMASK = F2_OFF_WP + 33280,
+                          F2_OFF_I16 = F2_OFF_KMASK + 128, F2_OFF_BARS = F2_OFF_I16 + 512,
+                          AT2_SMEM = F2_OFF_BARS + 256 + 1024;
+static_assert(W_BYTES <= 33280 && AT2_SMEM <= 232448, "shared memory budget (forward, generation 2)");
+
+// this thread's row r of a staging matrix: 8 byte offsets for the column residues, then +-128 bytes per 8 columns
+__device__ __forceinline__ uint32_t w_row_base(int r) { return (uint32_t)(r >> 3) * W_SB + (uint32_t)(r & 7) * 16; }
+__device__ __forceinline__ int w_col_off(int x) { return (x >> 3) * (int)W_LB + (x & 7) * 2; }   // x may be < 0 (masked)
+
+// X2 chunk (32 TMEM columns of key row b): element e -> column x = x_first + e.   MODE as in stage_p2c.
+template <int MODE>
+__device__ __forceinline__ void stage_wp(uint8_t* row, const int (&off)[8], int m0, const uint32_t (&v)[32], int thr) {
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    if (MODE == 1 || (MODE == 0 && e >= thr) || (MODE == 2 && e < thr))
+      *reinterpret_cast<__half*>(row + off[e & 7] + (m0 + (e >> 3)) * (int)W_LB) = __float2half_rn(__uint_as_float(v[e]));
+  }
+}
+// X1 chunk (32 TMEM columns of query row a): element e -> column k = k_first - e.
+template <int MODE>
+__device__ __forceinline__ void stage_wc(uint8_t* row, const int (&off)[8], int m0, const uint32_t (&v)[32], int thr) {
+#pragma unroll
+  for (int e = 0; e < 32; ++e) {
+    if (MODE == 1 || (MODE == 0 && e >= thr) || (MODE == 2 && e < thr))
+      *reinterpret_cast<__half*>(row + off[e & 7] - (m0 + (e >> 3)) * (int)W_LB) = __float2half_rn(__uint_as_float(v[e]));
+  }
+}
+
+template <bool REL>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                 const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_pk,
+                 const __grid_constant__ CUtensorMap map_pq, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F2_OFF_BARS);
+  uint64_t* bar_q = bars + 0;
+  uint64_t* bar_k = bars + 1;        // TMA: K block + PQ band (operands of S and X2)
+  uint64_t* bar_v = bars + 2;
+  uint64_t* bar_mma1 = bars + 3;     // S (content term), X2 complete
+  uint64_t* bar_xfree = bars + 4;    // X2 is out of TMEM and Wp is staged (all 8 warps)
+  uint64_t* bar_mma2 = bars + 5;     // X1 complete
+  uint64_t* bar_pready = bars + 6;   // [2], one per softmax warpgroup
+  uint64_t* bar_mma3 = bars + 8;     // [2]
+  uint64_t* bar_pk = bars + 10;      // TMA: PK band (operand of X1)
+  uint64_t* bar_sfree = bars + 11;   // S consumed by all 8 warps (and the staging matrices are free)
+  uint64_t* bar_cready = bars + 12;  // X1 is out of TMEM and Wc is staged (all 8 warps)
+  uint64_t* bar_mmas = bars + 13;    // S final: both positional terms added
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint8_t* wc = smem + F2_OFF_WC;
+  uint8_t* wp = smem + F2_OFF_WP;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * 128, hh = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+    tma_prefetch_desc(&map_pk); tma_prefetch_desc(&map_pq);
+    mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1);
+    mbar_init(bar_mma1, 1); mbar_init(bar_xfree, 8); mbar_init(bar_mma2, 1);
+    mbar_init(&bar_pready[0], 4); mbar_init(&bar_pready[1], 4);
+    mbar_init(&bar_mma3[0], 1); mbar_init(&bar_mma3[1], 1);
+    mbar_init(bar_pk, 1); mbar_init(bar_sfree, 8); mbar_init(bar_cready, 8); mbar_init(bar_mmas, 1);
+    fence_barrier_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (REL && threadIdx.x < 256) {
+    // I16[n][k] (fp16) as a K-major SWIZZLE_NONE B operand: core matrices (n >> 3, k >> 3), LBO (K) = 128, SBO (N) = 256
+    const int n = threadIdx.x >> 4, k = threadIdx.x & 15;
+    *reinterpret_cast<uint16_t*>(smem + F2_OFF_I16 + (n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2) =
+        (n == k) ? static_cast<uint16_t>(0x3C00) : static_cast<uint16_t>(0);
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AT_REGS_CONTROL));
+    if (warp == 8 && elect_one_sync()) {
+      // ======================= TMA + MMA control thread =======================
+      constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_band = make_idesc_bf16(128, 256, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
+      constexpr uint32_t idesc_addc = make_idesc_f16(128, 16, 0, 0);   // S[:, 16j..] += Wc[:, 16j..] . I
+      constexpr uint32_t idesc_addp = make_idesc_f16(128, 16, 1, 0);   // S[:, 16j..] += Wp[16j.., :]^T . I
+      const uint32_t sQ = smem_u32(smem + OFF_Q), sK = smem_u32(smem + OFF_K), sV = smem_u32(smem + OFF_V),
+                     sPK = smem_u32(smem + OFF_PK), sPQ = smem_u32(smem + OFF_PQ), sP = smem_u32(smem + OFF_P),
+                     sWc = smem_u32(wc), sWp = smem_u32(wp);
+      const uint64_t idb = make_smem_desc_none(smem_u32(smem + F2_OFF_I16), 128, 256);
+      auto load_k = [&](int kb) {
+        const int j0 = kb * 128;
+        mbar_arrive_expect_tx(bar_k, REL ? 16384 + 32768 : 16384);
+        tma_load_4d(smem + OFF_K, &map_k, bar_k, 0, hh, j0, b);
+        if constexpr (REL) tma_load_3d(smem + OFF_PQ, &map_pq, bar_k, 0, i0 - j0 - 127 + p.rel_off, hh);
+      };
+      auto load_pk = [&](int kb) {
+        if constexpr (REL) {
+          mbar_arrive_expect_tx(bar_pk, 32768);
+          tma_load_3d(smem + OFF_PK, &map_pk, bar_pk, 0, i0 - kb * 128 - 127 + p.rel_off, hh);
+        }
+      };
+      auto load_v = [&](int kb) {
+        mbar_arrive_expect_tx(bar_v, 16384);
+        tma_load_4d(smem + OFF_V, &map_v, bar_v, 0, hh, kb * 128, b);
+      };
+      auto issue_mma1 = [&]() {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + TM_S, make_smem_desc_sw128(sQ + k * 32, 16, 1024),
+                    make_smem_desc_sw128(sK + k * 32, 16, 1024), idesc_qk, k > 0);
+        if constexpr (REL) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + TM_X, make_smem_desc_sw128(sK + k * 32, 16, 1024),
+                      make_smem_desc_sw128(sPQ + k * 32, 16, 1024), idesc_band, k > 0);
+        }
+        umma_commit(bar_mma1);
+      };
+      mbar_arrive_expect_tx(bar_q, 16384);
+      tma_load_4d(smem + OFF_Q, &map_q, bar_q, 0, hh, i0, b);
+      load_k(0);
+      load_pk(0);
+      load_v(0);
+      mbar_wait(bar_q, 0);
+      mbar_wait(bar_k, 0);
+      tc_fence_after();
+      issue_mma1();
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        const uint32_t ph = kb & 1;
+        const bool has_next = kb + 1 < p.nkb;
+        mbar_wait(bar_mma1, ph);      // S / X2 of this block are complete: the K and PQ tiles are free
+        if (has_next) load_k(kb + 1);
+        if (kb > 0) {
+          mbar_wait(&bar_mma3[0], (kb - 1) & 1);
+          mbar_wait(&bar_mma3[1], (kb - 1) & 1);
+          load_v(kb);
+        }
+        if constexpr (REL) {
+          mbar_wait(bar_pk, ph);
+          mbar_wait(bar_xfree, ph);   // X2 is out of TMEM (its columns take X1) and Wp is staged
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + TM_X, make_smem_desc_sw128(sQ + k * 32, 16, 1024),
+                      make_smem_desc_sw128(sPK + k * 32, 16, 1024), idesc_band, k > 0);
+          umma_commit(bar_mma2);
+          // p2c term: S[a][16 j + n] += sum_{b in 16 j ..} Wp[b][a] I[b - 16 j][n]   (A = Wp^T: MN-major view, K = key rows)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            umma_bf16(tmem + TM_S + 16 * j, make_smem_desc_none(sWp + j * 2 * W_SB, W_SB, W_LB), idb, idesc_addp, 1u);
+          if (has_next) {
+            mbar_wait(bar_mma2, ph);  // the PK tile is free
+            load_pk(kb + 1);
+          }
+          mbar_wait(bar_cready, ph);  // X1 is out of TMEM and Wc is staged
+          tc_fence_after();
+          // c2p term: S[a][16 j + n] += sum_{k in 16 j ..} Wc[a][k] I[k - 16 j][n]
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            umma_bf16(tmem + TM_S + 16 * j, make_smem_desc_none(sWc + j * 2 * W_LB, W_LB, W_SB), idb, idesc_addc, 1u);
+          umma_commit(bar_mmas);
+        }
+        if (has_next) {
+          // next block's S / X2 as soon as every warp has pulled this block's S out of TMEM
+          mbar_wait(bar_sfree, ph);
+          mbar_wait(bar_k, (kb + 1) & 1);
+          tc_fence_after();
+          issue_mma1();
+        }
+        mbar_wait(bar_v, ph);
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&bar_pready[g], ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + TM_O + 64 * g, make_smem_desc_sw128(sP + g * 16384 + k * 32, 16, 1024),
+                      make_smem_desc_sw128(sV + (4 * g + k) * 2048, 16, 1024), idesc_pv, k > 0);
+          umma_commit(&bar_mma3[g]);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============ softmax warpgroups: thread = tile row, warpgroup g = key columns [64g, 64g+64) ============
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AT_REGS_SOFTMAX));
+    const int g = warp >> 2, wq = warp & 3;
+    const int a = wq * 32 + lane;        // row in tile == TMEM lane
+    const int i = i0 + a;
+    const bool valid_q = (i < p.L) && (!p.mask_queries || p.mask[(long long)b * p.L + i] != 0);
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>(wq * 32) << 16);
+    const uint32_t rowid = static_cast<uint32_t>((b * p.h + hh) * p.L + i);
+    const bool do_drop = p.drop_thresh16 != 0;
+    const uint32_t rowkey = drop_row_key_raw(rowid, p.seed_lo, p.seed_hi, p.off_lo, p.off_hi);
+    float m_run = -INFINITY, l_run = 0.0f, alpha_pend = 1.0f;
+    float o[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) o[k] = 0.0f;
+    auto accumulate_o = [&](int kb) {
+      mbar_wait(&bar_mma3[g], kb & 1);
+      tc_fence_after();
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(lane_base + TM_O + 64 * g, va);
+      tmem_ld_32x32(lane_base + TM_O + 64 * g + 32, vb);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        o[e] = fmaf(o[e], alpha_pend, __uint_as_float(va[e]));
+        o[32 + e] = fmaf(o[32 + e], alpha_pend, __uint_as_float(vb[e]));
+      }
+      tc_fence_before();
+    };
+    // staging addresses of this thread's row (the same row index a in Wp -- as a key -- and in Wc -- as a query)
+    uint8_t* wp_row = wp + w_row_base(a);
+    uint8_t* wc_row = wc + w_row_base(a);
+    int offp[8], offc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      offp[r] = w_col_off(lane - 31 + r);          // Wp column of (chunk 0, element r): x = lane - 31 + 32 q + e
+      offc[r] = w_col_off(lane + 127 - r);         // Wc column of (chunk 0, element r): k = lane + 127 - 32 q - e
+    }
+
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const uint32_t ph = kb & 1;
+      const int j0 = kb * 128;
+      mbar_wait(bar_mma1, ph);
+      tc_fence_after();
+      // key-validity bits of the two 32-key chunks this warp will score (each warp computes its own: no shared
+      // memory, no block-level barrier)
+      uint32_t kbits2[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int j = j0 + 64 * g + 32 * q + lane;
+        const bool ok = (j < p.L) && (p.mask[(long long)b * p.L + j] != 0);
+        kbits2[q] = __ballot_sync(0xffffffffu, ok);
+      }
+      // ---- p2c: lane = KEY row a of X2.  Its 128 values for the queries x = 0..127 sit at band columns 127 - a + x:
+      //      the warp loads the 160-column window starting at 96 - 32 wq, chunk q / element e is query
+      //      x = lane - 31 + 32 q + e (chunk 0 valid for e >= 31 - lane, chunks 1-3 for every lane, chunk 4 for
+      //      e < 31 - lane); warpgroup 0 takes chunks 0-2, warpgroup 1 chunks 3-4.
+      if constexpr (REL) {
+        uint32_t va[32], vb[32];
+        const uint32_t xbase = lane_base + TM_X + (96 - 32 * wq);
+        const int thr = 31 - lane;
+        if (g == 0) {
+          tmem_ld_32x32(xbase, va);
+          tmem_ld_wait();
+          tmem_ld_32x32(xbase + 32, vb);
+          stage_wp<0>(wp_row, offp, 0, va, thr);
+          tmem_ld_wait();
+          tmem_ld_32x32(xbase + 64, va);
+          stage_wp<1>(wp_row, offp, 4, vb, thr);
+          tmem_ld_wait();
+          stage_wp<1>(wp_row, offp, 8, va, thr);
+        } else {
+          tmem_ld_32x32(xbase + 96, va);
+          tmem_ld_wait();
+          tmem_ld_32x32(xbase + 128, vb);
+          stage_wp<1>(wp_row, offp, 12, va, thr);
+          tmem_ld_wait();
+          stage_wp<2>(wp_row, offp, 16, vb, thr);
+        }
+        fence_proxy_async_smem();    // generic-proxy stores -> visible to the tensor core (async proxy)
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_xfree);
+      if (kb > 0) accumulate_o(kb - 1);
+      if constexpr (REL) {
+        mbar_wait(bar_mma2, ph);
+        tc_fence_after();
+        // ---- c2p: lane = QUERY row a of X1.  Key k of this block sits at band column a + 127 - k: the warp loads the
+        //      160-column window starting at 32 wq, chunk q / element e is key k = lane + 127 - 32 q - e (chunk 0
+        //      valid for e >= lane, chunks 1-3 for every lane, chunk 4 for e < lane).
+        uint32_t va[32], vb[32];
+        const uint32_t xbase = lane_base + TM_X + 32 * wq;
+        if (g == 0) {
+          tmem_ld_32x32(xbase, va);
+          tmem_ld_wait();
+          tmem_ld_32x32(xbase + 32, vb);
+          stage_wc<0>(wc_row, offc, 0, va, lane);
+          tmem_ld_wait();
+          tmem_ld_32x32(xbase + 64, va);
+          stage_wc<1>(wc_row, offc, 4, vb, lane);
+          tmem_ld_wait();
+          stage_wc<1>(wc_row, offc, 8, va, lane);
+        } else {
+          tmem_ld_32x32(xbase + 96, va);
+          tmem_ld_wait();
+          tmem_ld_32x32(xbase + 128, vb);
+          stage_wc<1>(wc_row, offc, 12, va, lane);
+          tmem_ld_wait();
+          stage_wc<2>(wc_row, offc, 16, vb, lane);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_cready);
+        mbar_wait(bar_mmas, ph);     // both positional terms have been added to S by the tensor core
+        tc_fence_after();
+      }
+      // ---- this warpgroup's 64 final scores of the row
+      uint32_t sv[2][32];
+      tmem_ld_32x32(lane_base + TM_S + 64 * g, sv[0]);
+      tmem_ld_32x32(lane_base + TM_S + 64 * g + 32, sv[1]);
+      tmem_ld_wait();
+      // ---- pass A: scale, mask, row max over this warpgroup's 64 keys
+      float mblk = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        uint32_t (&v)[32] = sv[q];
+        const uint32_t kbits = valid_q ? kbits2[q] : 0u;
+        if (kbits == 0xffffffffu) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float sc = __uint_as_float(v[e]) * p.scale_log2;
+            mblk = fmaxf(mblk, sc);
+            v[e] = __float_as_uint(sc);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float sc = ((kbits >> e) & 1u) ? __uint_as_float(v[e]) * p.scale_log2 : -INFINITY;
+            mblk = fmaxf(mblk, sc);
+            v[e] = __float_as_uint(sc);
+          }
+        }
+      }
+      if (p.s_out != nullptr) {
+        // Saved scores for the backward (fp16, see the first kernel): the warp transposes its 32 rows x 128 bytes
+        // through a private 4 KB slice of the Wp staging matrix (free: the tensor core has finished reading it, the
+        // next block's staging starts only after bar_sfree) and writes four complete lines per instruction.
+        uint8_t* xb = wp + warp * 4096;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __half2 h2 = __floats2half2_rn(__uint_as_float(sv[q][8 * u + 2 * e]), __uint_as_float(sv[q][8 * u + 2 * e + 1]));
+              w[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(xb + lane * 128 + (((4 * q + u) ^ (lane & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+        __syncwarp();
+        const int rr = lane >> 3, uu = lane & 7;
+        __half* gbase = p.s_out + (((long long)b * p.h + hh) * p.L + i0 + 32 * wq) * p.lp + j0 + 64 * g + 8 * uu;
+#pragma unroll
+        for (int st = 0; st < 8; ++st) {
+          const int r = 4 * st + rr;
+          const uint4 x = *reinterpret_cast<const uint4*>(xb + r * 128 + ((uu ^ (r & 7)) << 4));
+          if (i0 + 32 * wq + r < p.L) *reinterpret_cast<uint4*>(gbase + (long long)r * p.lp) = x;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sfree);
+      const float m_new = fmaxf(m_run, mblk);
+      const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
+      const float alpha = ex2_approx(m_run - m_use);   // ex2(-inf) = +0
+      // ---- pass B: probabilities -> bf16 A-operand chunk g (128B-swizzled, K-major), partial row sum
+      float rsum = 0.0f;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c0 = 64 * g + 32 * q;
+        float pr[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          pr[e] = ex2_approx(__uint_as_float(sv[q][e]) - m_use);   // ex2(-inf) = +0
+          rsum += pr[e];
+        }
+        if (do_drop) {
+#pragma unroll
+          for (int gg = 0; gg < 4; ++gg) {
+            float f[8];
+            drop_factors8(rowkey, static_cast<uint32_t>(j0 + c0 + 8 * gg) >> 3, p.drop_thresh16, p.inv_keep, f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pr[8 * gg + e] *= f[e];
+          }
+        }
+        uint8_t* prow = smem + OFF_P + g * 16384 + a * 128;
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+          const uint4 pk = make_uint4(pack_bf16(pr[8 * gg], pr[8 * gg + 1]), pack_bf16(pr[8 * gg + 2], pr[8 * gg + 3]),
+                                      pack_bf16(pr[8 * gg + 4], pr[8 * gg + 5]), pack_bf16(pr[8 * gg + 6], pr[8 * gg + 7]));
+          const int unit = (q * 4 + gg) ^ (a & 7);
+          *reinterpret_cast<uint4*>(prow + unit * 16) = pk;
+        }
+      }
+      l_run = l_run * alpha + rsum;
+      m_run = m_new;
+      alpha_pend = alpha;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_pready[g]);
+    }
+    accumulate_o(p.nkb - 1);
+    // ---- merge the two key halves through shared memory (the staging matrices are free), then write ctx / LSE
+    named_bar_sync(1, 256);
+    float* xch = reinterpret_cast<float*>(wc);   // [128][66] floats = 33.8 KB <= the two staging matrices (66.5 KB)
+    if (g == 1) {
+      float* dstx = xch + a * 66;
+      dstx[0] = m_run; dstx[1] = l_run;
+#pragma unroll
+      for (int k = 0; k < 64; ++k) dstx[2 + k] = o[k];
+    }
+    named_bar_sync(1, 256);
+    if (g == 0 && i < p.L) {
+      const float* srcx = xch + a * 66;
+      const float m1 = srcx[0], l1 = srcx[1];
+      const float m_all = fmaxf(m_run, m1);
+      const float m_use = (m_all == -INFINITY) ? 0.0f : m_all;
+      const float a0 = exp2f(m_run - m_use), a1 = exp2f(m1 - m_use);
+      const float l_all = l_run * a0 + l1 * a1;
+      const float inv_l = (l_all > 0.0f) ? 1.0f / l_all : 0.0f;
+      __nv_bfloat16* dst = p.ctx + ((long long)b * p.L + i) * p.ldc + hh * 64;
+#pragma unroll
+      for (int gg = 0; gg < 8; ++gg) {
+        float r[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r[e] = (o[8 * gg + e] * a0 + srcx[2 + 8 * gg + e] * a1) * inv_l;
+        reinterpret_cast<uint4*>(dst)[gg] = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]),
+                                                        pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
+      }
+      p.lse[((long long)b * p.h + hh) * p.L + i] = (l_all > 0.0f) ? (m_all + log2f(l_all)) : INFINITY;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // Expand the per-bucket positional projections into per-relative-position tables:
 //   out[t][hh][row][0..63] = PQK[bucket_of_rel[row - rel_off + 511]][t * H + hh * 64 + ...]
 // where PQK = Linear_{q|k}(dropout(LayerNorm(rel_embeddings)))  [2S, 2H]  (deberta.py:847-853).
@@ -681,13 +1149,23 @@ int attn_fwd(const fb_attn_args* a, cudaStream_t st) {
   p.seed_lo = (uint32_t)a->seed; p.seed_hi = (uint32_t)(a->seed >> 32);
   p.off_lo = (uint32_t)a->offset; p.off_hi = (uint32_t)(a->offset >> 32);
   static bool configured = false;
+  static int generation = 2;   // FB_ATTN_FWD=1: the first-generation kernel (positional terms combined by the threads)
   if (!configured) {
     FB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     FB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    FB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
+    FB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
+    const char* e = getenv("FB_ATTN_FWD");
+    if (e != nullptr && atoi(e) == 1) generation = 1;
     configured = true;
   }
   dim3 grid(lpad / 128, a->h, a->B);
-  if (rel)
+  if (generation == 2) {
+    if (rel)
+      attn_fwd2_kernel<true><<<grid, AT_THREADS, AT2_SMEM, st>>>(mq, mk, mv, mpk, mpq, p);
+    else
+      attn_fwd2_kernel<false><<<grid, AT_THREADS, AT2_SMEM, st>>>(mq, mk, mv, mpk, mpq, p);
+  } else if (rel)
     attn_fwd_kernel<true><<<grid, AT_THREADS, AT_SMEM, st>>>(mq, mk, mv, mpk, mpq, p);
   else
     attn_fwd_kernel<false><<<grid, AT_THREADS, AT_SMEM, st>>>(mq, mk, mv, mpk, mpq, p);

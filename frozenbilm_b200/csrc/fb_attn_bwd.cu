@@ -70,15 +70,6 @@ static_assert(ZRel::BYTES >= ZRel::PRE + 15 * ZRel::SP + 32 * ZRel::LBO, "Z buff
 static_assert(ZFused::SP * 4 >= 125 * ZFused::LBO && ZRel::SP * 4 >= 125 * ZRel::LBO, "row-group windows overlap");
 static constexpr uint32_t Z_LBO = ZFused::LBO, Z_SBO = ZFused::SBO, Z_BYTES = ZFused::BYTES;   // fb_attn_bwd
 
-__device__ __forceinline__ uint64_t make_smem_desc_none(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  return d;   // layout type 0 = SWIZZLE_NONE
-}
-
 // Z1 rows are queries: this thread owns row a and W of its values, keys b = j_first + e (j_first % 8 == 0).
 // Window position of key b: y = b + 7 - rho.
 template <int W, class ZL = ZFused>
