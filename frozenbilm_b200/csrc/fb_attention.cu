@@ -509,26 +509,26 @@ static constexpr uint32_t F2_OFF_WC = OFF_T1, F2_OFF_WP = F2_OFF_WC + 33280, F2_
                           AT2_SMEM = F2_OFF_BARS + 256 + 1024;
 static_assert(W_BYTES <= 33280 && AT2_SMEM <= 232448, "shared memory budget (forward, generation 2)");
 
-// this thread's row r of a staging matrix: 8 byte offsets for the column residues, then +-128 bytes per 8 columns
+// Staging stores: 32-bit shared-space addresses (8 per thread, one per column residue, computed ONCE before the key
+// loop) + an immediate, so that every element is a single STS.U16 [R + imm].
+__device__ __forceinline__ void sts16(uint32_t addr, float v) {
+  const __half hv = __float2half_rn(v);
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const unsigned short*>(&hv)) : "memory");
+}
 __device__ __forceinline__ uint32_t w_row_base(int r) { return (uint32_t)(r >> 3) * W_SB + (uint32_t)(r & 7) * 16; }
 __device__ __forceinline__ int w_col_off(int x) { return (x >> 3) * (int)W_LB + (x & 7) * 2; }   // x may be < 0 (masked)
 
-// X2 chunk (32 TMEM columns of key row b): element e -> column x = x_first + e.   MODE as in stage_p2c.
-template <int MODE>
-__device__ __forceinline__ void stage_wp(uint8_t* row, const int (&off)[8], int m0, const uint32_t (&v)[32], int thr) {
+// NC consecutive TMEM columns of this thread's row, first element index e0 inside its 32-column chunk (for the
+// validity threshold); element e -> staging column (first + e) for DIR = +1 (Wp), (first - e) for DIR = -1 (Wc), where
+// `adr[r]` is the address of column (first +- r) and every further 8 columns are +-W_LB bytes away.
+//   MODE 0: elements with (e0 + e) >= thr   MODE 1: every element   MODE 2: elements with (e0 + e) < thr
+template <int MODE, int DIR, int NC>
+__device__ __forceinline__ void stage_w(const uint32_t (&adr)[8], int unit0, const uint32_t* v, int e0, int thr) {
 #pragma unroll
-  for (int e = 0; e < 32; ++e) {
-    if (MODE == 1 || (MODE == 0 && e >= thr) || (MODE == 2 && e < thr))
-      *reinterpret_cast<__half*>(row + off[e & 7] + (m0 + (e >> 3)) * (int)W_LB) = __float2half_rn(__uint_as_float(v[e]));
-  }
-}
-// X1 chunk (32 TMEM columns of query row a): element e -> column k = k_first - e.
-template <int MODE>
-__device__ __forceinline__ void stage_wc(uint8_t* row, const int (&off)[8], int m0, const uint32_t (&v)[32], int thr) {
-#pragma unroll
-  for (int e = 0; e < 32; ++e) {
-    if (MODE == 1 || (MODE == 0 && e >= thr) || (MODE == 2 && e < thr))
-      *reinterpret_cast<__half*>(row + off[e & 7] - (m0 + (e >> 3)) * (int)W_LB) = __float2half_rn(__uint_as_float(v[e]));
+  for (int e = 0; e < NC; ++e) {
+    const int ee = e0 + e;
+    if (MODE == 1 || (MODE == 0 && ee >= thr) || (MODE == 2 && ee < thr))
+      sts16(adr[ee & 7] + (uint32_t)(DIR * (unit0 + (ee >> 3)) * (int)W_LB), __uint_as_float(v[e]));
   }
 }
 
@@ -550,9 +550,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   uint64_t* bar_mma3 = bars + 8;     // [2]
   uint64_t* bar_pk = bars + 10;      // TMA: PK band (operand of X1)
   uint64_t* bar_sfree = bars + 11;   // S consumed by all 8 warps (and the staging matrices are free)
-  uint64_t* bar_cready = bars + 12;  // X1 is out of TMEM and Wc is staged (all 8 warps)
-  uint64_t* bar_mmas = bars + 13;    // S final: both positional terms added
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* bar_cready = bars + 12;  // [2] X1 is out of TMEM and the Wc columns of key half g are staged (warpgroup g)
+  uint64_t* bar_mmas = bars + 14;    // [2] S columns of key half g are final: both positional terms added
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   uint8_t* wc = smem + F2_OFF_WC;
   uint8_t* wp = smem + F2_OFF_WP;
 
@@ -566,7 +566,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     mbar_init(bar_mma1, 1); mbar_init(bar_xfree, 8); mbar_init(bar_mma2, 1);
     mbar_init(&bar_pready[0], 4); mbar_init(&bar_pready[1], 4);
     mbar_init(&bar_mma3[0], 1); mbar_init(&bar_mma3[1], 1);
-    mbar_init(bar_pk, 1); mbar_init(bar_sfree, 8); mbar_init(bar_cready, 8); mbar_init(bar_mmas, 1);
+    mbar_init(bar_pk, 1); mbar_init(bar_sfree, 8);
+    mbar_init(&bar_cready[0], 4); mbar_init(&bar_cready[1], 4); mbar_init(&bar_mmas[0], 1); mbar_init(&bar_mmas[1], 1);
     fence_barrier_init();
   }
   if (warp == 9) {
@@ -663,13 +664,18 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             mbar_wait(bar_mma2, ph);  // the PK tile is free
             load_pk(kb + 1);
           }
-          mbar_wait(bar_cready, ph);  // X1 is out of TMEM and Wc is staged
-          tc_fence_after();
-          // c2p term: S[a][16 j + n] += sum_{k in 16 j ..} Wc[a][k] I[k - 16 j][n]
+          // c2p term, one key half per softmax warpgroup (each half is released to its warpgroup on its own, so the
+          // two warpgroups drift apart and fill each other's waits):
+          //   S[a][16 j + n] += sum_{k in 16 j ..} Wc[a][k] I[k - 16 j][n],   j = 4 g .. 4 g + 3
+#pragma unroll 1
+          for (int g = 0; g < 2; ++g) {
+            mbar_wait(&bar_cready[g], ph);   // X1 is out of TMEM (for g = 1: for both halves) and the half is staged
+            tc_fence_after();
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            umma_bf16(tmem + TM_S + 16 * j, make_smem_desc_none(sWc + j * 2 * W_LB, W_LB, W_SB), idb, idesc_addc, 1u);
-          umma_commit(bar_mmas);
+            for (int j = 4 * g; j < 4 * g + 4; ++j)
+              umma_bf16(tmem + TM_S + 16 * j, make_smem_desc_none(sWc + j * 2 * W_LB, W_LB, W_SB), idb, idesc_addc, 1u);
+            umma_commit(&bar_mmas[g]);
+          }
         }
         if (has_next) {
           // next block's S / X2 as soon as every warp has pulled this block's S out of TMEM
@@ -721,14 +727,17 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       }
       tc_fence_before();
     };
-    // staging addresses of this thread's row (the same row index a in Wp -- as a key -- and in Wc -- as a query)
-    uint8_t* wp_row = wp + w_row_base(a);
-    uint8_t* wc_row = wc + w_row_base(a);
-    int offp[8], offc[8];
+    // staging addresses of this thread's row (the same row index a in Wp -- as a key -- and in Wc -- as a query):
+    //   Wp column of (chunk q, element e): x = lane - 31 + 32 q + e        -> adrp[e & 7] + (4 q + (e >> 3)) W_LB
+    //   Wc column of (chunk q, element e): k = 64 g + lane + 63 - 32 q - e -> adrc[e & 7] - (4 q + (e >> 3)) W_LB
+    uint32_t adrp[8], adrc[8];
+    {
+      const uint32_t rowp = smem_u32(wp) + w_row_base(a), rowc = smem_u32(wc) + w_row_base(a);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      offp[r] = w_col_off(lane - 31 + r);          // Wp column of (chunk 0, element r): x = lane - 31 + 32 q + e
-      offc[r] = w_col_off(lane + 127 - r);         // Wc column of (chunk 0, element r): k = lane + 127 - 32 q - e
+      for (int r = 0; r < 8; ++r) {
+        adrp[r] = rowp + (uint32_t)w_col_off(lane - 31 + r);
+        adrc[r] = rowc + (uint32_t)w_col_off(64 * g + lane + 63 - r);
+      }
     }
 
     for (int kb = 0; kb < p.nkb; ++kb) {
@@ -750,26 +759,31 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       //      x = lane - 31 + 32 q + e (chunk 0 valid for e >= 31 - lane, chunks 1-3 for every lane, chunk 4 for
       //      e < 31 - lane); warpgroup 0 takes chunks 0-2, warpgroup 1 chunks 3-4.
       if constexpr (REL) {
-        uint32_t va[32], vb[32];
+        // (the 160-column window is split 80 / 80 between the two warpgroups: chunks 0, 1 and the first half of chunk 2
+        //  for warpgroup 0, the rest for warpgroup 1)
+        uint32_t va[32], vb[32], vh[16];
         const uint32_t xbase = lane_base + TM_X + (96 - 32 * wq);
         const int thr = 31 - lane;
         if (g == 0) {
           tmem_ld_32x32(xbase, va);
           tmem_ld_wait();
           tmem_ld_32x32(xbase + 32, vb);
-          stage_wp<0>(wp_row, offp, 0, va, thr);
+          stage_w<0, 1, 32>(adrp, 0, va, 0, thr);
           tmem_ld_wait();
-          tmem_ld_32x32(xbase + 64, va);
-          stage_wp<1>(wp_row, offp, 4, vb, thr);
+          tmem_ld_32x16(xbase + 64, vh);
+          stage_w<1, 1, 32>(adrp, 4, vb, 0, thr);
           tmem_ld_wait();
-          stage_wp<1>(wp_row, offp, 8, va, thr);
+          stage_w<1, 1, 16>(adrp, 8, vh, 0, thr);
         } else {
+          tmem_ld_32x16(xbase + 80, vh);
+          tmem_ld_wait();
           tmem_ld_32x32(xbase + 96, va);
+          stage_w<1, 1, 16>(adrp, 8, vh, 16, thr);
           tmem_ld_wait();
           tmem_ld_32x32(xbase + 128, vb);
-          stage_wp<1>(wp_row, offp, 12, va, thr);
+          stage_w<1, 1, 32>(adrp, 12, va, 0, thr);
           tmem_ld_wait();
-          stage_wp<2>(wp_row, offp, 16, vb, thr);
+          stage_w<2, 1, 32>(adrp, 16, vb, 0, thr);
         }
         fence_proxy_async_smem();    // generic-proxy stores -> visible to the tensor core (async proxy)
       }
@@ -780,34 +794,25 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       if constexpr (REL) {
         mbar_wait(bar_mma2, ph);
         tc_fence_after();
-        // ---- c2p: lane = QUERY row a of X1.  Key k of this block sits at band column a + 127 - k: the warp loads the
-        //      160-column window starting at 32 wq, chunk q / element e is key k = lane + 127 - 32 q - e (chunk 0
-        //      valid for e >= lane, chunks 1-3 for every lane, chunk 4 for e < lane).
+        // ---- c2p: lane = QUERY row a of X1.  Key k of this block sits at band column a + 127 - k; warpgroup g stages
+        //      its own key half [64g, 64g+64): 3 chunks starting at column 32 wq + 64 (1 - g), chunk q / element e is
+        //      key 64 g + lane + 63 - 32 q - e (chunk 0 valid for e >= lane, chunk 1 for every lane, chunk 2 for e < lane).
         uint32_t va[32], vb[32];
-        const uint32_t xbase = lane_base + TM_X + 32 * wq;
-        if (g == 0) {
-          tmem_ld_32x32(xbase, va);
-          tmem_ld_wait();
-          tmem_ld_32x32(xbase + 32, vb);
-          stage_wc<0>(wc_row, offc, 0, va, lane);
-          tmem_ld_wait();
-          tmem_ld_32x32(xbase + 64, va);
-          stage_wc<1>(wc_row, offc, 4, vb, lane);
-          tmem_ld_wait();
-          stage_wc<1>(wc_row, offc, 8, va, lane);
-        } else {
-          tmem_ld_32x32(xbase + 96, va);
-          tmem_ld_wait();
-          tmem_ld_32x32(xbase + 128, vb);
-          stage_wc<1>(wc_row, offc, 12, va, lane);
-          tmem_ld_wait();
-          stage_wc<2>(wc_row, offc, 16, vb, lane);
-        }
+        const uint32_t xbase = lane_base + TM_X + 32 * wq + 64 * (1 - g);
+        tmem_ld_32x32(xbase, va);
+        tmem_ld_wait();
+        tmem_ld_32x32(xbase + 32, vb);
+        stage_w<0, -1, 32>(adrc, 0, va, 0, lane);
+        tmem_ld_wait();
+        tmem_ld_32x32(xbase + 64, va);
+        stage_w<1, -1, 32>(adrc, 4, vb, 0, lane);
+        tmem_ld_wait();
+        stage_w<2, -1, 32>(adrc, 8, va, 0, lane);
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_cready);
-        mbar_wait(bar_mmas, ph);     // both positional terms have been added to S by the tensor core
+        if (lane == 0) mbar_arrive(&bar_cready[g]);
+        mbar_wait(&bar_mmas[g], ph);   // both positional terms have been added to this key half of S
         tc_fence_after();
       }
       // ---- this warpgroup's 64 final scores of the row

@@ -331,10 +331,16 @@ class DebertaEngine:
                           cfg.layer_norm_eps, y32=R32, mean=rel_mean, rstd=rel_rstd)
         self._R32 = R32
         self._rel_tables_cache = {}
+        self._rel_side_ready = None
+        self._R32_event = torch.cuda.current_stream().record_event() if (self.use_rel and self.dw_side_stream) else None
+        # the positional tables of pass p + 1 are built on the side stream while pass p runs
+        pass_layers = list(range(NL - 1)) + [NL - 1, NL - 1]
+        self._rel_tables_prefetch(pass_layers[0], 0, L)
 
         # ---- encoder: NL-1 ordinary passes (the NL-th only feeds hidden_states[-1], which nothing reads)
         pass_id = 0
         for i in range(NL - 1):
+            self._rel_tables_prefetch(pass_layers[pass_id + 1], pass_id + 1, L)
             qkv = sws.get(f"qkv.{pass_id}", (T, 3 * H), AD) if training else ws.get("qkv", (T, 3 * H), AD)
             lib.gemm(x16, W[f"qkv.w.{i}"], qkv, bias=W[f"qkv.b.{i}"])
             y32, y16, rec = self._layer_pass(i, pass_id, x32, qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], training)
@@ -369,6 +375,8 @@ class DebertaEngine:
         lib.gemm(kv16, W[f"qkv.w.{last}"][H:], kvp, bias=W[f"qkv.b.{last}"][H:].contiguous())
         q32, q16 = z32, z16
         for j in range(2):
+            if j == 0:
+                self._rel_tables_prefetch(last, pass_id + 1, L)
             qp = sws.get(f"emd.q.{j}", (T, H), AD)
             lib.gemm(q16, W[f"qkv.w.{last}"][:H], qp, bias=W[f"qkv.b.{last}"][:H].contiguous())
             y32, y16, rec = self._layer_pass(last, pass_id, q32, qp, kvp[:, :H], kvp[:, H:], training, tag=f"e{j}")
@@ -386,35 +394,58 @@ class DebertaEngine:
         st.o2 = (q32, q16)
         return q32, q16
 
-    def _rel_tables(self, layer, pass_id, L):
+    def _rel_tables_compute(self, layer, pass_id, L):
         """PQrel / PKrel for one layer pass: Linear_{q|k}(dropout(R)) expanded to relative positions
         (fp32-class mode: the un-expanded [2S, 2H] projections, the fp32 attention indexes them by bucket)."""
         cfg, W, ws, sws = self.cfg, self.W, self.ws, self.sws
         H, h = cfg.hidden_size, cfg.num_attention_heads
-        p = cfg.hidden_dropout_prob if self.training else 0.0
-        key = layer if p == 0.0 else None
-        if key is not None and key in self._rel_tables_cache:
-            return self._rel_tables_cache[key]
         S2 = 2 * cfg.position_buckets
-        tagk = f".{pass_id}" if self.training else ""
+        tagk = f".{pass_id}" if self.training else f".L{layer}"
         tws = sws if self.training else ws
         Rd16 = ws.get("Rd16", (S2, H), self.AD)
         lib.dropout_apply(self._R32, self.drop(cfg.hidden_dropout_prob, pass_id * 8 + SITE_POS), out16=Rd16)
         if self.precise:
             pqk = tws.get("pqk32" + tagk, (S2, 2 * H), F32)
             lib.gemm(Rd16, W[f"qkv.w.{layer}"][:2 * H], pqk, bias=W[f"qkv.b.{layer}"][:2 * H].contiguous())
-            out = (pqk, None, None)
-        else:
-            pqk = ws.get("pqk16", (S2, 2 * H), BF16)
-            lib.gemm(Rd16, W[f"qkv.w.{layer}"][:2 * H], pqk, bias=W[f"qkv.b.{layer}"][:2 * H].contiguous())
-            rel_rows, _ = lib.rel_table_geometry(L)
-            pq = tws.get("PQrel" + tagk, (h, rel_rows, 64), BF16)
-            pk = tws.get("PKrel" + tagk, (h, rel_rows, 64), BF16)
-            pkr = tws.get("PKrev" + tagk, (h, rel_rows, 64), BF16) if (self.training and self.fused_attn_bwd) else None
-            lib.build_rel_tables(pqk, self.bucket_of_rel, L, h, out_pq=pq, out_pk=pk, out_pk_rev=pkr)
-            out = (pq, pk, pkr)
-        if key is not None:
-            self._rel_tables_cache[key] = out
+            return (pqk, None, None)
+        pqk = ws.get("pqk16", (S2, 2 * H), BF16)
+        lib.gemm(Rd16, W[f"qkv.w.{layer}"][:2 * H], pqk, bias=W[f"qkv.b.{layer}"][:2 * H].contiguous())
+        rel_rows, _ = lib.rel_table_geometry(L)
+        pq = tws.get("PQrel" + tagk, (h, rel_rows, 64), BF16)
+        pk = tws.get("PKrel" + tagk, (h, rel_rows, 64), BF16)
+        pkr = tws.get("PKrev" + tagk, (h, rel_rows, 64), BF16) if (self.training and self.fused_attn_bwd) else None
+        lib.build_rel_tables(pqk, self.bucket_of_rel, L, h, out_pq=pq, out_pk=pk, out_pk_rev=pkr)
+        return (pq, pk, pkr)
+
+    def _rel_tables_prefetch(self, layer, pass_id, L):
+        """Issues the table construction of a LATER pass on the low-priority side stream: it only depends on the
+        relative embeddings (R), never on the activations, so it is taken off the critical path of the forward (three
+        small launches per pass: dropout, a [512 x 2H x H] GEMM, the table expansion)."""
+        if not self.use_rel or not self.dw_side_stream:
+            return
+        p = self.cfg.hidden_dropout_prob if self.training else 0.0
+        key = ("L", layer) if p == 0.0 else ("P", pass_id)
+        if key in self._rel_tables_cache:
+            return
+        _, lo = _priority_streams(self.device)
+        if self._rel_side_ready is None:
+            lo.wait_event(self._R32_event)          # R = LN(rel_embeddings) of THIS forward
+            self._rel_side_ready = True
+        with torch.cuda.stream(lo):
+            out = self._rel_tables_compute(layer, pass_id, L)
+            ev = lo.record_event()
+        self._rel_tables_cache[key] = (out, ev)
+
+    def _rel_tables(self, layer, pass_id, L):
+        p = self.cfg.hidden_dropout_prob if self.training else 0.0
+        key = ("L", layer) if p == 0.0 else ("P", pass_id)     # without dropout the tables only depend on the layer
+        hit = self._rel_tables_cache.get(key)
+        if hit is None:
+            hit = (self._rel_tables_compute(layer, pass_id, L), None)
+            self._rel_tables_cache[key] = hit
+        out, ev = hit
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
         return out
 
     def _sublayer_out(self, name, i, pass_id, u_in16, W_dense, b_dense, ad_prefix, ln_prefix, resid32, site_ad,
