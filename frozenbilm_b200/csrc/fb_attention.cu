@@ -585,6 +585,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_prologue();
 
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AT_REGS_CONTROL));
@@ -966,6 +967,7 @@ build_rel_tables_kernel(const __nv_bfloat16* __restrict__ pqk, long long ld, int
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int hh = blockIdx.y, t = blockIdx.z;
   if (row >= rel_rows) return;
+  pdl_prologue();
   const int rel = row - rel_off;
   uint32_t val = 0;
   if (rel > -L && rel < L) {
@@ -1095,6 +1097,7 @@ rel_to_bucket_kernel(const float* __restrict__ gpq, const float* __restrict__ gp
   const int row = blockIdx.x * 4 + (threadIdx.x >> 6), col = threadIdx.x & 63;
   const int hh = blockIdx.y, t = blockIdx.z;
   if (row >= rel_rows) return;
+  pdl_prologue();
   const int rel = row - rel_off;
   if (rel <= -L || rel >= L) return;
   const int bucket = bucket_of_rel[rel + 511];
@@ -1167,9 +1170,9 @@ int attn_fwd(const fb_attn_args* a, cudaStream_t st) {
   dim3 grid(lpad / 128, a->h, a->B);
   if (generation == 2) {
     if (rel)
-      attn_fwd2_kernel<true><<<grid, AT_THREADS, AT2_SMEM, st>>>(mq, mk, mv, mpk, mpq, p);
+      FB_CHECK_CUDA(launch_pdl(attn_fwd2_kernel<true>, grid, dim3(AT_THREADS), AT2_SMEM, st, mq, mk, mv, mpk, mpq, p));
     else
-      attn_fwd2_kernel<false><<<grid, AT_THREADS, AT2_SMEM, st>>>(mq, mk, mv, mpk, mpq, p);
+      FB_CHECK_CUDA(launch_pdl(attn_fwd2_kernel<false>, grid, dim3(AT_THREADS), AT2_SMEM, st, mq, mk, mv, mpk, mpq, p));
   } else if (rel)
     attn_fwd_kernel<true><<<grid, AT_THREADS, AT_SMEM, st>>>(mq, mk, mv, mpk, mpq, p);
   else
@@ -1184,10 +1187,9 @@ int build_rel_tables(const void* pqk, long long ld, int H, int h, const int* buc
   FB_REQUIRE(pqk && bucket_of_rel && out_pq && out_pk, "fb_build_rel_tables: null arg");
   FB_REQUIRE(H == h * 64, "fb_build_rel_tables: head_dim must be 64");
   dim3 grid((rel_rows + 7) / 8, h, 2);
-  build_rel_tables_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(pqk), ld, H, h, bucket_of_rel,
-                                               rel_rows, rel_off, L, reinterpret_cast<__nv_bfloat16*>(out_pq),
-                                               reinterpret_cast<__nv_bfloat16*>(out_pk),
-                                               reinterpret_cast<__nv_bfloat16*>(out_pk_rev));
+  FB_CHECK_CUDA(launch_pdl(build_rel_tables_kernel, grid, dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(pqk), ld,
+                           H, h, bucket_of_rel, rel_rows, rel_off, L, reinterpret_cast<__nv_bfloat16*>(out_pq),
+                           reinterpret_cast<__nv_bfloat16*>(out_pk), reinterpret_cast<__nv_bfloat16*>(out_pk_rev)));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1220,8 +1222,8 @@ int attn_bwd_prep(const fb_attn_bwd_prep_args* a, cudaStream_t st) {
 int rel_to_bucket(const float* gpq, const float* gpk, int H, int h, const int* bucket_of_rel, int rel_rows,
                   int rel_off, int L, float* out, long long ldo, cudaStream_t st) {
   FB_REQUIRE(gpq && gpk && bucket_of_rel && out && H == h * 64, "fb_rel_to_bucket: bad args");
-  rel_to_bucket_kernel<<<dim3((rel_rows + 3) / 4, h, 2), 256, 0, st>>>(gpq, gpk, H, h, bucket_of_rel, rel_rows, rel_off,
-                                                                      L, out, ldo);
+  FB_CHECK_CUDA(launch_pdl(rel_to_bucket_kernel, dim3((rel_rows + 3) / 4, h, 2), dim3(256), 0, st, gpq, gpk, H, h,
+                           bucket_of_rel, rel_rows, rel_off, L, out, ldo));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -207,6 +207,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  pdl_prologue();   // everything below reads what earlier kernels of the stream wrote
   // per-thread row statistics for the query rows I * 128 + a: D = rowsum(dO * O), lse
   float Dr[4] = {0.f, 0.f, 0.f, 0.f}, Lr[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
   if (warp < 4 * NG) {
@@ -735,6 +736,7 @@ attn_bwd_rel_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_prologue();
 
   if (warp == 8) {
     if (elect_one_sync()) {
@@ -927,9 +929,11 @@ int attn_bwd(const fb_attn_bwd_args* a, cudaStream_t st) {
   }
   dim3 grid(a->h, a->B);
   if (rel)
-    attn_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, st>>>(mq, mk, mv, mdo, mpk, mpq, mds, mdq, mdk, mdv, p);
+    FB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true>, grid, dim3(AB_THREADS), AB_SMEM, st, mq, mk, mv, mdo, mpk, mpq, mds, mdq,
+                             mdk, mdv, p));
   else
-    attn_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, st>>>(mq, mk, mv, mdo, mpk, mpq, mds, mdq, mdk, mdv, p);
+    FB_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false>, grid, dim3(AB_THREADS), AB_SMEM, st, mq, mk, mv, mdo, mpk, mpq, mds, mdq,
+                             mdk, mdv, p));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -972,6 +976,7 @@ int attn_bwd_rel(const fb_attn_bwd_rel_args* a, cudaStream_t st) {
     FB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_rel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AR_SMEM));
     configured = true;
   }
+  // (plain launch: it follows the two memset nodes above, which are not kernels a dependent launch could overlap)
   attn_bwd_rel_kernel<<<dim3(nslices, a->h), AR_THREADS, AR_SMEM, st>>>(mq, mk, p);
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());

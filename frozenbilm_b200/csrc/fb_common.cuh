@@ -31,6 +31,7 @@ void set_last_error(const char* fmt, ...);
   } while (0)
 
 int num_sms();
+bool pdl_enabled();   // programmatic dependent launch (FB_PDL=0 disables it)
 // Generic bf16 tiled tensor map (rank <= 4), 128B swizzle, inner box = 64 elements (128 B).
 int make_tmap_bf16_nd(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
                       const uint64_t* strides_elems /*rank-1*/, const uint32_t* box);
@@ -57,6 +58,17 @@ __device__ __forceinline__ bool elect_one_sync() {
       "}\n"
       : "=r"(pred));
   return pred != 0;
+}
+
+// ---- programmatic dependent launch ----
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization (launch_pdl below):
+// it may become resident while the previous kernel of the stream is still draining, runs its prologue (barrier
+// initialisation, TMEM allocation, descriptor prefetch) and then blocks HERE until the previous grid has completed
+// and its memory is visible.  pdl_prologue() must therefore precede the first global-memory access of every
+// kernel launched that way; it also lets the NEXT kernel start its own launch early.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 // ---- mbarrier ----
@@ -468,6 +480,18 @@ __device__ __forceinline__ uint32_t drop_keep8(const DropSpec& d, uint32_t rowid
 }
 __device__ __forceinline__ uint32_t drop_row_key(const DropSpec& d, uint32_t rowid) {
   return drop_row_key_raw(rowid, d.seed_lo, d.seed_hi, d.off_lo, d.off_hi);
+}
+
+// Host side: <<<grid, block, smem, stream>>> with the programmatic-serialization attribute.
+template <typename... P, typename... A>
+inline cudaError_t launch_pdl(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
 }
 
 }  // namespace fb

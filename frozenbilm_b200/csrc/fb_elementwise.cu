@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const float* __restrict__ x, int M, const float* __restrict__ gamma, const float* __restrict__ beta,
               float eps, const uint8_t* __restrict__ rowmask, DropSpec drop, float* __restrict__ y32,
               __nv_bfloat16* __restrict__ y16, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  pdl_prologue();
   constexpr int H = NV * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
@@ -102,6 +103,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
               const uint8_t* __restrict__ rowmask, DropSpec out_drop, DropSpec in_drop, float* __restrict__ dx32,
               __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta,
               float* __restrict__ dx16_colsum) {
+  pdl_prologue();
   // TWO warps per row (64 lanes x NV/2 float4 each): halves the per-thread dgamma/dbeta/column-sum accumulators so
   // that two CTAs (16 warps) fit per SM; the row is streamed twice (second read hits L1/L2).
   constexpr int H = NV * 128;
@@ -234,8 +236,10 @@ int layernorm_fwd(const float* x, int M, int H, const float* gamma, const float*
   FB_REQUIRE(x && gamma && beta && M > 0 && H % 128 == 0, "fb_layernorm_fwd: bad args");
   const DropSpec d = drop_from(out_drop);
   const int grid = (M + 7) / 8;
-  FB_DISPATCH_NV(H, (ln_fwd_kernel<NV><<<grid, 256, 0, st>>>(x, M, gamma, beta, eps, rowmask, d, y32,
-                                                            reinterpret_cast<__nv_bfloat16*>(y16), mean, rstd)));
+  cudaError_t le = cudaSuccess;
+  FB_DISPATCH_NV(H, (le = launch_pdl(ln_fwd_kernel<NV>, dim3(grid), dim3(256), 0, st, x, M, gamma, beta, eps, rowmask, d, y32,
+                                     reinterpret_cast<__nv_bfloat16*>(y16), mean, rstd)));
+  FB_CHECK_CUDA(le);
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -247,9 +251,10 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
   FB_REQUIRE(dy && x && mean && rstd && gamma && M > 0 && H % 128 == 0, "fb_layernorm_bwd: bad args");
   const DropSpec od = drop_from(out_drop), id = drop_from(in_drop);
   const int grid = std::max(1, std::min((M + 3) / 4, 2 * num_sms()));
-  FB_DISPATCH_NV(H, (ln_bwd_kernel<NV><<<grid, 256, 0, st>>>(dy, x, mean, rstd, gamma, M, rowmask, od, id, dx32,
-                                                            reinterpret_cast<__nv_bfloat16*>(dx16), dgamma, dbeta,
-                                                            dx16_colsum)));
+  cudaError_t le = cudaSuccess;
+  FB_DISPATCH_NV(H, (le = launch_pdl(ln_bwd_kernel<NV>, dim3(grid), dim3(256), 0, st, dy, x, mean, rstd, gamma, M, rowmask, od,
+                                     id, dx32, reinterpret_cast<__nv_bfloat16*>(dx16), dgamma, dbeta, dx16_colsum)));
+  FB_CHECK_CUDA(le);
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -264,6 +269,7 @@ template <typename TI, typename TO>
 __global__ void rows_kernel(const TI* __restrict__ in, long long ld_in, const long long* __restrict__ idx_in,
                             const long long* __restrict__ idx_out, int ncols, TO* __restrict__ out,
                             long long ld_out) {
+  pdl_prologue();
   const int r = blockIdx.x;
   const long long ji = idx_in ? idx_in[r] : r, jo = idx_out ? idx_out[r] : r;
   if (ji < 0 || jo < 0) return;
@@ -281,17 +287,17 @@ int move_rows(const void* in, long long ld_in, int in_bf16, const long long* idx
   FB_REQUIRE(in && out && R > 0 && ncols > 0, "fb_move_rows: bad args");
   const int threads = 256;
   if (in_bf16 && out_bf16)
-    rows_kernel<__nv_bfloat16, __nv_bfloat16><<<R, threads, 0, st>>>((const __nv_bfloat16*)in, ld_in, idx_in, idx_out,
-                                                                     ncols, (__nv_bfloat16*)out, ld_out);
+    FB_CHECK_CUDA(launch_pdl(rows_kernel<__nv_bfloat16, __nv_bfloat16>, dim3(R), dim3(threads), 0, st, (const __nv_bfloat16*)in,
+                             ld_in, idx_in, idx_out, ncols, (__nv_bfloat16*)out, ld_out));
   else if (in_bf16 && !out_bf16)
-    rows_kernel<__nv_bfloat16, float><<<R, threads, 0, st>>>((const __nv_bfloat16*)in, ld_in, idx_in, idx_out, ncols,
-                                                             (float*)out, ld_out);
+    FB_CHECK_CUDA(launch_pdl(rows_kernel<__nv_bfloat16, float>, dim3(R), dim3(threads), 0, st, (const __nv_bfloat16*)in, ld_in,
+                             idx_in, idx_out, ncols, (float*)out, ld_out));
   else if (!in_bf16 && out_bf16)
-    rows_kernel<float, __nv_bfloat16><<<R, threads, 0, st>>>((const float*)in, ld_in, idx_in, idx_out, ncols,
-                                                             (__nv_bfloat16*)out, ld_out);
+    FB_CHECK_CUDA(launch_pdl(rows_kernel<float, __nv_bfloat16>, dim3(R), dim3(threads), 0, st, (const float*)in, ld_in, idx_in,
+                             idx_out, ncols, (__nv_bfloat16*)out, ld_out));
   else
-    rows_kernel<float, float><<<R, threads, 0, st>>>((const float*)in, ld_in, idx_in, idx_out, ncols, (float*)out,
-                                                     ld_out);
+    FB_CHECK_CUDA(launch_pdl(rows_kernel<float, float>, dim3(R), dim3(threads), 0, st, (const float*)in, ld_in, idx_in, idx_out,
+                             ncols, (float*)out, ld_out));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -302,6 +308,7 @@ int move_rows(const void* in, long long ld_in, int in_bf16, const long long* idx
 // embedding output, zero padded per sample; col2im is its transpose for the backward.
 // ---------------------------------------------------------------------------------------------
 __global__ void im2col3_kernel(const __nv_bfloat16* __restrict__ x, int L, int H, __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
   const int row = blockIdx.x;  // b * L + t
   const int t = row % L;
   const int hv = H / 8;
@@ -315,6 +322,7 @@ __global__ void im2col3_kernel(const __nv_bfloat16* __restrict__ x, int L, int H
 }
 __global__ void col2im3_kernel(const __nv_bfloat16* __restrict__ dcol, int L, int H, float* __restrict__ dx,
                                int accumulate) {
+  pdl_prologue();
   const int row = blockIdx.x;
   const int t = row % L;
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
@@ -332,6 +340,7 @@ __global__ void col2im3_kernel(const __nv_bfloat16* __restrict__ dcol, int L, in
 // ---------------------------------------------------------------------------------------------
 __global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int M, int N, int rows_per_cta,
                               float* __restrict__ out) {
+  pdl_prologue();
   const int c2 = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
   if (c2 >= N) return;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
@@ -380,6 +389,7 @@ __global__ void __launch_bounds__(CE_THREADS, 1)
 ce_kernel(const float* __restrict__ logits, long long ld, int V, const long long* __restrict__ labels,
           float* __restrict__ loss_sum, float loss_scale, GT* __restrict__ dlogits, long long ldd,
           float grad_scale) {
+  pdl_prologue();
   __shared__ float sm[32], ss[32];
   __shared__ float sbc[2];
   const int row = blockIdx.x;
@@ -445,6 +455,7 @@ ce_kernel(const float* __restrict__ logits, long long ld, int V, const long long
 // ---------------------------------------------------------------------------------------------
 __global__ void dropout_kernel(const float* __restrict__ x, int M, int N, DropSpec d, float* __restrict__ out32,
                                int accumulate, __nv_bfloat16* __restrict__ out16) {
+  pdl_prologue();
   const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= (long long)M * N) return;
   const int row = (int)(i4 / N), col = (int)(i4 % N);
@@ -467,6 +478,7 @@ __global__ void dropout_kernel(const float* __restrict__ x, int M, int N, DropSp
 
 __global__ void gelu_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ pre, int M, int N,
                                 const uint8_t* __restrict__ rowmask, DropSpec d, __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
   const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= (long long)M * N) return;
   const int row = (int)(i4 / N), col = (int)(i4 % N);
@@ -486,6 +498,7 @@ __global__ void gelu_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat1
 }
 __global__ void add_rowbcast_kernel(const float* __restrict__ a, const float* __restrict__ b, long long period,
                                     long long n4, float* __restrict__ out32, __nv_bfloat16* __restrict__ out16) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 x = reinterpret_cast<const float4*>(a)[i];
@@ -500,6 +513,7 @@ __global__ void add_rowbcast_kernel(const float* __restrict__ a, const float* __
 // args.py:246-262), also refreshing the bf16 operand copy of the updated parameters.
 // ---------------------------------------------------------------------------------------------
 __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float sred[8];
   float s = 0.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -519,6 +533,7 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __
 // bit-identical across replicas (float atomics would add the partials in arrival order).
 __global__ void sumsq_det_kernel(const float* __restrict__ g, long long n, float* __restrict__ out,
                                  float* __restrict__ scratch) {
+  pdl_prologue();
   __shared__ float sred[8];
   __shared__ bool last;
   float s = 0.0f;
@@ -548,6 +563,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float bc1,
                             float bc2, const float* __restrict__ gnorm_sq, float max_norm, float grad_scale,
                             __nv_bfloat16* __restrict__ p16) {
+  pdl_prologue();
   float coef = grad_scale;
   if (gnorm_sq && max_norm > 0.0f) {
     const float norm = sqrtf(*gnorm_sq) * grad_scale;
@@ -565,6 +581,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 __global__ void cast_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __restrict__ out) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(x[i]);
 }
@@ -579,6 +596,7 @@ static constexpr int STK_THREADS = 256;
 __global__ void __launch_bounds__(STK_THREADS)
 softmax_topk_kernel(const float* __restrict__ logits, long long ld, int V, int k, float* __restrict__ probs_out,
                     long long ldp, float* __restrict__ top_p, long long* __restrict__ top_i) {
+  pdl_prologue();
   extern __shared__ float srow[];                 // V probabilities
   __shared__ float rv[STK_THREADS / 32];
   __shared__ int ri[STK_THREADS / 32];
@@ -663,9 +681,8 @@ int fb_gelu_bwd(const float* dy, const void* pre_bf16, int M, int N, const unsig
                 const fb_dropout* drop, void* out_bf16, void* stream) {
   FB_REQUIRE(dy && pre_bf16 && out_bf16 && M > 0 && N % 8 == 0, "fb_gelu_bwd: bad args");
   const long long n4 = (long long)M * N / 4;
-  gelu_bwd_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, ST(stream)>>>(dy, (const __nv_bfloat16*)pre_bf16, M, N,
-                                                                       rowmask, drop_from(drop),
-                                                                       (__nv_bfloat16*)out_bf16);
+  FB_CHECK_CUDA(launch_pdl(gelu_bwd_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, ST(stream), dy,
+                           (const __nv_bfloat16*)pre_bf16, M, N, rowmask, drop_from(drop), (__nv_bfloat16*)out_bf16));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -676,22 +693,24 @@ int fb_add_rowbcast(const float* a, const float* b, int B, int L, int H, float* 
                     void* stream) {
   FB_REQUIRE(a && b && out_f32 && B > 0 && L > 0 && H % 4 == 0, "fb_add_rowbcast: bad args");
   const long long n4 = (long long)B * L * H / 4;
-  add_rowbcast_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, ST(stream)>>>(a, b, (long long)L * H, n4, out_f32,
-                                                                           (__nv_bfloat16*)out_bf16);
+  FB_CHECK_CUDA(launch_pdl(add_rowbcast_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, ST(stream), a, b,
+                           (long long)L * H, n4, out_f32, (__nv_bfloat16*)out_bf16));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int fb_conv_im2col(const void* x_bf16, int B, int L, int H, void* out_bf16, void* stream) {
   FB_REQUIRE(x_bf16 && out_bf16 && B > 0 && L > 0 && H % 8 == 0, "fb_conv_im2col: bad args");
-  im2col3_kernel<<<B * L, 256, 0, ST(stream)>>>((const __nv_bfloat16*)x_bf16, L, H, (__nv_bfloat16*)out_bf16);
+  FB_CHECK_CUDA(launch_pdl(im2col3_kernel, dim3(B * L), dim3(256), 0, ST(stream), (const __nv_bfloat16*)x_bf16, L, H,
+                           (__nv_bfloat16*)out_bf16));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int fb_conv_col2im(const void* dcol_bf16, int B, int L, int H, float* dx, int accumulate, void* stream) {
   FB_REQUIRE(dcol_bf16 && dx && B > 0 && L > 0, "fb_conv_col2im: bad args");
-  col2im3_kernel<<<B * L, 256, 0, ST(stream)>>>((const __nv_bfloat16*)dcol_bf16, L, H, dx, accumulate);
+  FB_CHECK_CUDA(launch_pdl(col2im3_kernel, dim3(B * L), dim3(256), 0, ST(stream), (const __nv_bfloat16*)dcol_bf16, L, H, dx,
+                           accumulate));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -700,7 +719,7 @@ int fb_colsum_bf16(const void* x, long long ld, int M, int N, float* out, void* 
   FB_REQUIRE(x && out && M > 0 && N > 0 && (ld % 2 == 0), "fb_colsum_bf16: bad args");
   const int rows_per_cta = 64;
   dim3 grid(((N + 1) / 2 + 127) / 128, (M + rows_per_cta - 1) / rows_per_cta);
-  colsum_kernel<<<grid, 128, 0, ST(stream)>>>((const __nv_bfloat16*)x, ld, M, N, rows_per_cta, out);
+  FB_CHECK_CUDA(launch_pdl(colsum_kernel, grid, dim3(128), 0, ST(stream), (const __nv_bfloat16*)x, ld, M, N, rows_per_cta, out));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -714,8 +733,8 @@ int fb_cross_entropy(const float* logits, long long ld, int P, int V, const long
                                        fb::CE_SMEM));
     configured = true;
   }
-  fb::ce_kernel<__nv_bfloat16><<<P, fb::CE_THREADS, fb::CE_SMEM, ST(stream)>>>(
-      logits, ld, V, labels, loss_sum, loss_scale, (__nv_bfloat16*)dlogits_bf16, ldd, grad_scale);
+  FB_CHECK_CUDA(launch_pdl(fb::ce_kernel<__nv_bfloat16>, dim3(P), dim3(fb::CE_THREADS), fb::CE_SMEM, ST(stream), logits, ld, V,
+                           labels, loss_sum, loss_scale, (__nv_bfloat16*)dlogits_bf16, ldd, grad_scale));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -750,8 +769,8 @@ int fb_dropout_apply(const float* x, int M, int N, const fb_dropout* drop, float
                      void* out_bf16, void* stream) {
   FB_REQUIRE(x && M > 0 && N > 0 && N % 8 == 0, "fb_dropout_apply: bad args (N must be a multiple of 8)");
   const long long n4 = (long long)M * N / 4;
-  dropout_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, ST(stream)>>>(x, M, N, drop_from(drop), out_f32, accumulate,
-                                                                      (__nv_bfloat16*)out_bf16);
+  FB_CHECK_CUDA(launch_pdl(dropout_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, ST(stream), x, M, N,
+                           drop_from(drop), out_f32, accumulate, (__nv_bfloat16*)out_bf16));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -768,7 +787,7 @@ int fb_sumsq_det(const float* g, long long n, float* out, float* scratch, int sc
   FB_REQUIRE(g && out && scratch && n > 0 && scratch_len >= 2, "fb_sumsq_det: bad args");
   const int grid = (int)std::max<long long>(1, std::min<long long>(std::min<long long>((n + 255) / 256, 4LL * num_sms()),
                                                                    scratch_len - 1));
-  sumsq_det_kernel<<<grid, 256, 0, ST(stream)>>>(g, n, out, scratch);
+  FB_CHECK_CUDA(launch_pdl(sumsq_det_kernel, dim3(grid), dim3(256), 0, ST(stream), g, n, out, scratch));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -779,8 +798,8 @@ int fb_adam_step(float* p, const float* g, float* m, float* v, long long n, floa
   FB_REQUIRE(p && g && m && v && n > 0 && step >= 1, "fb_adam_step: bad args");
   const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
   const int grid = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 8LL * num_sms()));
-  adam_kernel<<<grid, 256, 0, ST(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2, gnorm_sq, max_norm,
-                                            grad_scale, (__nv_bfloat16*)p_bf16);
+  FB_CHECK_CUDA(launch_pdl(adam_kernel, dim3(grid), dim3(256), 0, ST(stream), p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2,
+                           gnorm_sq, max_norm, grad_scale, (__nv_bfloat16*)p_bf16));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -788,7 +807,7 @@ int fb_adam_step(float* p, const float* g, float* m, float* v, long long n, floa
 int fb_cast_f32_bf16(const float* x, long long n, void* out, void* stream) {
   FB_REQUIRE(x && out && n > 0, "fb_cast_f32_bf16: bad args");
   const int grid = (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 8LL * num_sms()));
-  cast_kernel<<<grid, 256, 0, ST(stream)>>>(x, n, (__nv_bfloat16*)out);
+  FB_CHECK_CUDA(launch_pdl(cast_kernel, dim3(grid), dim3(256), 0, ST(stream), x, n, (__nv_bfloat16*)out));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -369,6 +369,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   if constexpr (CL > 1) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue();   // operands / epilogue inputs come from the previous kernel of the stream
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -668,6 +669,15 @@ const char* last_error() { return g_err; }
 std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("FB_PDL");
+    on = (e == nullptr || atoi(e) != 0) ? 1 : 0;
+  }
+  return on == 1;
+}
+
 int num_sms() {
   static int n = -1;
   if (n < 0) {
@@ -776,16 +786,18 @@ static int launch_gemm_impl(const CUtensorMap& ma, const CUtensorMap& mb, const 
   if (CL == 1) {
     int grid = std::min(p.total_tiles, num_sms());
     FB_REQUIRE(grid > 0, "no CUDA device / empty GEMM");
-    kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, md, mpre, p);
+    FB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES, st, ma, mb, md, mpre, p));
   } else {
     const int clusters = std::min(p.total_tiles / CL, max_clusters);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(clusters * CL); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 2;
     FB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, md, mpre, p));
   }
   count_launch();
