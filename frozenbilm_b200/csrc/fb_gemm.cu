@@ -669,13 +669,14 @@ const char* last_error() { return g_err; }
 std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+static std::atomic<int> g_pdl{-1};   // -1: not yet read from the environment (FB_PDL, default on)
+static int pdl_env() {
+  static const int v = [] { const char* e = getenv("FB_PDL"); return (e == nullptr || atoi(e) != 0) ? 1 : 0; }();
+  return v;
+}
 bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("FB_PDL");
-    on = (e == nullptr || atoi(e) != 0) ? 1 : 0;
-  }
-  return on == 1;
+  const int v = g_pdl.load(std::memory_order_relaxed);
+  return (v < 0 ? pdl_env() : (v && pdl_env())) == 1;
 }
 
 int num_sms() {
@@ -968,5 +969,10 @@ const char* fb_last_error(void) { return fb::last_error(); }
 int fb_abi_version(void) { return FB_ABI_VERSION; }
 long long fb_launch_count(void) { return fb::g_launches.load(); }
 int fb_gemm_cluster_capacity(void) { return fb::cluster_capacity(); }
+int fb_set_pdl(int on) {
+  const int prev = fb::pdl_enabled() ? 1 : 0;
+  fb::g_pdl.store(on ? 1 : 0, std::memory_order_relaxed);
+  return prev;
+}
 int fb_gemm(const fb_gemm_args* args, void* stream) { return fb::gemm(args, reinterpret_cast<cudaStream_t>(stream)); }
 }

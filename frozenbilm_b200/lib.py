@@ -225,7 +225,7 @@ EXPORTS = [
     "fb_cast_f32_bf16", "fb_attn_bwd_prep", "fb_rel_to_bucket", "fb_attn_bwd", "fb_attn_bwd_rel",
     "fb_mlm_corrupt", "fb_gather_frames", "fb_gemm_cluster_capacity",
     "fb_split3", "fb_epilogue_f32", "fb_colsum_f32", "fb_conv_im2col_f32", "fb_conv_col2im_f32",
-    "fb_cross_entropy_f32", "fb_attn_fwd_f32", "fb_attn_bwd_f32", "fb_softmax_topk", "fb_sumsq_det",
+    "fb_cross_entropy_f32", "fb_attn_fwd_f32", "fb_attn_bwd_f32", "fb_softmax_topk", "fb_sumsq_det", "fb_set_pdl",
 ]
 # include/frozenbilm_b200_debug.h: only in libfrozenbilm_sm100_dbg.so
 DEBUG_EXPORTS = ["fb_umma_probe", "fb_attn_bwd_set_debug"]
@@ -242,6 +242,11 @@ def stream_ptr() -> C.c_void_p:
 
 def _dp(d):
     return C.byref(d) if d is not None else None
+
+
+def set_pdl(on: bool) -> bool:
+    """Programmatic dependent launch for the following launches; returns the previous setting."""
+    return bool(load().fb_set_pdl(int(bool(on))))
 
 
 def launch_count() -> int:

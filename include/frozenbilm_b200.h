@@ -26,6 +26,12 @@ extern "C" {
 
 const char* fb_last_error(void);
 int fb_abi_version(void);
+/* Programmatic dependent launch for the launches that follow (process-wide; returns the previous setting; FB_PDL=0 in
+ * the environment disables it for good).  Every kernel of the library blocks on griddepcontrol.wait before its first
+ * global access, so a dependent launch only overlaps launch latency and prologues.  The host side switches it off
+ * while the low-priority side stream has work (the backward of a training step): early-resident kernels that sit in
+ * griddepcontrol.wait keep the side stream's CTAs off the SMs they were meant to fill (measured: +1.5 ms/step). */
+int fb_set_pdl(int on);
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
 long long fb_launch_count(void);
 

@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-( timeout 1500 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log )
-grep -E "^E  |FAILED|passed|failed|pytest exit" gpurun_out/pytest_gpu.log | cut -c1-250 | head -40
-timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench.json 2>gpurun_out/bench.err; cut -c1-260 gpurun_out/bench.json; tail -2 gpurun_out/bench.err
-FB_PDL=0 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench_nopdl.json 2>/dev/null; cut -c1-260 gpurun_out/bench_nopdl.json
-timeout 300 python bench.py --no-cpu-baseline --workload mc > gpurun_out/bench_mc.json 2>/dev/null; cut -c1-260 gpurun_out/bench_mc.json
-timeout 300 python bench.py --no-cpu-baseline --workload bert > gpurun_out/bench_bert.json 2>/dev/null; cut -c1-260 gpurun_out/bench_bert.json
+timeout 200 python scripts/gpu_probe_kernels.py 2>&1 | tail -5
+timeout 200 python scripts/gpu_sanitize.py 2>&1 | tail -3
+for tool in memcheck racecheck; do
+  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python scripts/gpu_sanitize.py > gpurun_out/sanitizer_$tool.log 2>&1
+  echo "sanitizer $tool exit $?"; tail -4 gpurun_out/sanitizer_$tool.log
+done
