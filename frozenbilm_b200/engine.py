@@ -641,7 +641,9 @@ class DebertaEngine:
         dt32 = ws.rows("bw.dt32", n, H, F32)
         if dlogits is None:
             lib.gemm(hs["dlog16"], hs["E"], dt32, b_mn_major=True, K=hs["V"], N=H)
-            if scale is not None and scale != 1.0:
+            if torch.is_tensor(scale):
+                dt32.mul_(scale.to(dt32.dtype))         # d(loss) from autograd: a device scalar, never read on the host
+            elif scale is not None and scale != 1.0:
                 dt32.mul_(scale)
         else:
             nans = hs["V"]

@@ -75,7 +75,7 @@ class _MLMLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dloss):
-        ctx.module._run_backward(ctx.state, scale=float(dloss))
+        ctx.module._run_backward(ctx.state, scale=dloss)      # stays on the device: no host sync in the backward
         ctx.state = None
         return None, None, None, None
 
@@ -262,15 +262,26 @@ class FrozenBiLMBase(nn.Module):
         training = self.training and torch.is_grad_enabled()
         fb = self.fb
         if labels is not None:
+            labels_on_host = labels if labels.device.type == "cpu" else None
             labels = labels.to(dev)
             flat_lab = torch.cat([torch.full((B, F), -100, dtype=torch.long, device=dev), labels], 1).reshape(-1) \
                 if F else labels.reshape(-1)
-            sel = torch.nonzero(flat_lab != -100).reshape(-1)        # one host sync, before any kernel is queued
-            n_sel = int(sel.numel())
+            # Number of labelled rows (the head's GEMM M): counted on the host when the labels live there; otherwise on
+            # the device into pinned memory, and read only AFTER the encoder has been queued -- the wait then ends when
+            # the GPU reaches the start of this forward, with the whole encoder still in its queue (no idle GPU).
+            lab_ne = flat_lab != -100
+            if labels_on_host is not None:
+                n_sel, cnt_ev = int((labels_on_host != -100).sum()), None
+            else:
+                n_sel, cnt_ev = None, self._count_async(lab_ne)
         with torch.no_grad():
             eng.forward_encoder(video, video_mask, input_ids, attention_mask, training)
             state = eng.cur
             if labels is not None:
+                if n_sel is None:
+                    cnt_ev.synchronize()
+                    n_sel = int(self._count_host[0])
+                sel = torch.nonzero_static(lab_ne, size=n_sel).reshape(-1)     # size known: no host sync
                 if n_sel == 0:
                     loss = torch.full((), float("nan"), device=dev)
                 else:
@@ -305,13 +316,20 @@ class FrozenBiLMBase(nn.Module):
             raise ValueError("answer_scores needs the answer head (n_ans > 0)")
         eng = self._ensure_engine()
         dev = self.device
+        ids_on_host = input_ids if input_ids.device.type == "cpu" else None
         input_ids = input_ids.to(dev)
         Bt, Lt = input_ids.shape
         use_video = bool(self.features_dim) and video is not None
         F = video.shape[1] if use_video else 0
+        is_mask = input_ids.reshape(-1) == mask_token_id
+        # [MASK] count: on the host when the ids live there, else read back only after the encoder has been queued
+        n, cnt_ev = (int((ids_on_host == mask_token_id).sum()), None) if ids_on_host is not None \
+            else (None, self._count_async(is_mask))
         eng.forward_encoder(video, video_mask, input_ids, attention_mask, False, video_repeat=candidates)
-        pos = torch.nonzero(input_ids.reshape(-1) == mask_token_id).reshape(-1)     # like the reference's boolean index
-        n = int(pos.numel())
+        if n is None:
+            cnt_ev.synchronize()
+            n = int(self._count_host[0])
+        pos = torch.nonzero_static(is_mask, size=n).reshape(-1)      # the reference's boolean index, size known
         rows = (pos // Lt) * (F + Lt) + F + pos % Lt
         rows16 = eng.ws.rows("ans.rows16", n, self.fb.hidden_size, eng.AD)
         lib.move_rows(eng.cur.o2[1], rows16, idx_in=rows.contiguous())
@@ -322,6 +340,16 @@ class FrozenBiLMBase(nn.Module):
         if return_probs:
             out["probs"] = probs
         return out
+
+    def _count_async(self, flags):
+        """flags.sum() -> pinned host memory on the current stream; returns the event to wait for before reading
+        ``self._count_host``."""
+        if getattr(self, "_count_host", None) is None:
+            self._count_host = torch.zeros(1, dtype=torch.long).pin_memory()
+        self._count_host.copy_(flags.sum(), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return ev
 
     def _full_logits(self, eng, state, B, L, mlm, scratch=False):
         if eng.cur is not state:
