@@ -963,10 +963,17 @@ __global__ void __launch_bounds__(256)
 build_rel_tables_kernel(const __nv_bfloat16* __restrict__ pqk, long long ld, int H, int h,
                         const int* __restrict__ bucket_of_rel, int rel_rows, int rel_off, int L,
                         __nv_bfloat16* __restrict__ out_pq, __nv_bfloat16* __restrict__ out_pk,
-                        __nv_bfloat16* __restrict__ out_pk_rev) {
+                        __nv_bfloat16* __restrict__ out_pk_rev, long long stride_pqk) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  const int hh = blockIdx.y, t = blockIdx.z;
+  const int hh = blockIdx.y, t = blockIdx.z & 1;
   if (row >= rel_rows) return;
+  {
+    // batched over layer passes: blockIdx.z = 2 * pass + t, the tables of a pass are [h, rel_rows, 64] back to back
+    const long long pass = blockIdx.z >> 1, tab = (long long)h * rel_rows * 64;
+    pqk += pass * stride_pqk;
+    out_pq += pass * tab; out_pk += pass * tab;
+    if (out_pk_rev != nullptr) out_pk_rev += pass * tab;
+  }
   pdl_prologue();
   const int rel = row - rel_off;
   uint32_t val = 0;
@@ -1092,11 +1099,17 @@ __global__ void __launch_bounds__(256) attn_bwd_z2_kernel(const __nv_bfloat16* _
 __global__ void __launch_bounds__(256)
 rel_to_bucket_kernel(const float* __restrict__ gpq, const float* __restrict__ gpk, int H, int h,
                      const int* __restrict__ bucket_of_rel, int rel_rows, int rel_off, int L,
-                     float* __restrict__ out, long long ldo) {
+                     float* __restrict__ out, long long ldo, long long stride_out) {
   // 4 table rows per CTA (64 threads = 64 columns each)
   const int row = blockIdx.x * 4 + (threadIdx.x >> 6), col = threadIdx.x & 63;
-  const int hh = blockIdx.y, t = blockIdx.z;
+  const int hh = blockIdx.y, t = blockIdx.z & 1;
   if (row >= rel_rows) return;
+  {
+    // batched over layer passes: blockIdx.z = 2 * pass + t
+    const long long pass = blockIdx.z >> 1, tab = (long long)h * rel_rows * 64;
+    gpq += pass * tab; gpk += pass * tab;
+    out += pass * stride_out;
+  }
   pdl_prologue();
   const int rel = row - rel_off;
   if (rel <= -L || rel >= L) return;
@@ -1183,13 +1196,16 @@ int attn_fwd(const fb_attn_args* a, cudaStream_t st) {
 }
 
 int build_rel_tables(const void* pqk, long long ld, int H, int h, const int* bucket_of_rel, int rel_rows,
-                     int rel_off, int L, void* out_pq, void* out_pk, void* out_pk_rev, cudaStream_t st) {
+                     int rel_off, int L, void* out_pq, void* out_pk, void* out_pk_rev, int nb, long long stride_pqk,
+                     cudaStream_t st) {
   FB_REQUIRE(pqk && bucket_of_rel && out_pq && out_pk, "fb_build_rel_tables: null arg");
   FB_REQUIRE(H == h * 64, "fb_build_rel_tables: head_dim must be 64");
-  dim3 grid((rel_rows + 7) / 8, h, 2);
+  FB_REQUIRE(nb >= 1 && nb <= 32767, "fb_build_rel_tables: bad batch %d", nb);
+  dim3 grid((rel_rows + 7) / 8, h, 2 * nb);
   FB_CHECK_CUDA(launch_pdl(build_rel_tables_kernel, grid, dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(pqk), ld,
                            H, h, bucket_of_rel, rel_rows, rel_off, L, reinterpret_cast<__nv_bfloat16*>(out_pq),
-                           reinterpret_cast<__nv_bfloat16*>(out_pk), reinterpret_cast<__nv_bfloat16*>(out_pk_rev)));
+                           reinterpret_cast<__nv_bfloat16*>(out_pk), reinterpret_cast<__nv_bfloat16*>(out_pk_rev),
+                           stride_pqk));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1220,10 +1236,11 @@ int attn_bwd_prep(const fb_attn_bwd_prep_args* a, cudaStream_t st) {
 }
 
 int rel_to_bucket(const float* gpq, const float* gpk, int H, int h, const int* bucket_of_rel, int rel_rows,
-                  int rel_off, int L, float* out, long long ldo, cudaStream_t st) {
+                  int rel_off, int L, float* out, long long ldo, int nb, long long stride_out, cudaStream_t st) {
   FB_REQUIRE(gpq && gpk && bucket_of_rel && out && H == h * 64, "fb_rel_to_bucket: bad args");
-  FB_CHECK_CUDA(launch_pdl(rel_to_bucket_kernel, dim3((rel_rows + 3) / 4, h, 2), dim3(256), 0, st, gpq, gpk, H, h,
-                           bucket_of_rel, rel_rows, rel_off, L, out, ldo));
+  FB_REQUIRE(nb >= 1 && nb <= 32767, "fb_rel_to_bucket: bad batch %d", nb);
+  FB_CHECK_CUDA(launch_pdl(rel_to_bucket_kernel, dim3((rel_rows + 3) / 4, h, 2 * nb), dim3(256), 0, st, gpq, gpk, H, h,
+                           bucket_of_rel, rel_rows, rel_off, L, out, ldo, stride_out));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1237,13 +1254,24 @@ int fb_attn_bwd_prep(const fb_attn_bwd_prep_args* args, void* stream) {
 }
 int fb_rel_to_bucket(const float* gpq, const float* gpk, int H, int h, const int* bucket_of_rel, int rel_rows,
                      int rel_off, int L, float* out, long long ldo, void* stream) {
-  return fb::rel_to_bucket(gpq, gpk, H, h, bucket_of_rel, rel_rows, rel_off, L, out, ldo,
+  return fb::rel_to_bucket(gpq, gpk, H, h, bucket_of_rel, rel_rows, rel_off, L, out, ldo, 1, 0,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+int fb_rel_to_bucket_batched(const float* gpq, const float* gpk, int H, int h, const int* bucket_of_rel, int rel_rows,
+                             int rel_off, int L, float* out, long long ldo, int nb, long long stride_out, void* stream) {
+  return fb::rel_to_bucket(gpq, gpk, H, h, bucket_of_rel, rel_rows, rel_off, L, out, ldo, nb, stride_out,
                            reinterpret_cast<cudaStream_t>(stream));
 }
 int fb_attn_fwd(const fb_attn_args* args, void* stream) { return fb::attn_fwd(args, reinterpret_cast<cudaStream_t>(stream)); }
 int fb_build_rel_tables(const void* pqk, long long ld, int H, int h, const int* bucket_of_rel, int rel_rows,
                         int rel_off, int L, void* out_pq, void* out_pk, void* out_pk_rev, void* stream) {
-  return fb::build_rel_tables(pqk, ld, H, h, bucket_of_rel, rel_rows, rel_off, L, out_pq, out_pk, out_pk_rev,
+  return fb::build_rel_tables(pqk, ld, H, h, bucket_of_rel, rel_rows, rel_off, L, out_pq, out_pk, out_pk_rev, 1, 0,
                               reinterpret_cast<cudaStream_t>(stream));
+}
+int fb_build_rel_tables_batched(const void* pqk, long long ld, int H, int h, const int* bucket_of_rel, int rel_rows,
+                                int rel_off, int L, void* out_pq, void* out_pk, void* out_pk_rev, int nb,
+                                long long stride_pqk, void* stream) {
+  return fb::build_rel_tables(pqk, ld, H, h, bucket_of_rel, rel_rows, rel_off, L, out_pq, out_pk, out_pk_rev, nb,
+                              stride_pqk, reinterpret_cast<cudaStream_t>(stream));
 }
 }

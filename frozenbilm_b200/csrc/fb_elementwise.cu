@@ -476,6 +476,48 @@ __global__ void dropout_kernel(const float* __restrict__ x, int M, int N, DropSp
   if (out16) *reinterpret_cast<uint2*>(out16 + i4) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
 }
 
+// The same dropout for ALL layer passes of a step in one launch (the per-pass positional chain, engine.py):
+//   expand (out16 != null): out16[b][r][c] = dropout_b(x[r][c])            x shared by the nb passes
+//   reduce (out32 != null): out32[r][c]   += sum_b dropout_b(x[b][r][c])   (the backward: dR accumulates over passes)
+// pass b uses the site offset d.off_lo + b * off_stride and element id (r, c): bit-identical to nb calls of
+// dropout_kernel with those offsets.
+__global__ void dropout_batched_kernel(const float* __restrict__ x, int M, int N, int nb, DropSpec d, uint32_t off_stride,
+                                       float* __restrict__ out32, __nv_bfloat16* __restrict__ out16) {
+  pdl_prologue();
+  const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const long long MN = (long long)M * N;
+  if (i4 >= MN) return;
+  const int row = (int)(i4 / N), col = (int)(i4 % N);
+  const bool reduce = out32 != nullptr;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!reduce) v = *reinterpret_cast<const float4*>(x + i4);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int b = 0; b < nb; ++b) {
+    if (reduce) v = *reinterpret_cast<const float4*>(x + b * MN + i4);
+    float o[4] = {v.x, v.y, v.z, v.w};
+    if (d.thresh16) {
+      DropSpec db = d;
+      db.off_lo = d.off_lo + (uint32_t)b * off_stride;
+      float f[4];
+      drop_factors4(db, (uint32_t)row, col, f);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] *= f[e];
+    }
+    if (reduce) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e] += o[e];
+    } else {
+      *reinterpret_cast<uint2*>(out16 + b * MN + i4) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+    }
+  }
+  if (reduce) {
+    float4* p = reinterpret_cast<float4*>(out32 + i4);
+    float4 q = *p;
+    q.x += acc[0]; q.y += acc[1]; q.z += acc[2]; q.w += acc[3];
+    *p = q;
+  }
+}
+
 __global__ void gelu_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat16* __restrict__ pre, int M, int N,
                                 const uint8_t* __restrict__ rowmask, DropSpec d, __nv_bfloat16* __restrict__ out) {
   pdl_prologue();
@@ -771,6 +813,17 @@ int fb_dropout_apply(const float* x, int M, int N, const fb_dropout* drop, float
   const long long n4 = (long long)M * N / 4;
   FB_CHECK_CUDA(launch_pdl(dropout_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, ST(stream), x, M, N,
                            drop_from(drop), out_f32, accumulate, (__nv_bfloat16*)out_bf16));
+  count_launch();
+  FB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int fb_dropout_batched(const float* x, int M, int N, int nb, const fb_dropout* drop, unsigned long long offset_stride,
+                       float* out_f32_accum, void* out_bf16, void* stream) {
+  FB_REQUIRE(x && M > 0 && N > 0 && N % 8 == 0 && nb > 0, "fb_dropout_batched: bad args (N must be a multiple of 8)");
+  FB_REQUIRE((out_f32_accum != nullptr) != (out_bf16 != nullptr), "fb_dropout_batched: exactly one of the outputs");
+  const long long n4 = (long long)M * N / 4;
+  FB_CHECK_CUDA(launch_pdl(fb::dropout_batched_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, ST(stream), x, M, N,
+                           nb, drop_from(drop), (uint32_t)offset_stride, out_f32_accum, (__nv_bfloat16*)out_bf16));
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -52,7 +52,7 @@ struct GemmParams {
   int mblocks, nblocks, kblocks, split_k, kblocks_per_split, total_tiles;
   void* D; long long ldd, stride_d; int d_f32;
   float alpha;
-  const float* bias;
+  const float* bias; long long stride_bias;   // stride_bias: bias offset per OUTER batch (batched mode only)
   __nv_bfloat16* D_pre; long long ld_pre;
   int act;
   const __nv_bfloat16* aux; long long ld_aux; int aux_op;
@@ -92,9 +92,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * p.alpha;
   if (first_split) {
     if (p.bias) {
+      const float* bias = p.bias + (long long)(b / p.batch_inner) * p.stride_bias;
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (full || col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+        if (full || col0 + i < p.N) v[i] += __ldg(bias + col0 + i);
     }
     if (p.rowmask && p.rowmask[row] == 0) {
 #pragma unroll
@@ -933,6 +934,7 @@ int gemm(const fb_gemm_args* a, cudaStream_t st) {
   p.D = a->D; p.ldd = a->ldd; p.stride_d = a->stride_d; p.d_f32 = (a->d_dtype == FB_DT_F32);
   p.alpha = a->alpha;
   p.bias = a->bias;
+  p.stride_bias = (batch_total > 1) ? a->stride_bias : 0;
   p.D_pre = reinterpret_cast<__nv_bfloat16*>(a->D_pre); p.ld_pre = a->ld_pre;
   p.act = a->act;
   p.aux = reinterpret_cast<const __nv_bfloat16*>(a->aux); p.ld_aux = a->ld_aux;

@@ -163,6 +163,10 @@ class DebertaEngine:
         # Measured at config 2: 71.9 ms/step vs 71.1 ms without -- a running low-priority GEMM CTA is not preempted, so
         # the [512 x 2H x H] projection delays the chain more than the three launches it takes off it.  Off by default.
         self.rel_prefetch = self.dw_side_stream and os.environ.get("FB_REL_PREFETCH", "0") == "1"
+        # FB_REL_BATCHED=0: build the positional tables pass by pass inside the chain (three launches per pass) instead
+        # of for all passes up front (_rel_tables_all)
+        self.rel_batched = os.environ.get("FB_REL_BATCHED", "1") != "0"
+        self._rel_bwd_batched = False
         self.attn_scale = 1.0 / math.sqrt(3 * 64)             # deberta.py:769-777
         self.layer_prefix = self.LAYER_PREFIX
         if cfg.hidden_size % 128 != 0:
@@ -183,13 +187,20 @@ class DebertaEngine:
         H = cfg.hidden_size
         BF16 = self.AD   # fp32-class mode keeps the operands unrounded (split at the GEMM)
         with torch.no_grad():
-            for i in range(cfg.num_hidden_layers):
+            # Q|K|V weights of ALL layers in one [NL, 3H, H] tensor (constant layer stride): the positional projections
+            # of every layer pass are one batched GEMM (_rel_tables_all)
+            NL = cfg.num_hidden_layers
+            W["qkv.w.all"] = torch.empty(NL, 3 * H, H, device=self.device, dtype=BF16)
+            W["qkv.b.all"] = torch.empty(NL, 3 * H, device=self.device, dtype=F32)
+            for i in range(NL):
                 p = f"deberta.encoder.layer.{i}."
                 a = p + "attention.self."
-                W[f"qkv.w.{i}"] = torch.cat([P[a + "query_proj.weight"], P[a + "key_proj.weight"],
-                                             P[a + "value_proj.weight"]], 0).to(BF16).contiguous()
-                W[f"qkv.b.{i}"] = torch.cat([P[a + "query_proj.bias"], P[a + "key_proj.bias"],
-                                             P[a + "value_proj.bias"]], 0).float().contiguous()
+                W[f"qkv.w.{i}"] = W["qkv.w.all"][i]
+                W[f"qkv.b.{i}"] = W["qkv.b.all"][i]
+                for j, n in enumerate(("query_proj", "key_proj", "value_proj")):
+                    W[f"qkv.w.{i}"][j * H:(j + 1) * H].copy_(P[a + n + ".weight"])
+                W[f"qkv.b.{i}"].copy_(torch.cat([P[a + "query_proj.bias"], P[a + "key_proj.bias"],
+                                                 P[a + "value_proj.bias"]], 0))
                 W[f"o.w.{i}"] = P[p + "attention.output.dense.weight"].to(BF16).contiguous()
                 W[f"ffn1.w.{i}"] = P[p + "intermediate.dense.weight"].to(BF16).contiguous()
                 W[f"ffn2.w.{i}"] = P[p + "output.dense.weight"].to(BF16).contiguous()
@@ -339,6 +350,8 @@ class DebertaEngine:
         self._R32_event = torch.cuda.current_stream().record_event() if (self.use_rel and self.rel_prefetch) else None
         # the positional tables of pass p + 1 are built on the side stream while pass p runs
         pass_layers = list(range(NL - 1)) + [NL - 1, NL - 1]
+        if self.use_rel and self.rel_batched and not self.precise:
+            self._rel_tables_all(L, pass_layers)
         self._rel_tables_prefetch(pass_layers[0], 0, L)
 
         # ---- encoder: NL-1 ordinary passes (the NL-th only feeds hidden_states[-1], which nothing reads)
@@ -420,6 +433,47 @@ class DebertaEngine:
         pkr = tws.get("PKrev" + tagk, (h, rel_rows, 64), BF16) if (self.training and self.fused_attn_bwd) else None
         lib.build_rel_tables(pqk, self.bucket_of_rel, L, h, out_pq=pq, out_pk=pk, out_pk_rev=pkr)
         return (pq, pk, pkr)
+
+    def _rel_tables_all(self, L, pass_layers):
+        """PQrel / PKrel of EVERY layer pass of this forward in four launches (dropout, one batched GEMM over the
+        layers, the trailing passes that reuse the last layer, the table expansion) instead of three per pass inside
+        the chain: the projections depend on the relative embeddings and the frozen weights only, never on the
+        activations.  Same per-pass dropout sites as _rel_tables_compute (bit-identical tables)."""
+        cfg, W, ws = self.cfg, self.W, self.ws
+        H, h, NL = cfg.hidden_size, cfg.num_attention_heads, cfg.num_hidden_layers
+        S2 = 2 * cfg.position_buckets
+        if pass_layers[:NL] != list(range(NL)):
+            return                                     # unexpected pass order: the per-pass path handles it
+        p = cfg.hidden_dropout_prob if self.training else 0.0
+        tws = self.sws if self.training else ws
+        wall, ball = W["qkv.w.all"], W["qkv.b.all"]
+        if p == 0.0:
+            # without dropout the tables only depend on the LAYER
+            keys = [("L", l) for l in range(NL)]
+            Rd16 = ws.get("Rd16", (S2, H), BF16)
+            lib.dropout_apply(self._R32, self.drop(0.0, SITE_POS), out16=Rd16)
+            pqk = ws.get("pqk16.all", (NL, S2, 2 * H), BF16)
+            lib.gemm(Rd16, wall[0][:2 * H], pqk[0], bias=ball[0][:2 * H],
+                     batch={"outer": (NL, 0, 3 * H * H, S2 * 2 * H), "bias_stride": 3 * H})
+        else:
+            NP = len(pass_layers)
+            keys = [("P", q) for q in range(NP)]
+            Rd16 = ws.get("Rd16.all", (NP, S2, H), BF16)
+            lib.dropout_batched(self._R32, self.drop(p, SITE_POS), 8, out16=Rd16)     # pass q: site q * 8 + SITE_POS
+            pqk = ws.get("pqk16.all", (NP, S2, 2 * H), BF16)
+            lib.gemm(Rd16[0], wall[0][:2 * H], pqk[0], bias=ball[0][:2 * H],
+                     batch={"outer": (NL, S2 * H, 3 * H * H, S2 * 2 * H), "bias_stride": 3 * H})
+            for q in range(NL, NP):                    # the enhanced-mask-decoder passes reuse the last layer
+                l = pass_layers[q]
+                lib.gemm(Rd16[q], wall[l][:2 * H], pqk[q], bias=ball[l][:2 * H])
+        nb = len(keys)
+        rel_rows, _ = lib.rel_table_geometry(L)
+        pq = tws.get("PQrel.all", (nb, h, rel_rows, 64), BF16)
+        pk = tws.get("PKrel.all", (nb, h, rel_rows, 64), BF16)
+        pkr = tws.get("PKrev.all", (nb, h, rel_rows, 64), BF16) if (self.training and self.fused_attn_bwd) else None
+        lib.build_rel_tables_batched(pqk, self.bucket_of_rel, L, h, pq, pk, pkr)
+        for j, key in enumerate(keys):
+            self._rel_tables_cache[key] = ((pq[j], pk[j], pkr[j] if pkr is not None else None), None)
 
     def _rel_tables_prefetch(self, layer, pass_id, L):
         """Issues the table construction of a LATER pass on the low-priority side stream: it only depends on the
@@ -671,6 +725,11 @@ class DebertaEngine:
         H = cfg.hidden_size
         self._dR32 = ws.get("bw.dR32", (2 * cfg.position_buckets, H), F32, zero=True)
         passes = sv["passes"]
+        # batched positional-gradient chain: the passes are layers 0 .. NL-1 in order, then repeats of the last layer
+        self._rel_bwd_batched = (self.use_rel and self.rel_batched and not self.precise and self.fused_attn_bwd and
+                                 [r["layer"] for r in passes[:cfg.num_hidden_layers]] ==
+                                 list(range(min(cfg.num_hidden_layers, len(passes)))) and
+                                 all(r["pass_id"] == k for k, r in enumerate(passes)))
         NL = cfg.num_hidden_layers
         last = NL - 1
         # ---- enhanced mask decoder passes (reverse): shared K/V projection of h[-2]
@@ -703,6 +762,12 @@ class DebertaEngine:
             lib.conv_col2im(dcol16, B, L, H, dx32, accumulate=True)
         self._bwd_embeddings(dx32, "deberta.embeddings.", rowmask=self.mask_u8)
         # ---- relative-embedding LayerNorm (trainable under ft_ln): gamma/beta only, the table is frozen
+        if self._rel_bwd_batched:
+            if self._side is not None and self.rel_side_stream:
+                with torch.cuda.stream(self._side):
+                    self._bwd_rel_all()
+            else:
+                self._bwd_rel_all()
         if self._side is not None and self.rel_side_stream:
             torch.cuda.current_stream().wait_stream(self._side)   # dR has been accumulated on the side stream
         lib.layernorm_bwd(self._dR32, P[c + "rel_embeddings.weight"], sv["rel_mean"], sv["rel_rstd"],
@@ -838,13 +903,21 @@ class DebertaEngine:
         if not rel:
             return
         rel_rows, _ = lib.rel_table_geometry(L)
-        gpk = ws.get("bw.gpk", (h, rel_rows, 64), F32)
-        gpq = ws.get("bw.gpq", (h, rel_rows, 64), F32)
+        batched = self._rel_bwd_batched
+        if batched:
+            # every pass keeps its band gradients; the chain down to dR runs ONCE for all passes (_bwd_rel_all)
+            NP = len(self.saved["passes"])
+            gpk = ws.get("bw.gpk.all", (NP, h, rel_rows, 64), F32)[pass_id]
+            gpq = ws.get("bw.gpq.all", (NP, h, rel_rows, 64), F32)[pass_id]
+        else:
+            gpk = ws.get("bw.gpk", (h, rel_rows, 64), F32)
+            gpq = ws.get("bw.gpq", (h, rel_rows, 64), F32)
 
         def positional_grads():
             lib.attn_bwd_rel(ds, Q, K, gpk, gpq, B=B, L=L, h=h, scale=self.attn_scale,
                              units_per_cta=self.rel_side_units if side is not None else 0)
-            self._bwd_rel_tables(gpq, gpk, i, pass_id, L, h)
+            if not batched:
+                self._bwd_rel_tables(gpq, gpk, i, pass_id, L, h)
 
         if side is None:
             positional_grads()
@@ -853,6 +926,32 @@ class DebertaEngine:
             side.wait_event(ev)
             with torch.cuda.stream(side):
                 positional_grads()
+
+    def _bwd_rel_all(self):
+        """d(per-relative-position tables) of ALL passes -> d(Linear_{q|k}(dropout(R))) -> dR in five launches (fold
+        onto the bucket rows, cast, one batched GEMM over the layers + the trailing passes, dropout backward summed
+        over the passes) instead of five per pass; the mirror image of _rel_tables_all."""
+        cfg, W, ws = self.cfg, self.W, self.ws
+        B, L, F, Lt, T = self.dims
+        H, h, NL = cfg.hidden_size, cfg.num_attention_heads, cfg.num_hidden_layers
+        S2 = 2 * cfg.position_buckets
+        passes = self.saved["passes"]
+        NP = len(passes)
+        rel_rows, _ = lib.rel_table_geometry(L)
+        gpk = ws.get("bw.gpk.all", (NP, h, rel_rows, 64), F32)
+        gpq = ws.get("bw.gpq.all", (NP, h, rel_rows, 64), F32)
+        dpqk32 = ws.get("bw.dpqk32.all", (NP, S2, 2 * H), F32, zero=True)
+        lib.rel_to_bucket_batched(gpq, gpk, self.bucket_of_rel, L, h, dpqk32)
+        dpqk16 = ws.get("bw.dpqk16.all", (NP, S2, 2 * H), BF16)
+        lib.cast_bf16(dpqk32, dpqk16)
+        dRd32 = ws.get("bw.dRd32.all", (NP, S2, H), F32)
+        wall = W["qkv.w.all"]
+        nlead = min(NL, NP)
+        lib.gemm(dpqk16[0], wall[0][:2 * H], dRd32[0], b_mn_major=True,
+                 batch={"outer": (nlead, S2 * 2 * H, 3 * H * H, S2 * H)})
+        for q in range(nlead, NP):
+            lib.gemm(dpqk16[q], wall[passes[q]["layer"]][:2 * H], dRd32[q], b_mn_major=True)
+        lib.dropout_batched(dRd32, self.drop(cfg.hidden_dropout_prob, SITE_POS), 8, out32_accum=self._dR32)
 
     def _bwd_rel_tables(self, gpq, gpk, i, pass_id, L, h):
         """d(per-relative-position tables) -> d(Linear_{q|k}(dropout(R))) -> accumulate dR (deberta.py:847-853)."""

@@ -51,6 +51,7 @@ class GemmArgs(C.Structure):
         ("stride_d_in", C.c_longlong),
         ("rowmask", C.c_void_p),
         ("drop", Dropout), ("drop_pos", C.c_int),
+        ("stride_bias", C.c_longlong),
     ]
 
 
@@ -206,6 +207,9 @@ def _load(path, exports) -> C.CDLL:
     lib.fb_cast_f32_bf16.argtypes = [vp, ll, vp, vp]
     lib.fb_build_rel_tables.argtypes = [vp, ll, i, i, vp, i, i, i, vp, vp, vp, vp]
     lib.fb_rel_to_bucket.argtypes = [vp, vp, i, i, vp, i, i, i, vp, ll, vp]
+    lib.fb_build_rel_tables_batched.argtypes = [vp, ll, i, i, vp, i, i, i, vp, vp, vp, i, ll, vp]
+    lib.fb_rel_to_bucket_batched.argtypes = [vp, vp, i, i, vp, i, i, i, vp, ll, i, ll, vp]
+    lib.fb_dropout_batched.argtypes = [vp, i, i, i, dp, C.c_ulonglong, vp, vp, vp]
     lib.fb_mlm_corrupt.argtypes = [vp, vp, ll, ll, ll, ll, f, C.c_ulonglong, vp, vp, vp]
     lib.fb_gather_frames.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp]
     lib.fb_softmax_topk.argtypes = [vp, ll, i, i, i, vp, ll, vp, vp, vp]
@@ -226,6 +230,7 @@ EXPORTS = [
     "fb_mlm_corrupt", "fb_gather_frames", "fb_gemm_cluster_capacity",
     "fb_split3", "fb_epilogue_f32", "fb_colsum_f32", "fb_conv_im2col_f32", "fb_conv_col2im_f32",
     "fb_cross_entropy_f32", "fb_attn_fwd_f32", "fb_attn_bwd_f32", "fb_softmax_topk", "fb_sumsq_det", "fb_set_pdl",
+    "fb_build_rel_tables_batched", "fb_rel_to_bucket_batched", "fb_dropout_batched",
 ]
 # include/frozenbilm_b200_debug.h: only in libfrozenbilm_sm100_dbg.so
 DEBUG_EXPORTS = ["fb_umma_probe", "fb_attn_bwd_set_debug"]
@@ -275,10 +280,12 @@ def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, a_mn_major=False,
     nbatch = 1
     sa = sb = sd = 0
     bin_, sai, sbi, sdi = 1, 0, 0, 0
+    args_stride_bias = 0
     if batch is not None:
         # explicit batching over 2-D base views: batch = dict(outer=(n, sa, sb, sd), inner=(n, sa, sb, sd))
         A2, B2, D2 = A, B, D
         nbatch, sa, sb, sd = batch.get("outer", (1, 0, 0, 0))
+        args_stride_bias = int(batch.get("bias_stride", 0))
         bin_, sai, sbi, sdi = batch.get("inner", (1, 0, 0, 0))
     elif A.dim() == 3:
         nbatch = A.shape[0]
@@ -309,6 +316,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, D: torch.Tensor, *, a_mn_major=False,
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous()
     args.bias = _ptr(bias)
+    args.stride_bias = args_stride_bias
     if D_pre is not None:
         assert D_pre.dtype == torch.bfloat16
         args.D_pre, args.ld_pre = _ptr(D_pre), D_pre.stride(0)
@@ -453,6 +461,20 @@ def build_rel_tables(pqk: torch.Tensor, bucket_of_rel: torch.Tensor, L: int, h: 
                                      rel_off, L, _ptr(out_pq), _ptr(out_pk), _ptr(out_pk_rev), stream_ptr()),
           "fb_build_rel_tables")
     return out_pq, out_pk
+
+
+def build_rel_tables_batched(pqk: torch.Tensor, bucket_of_rel: torch.Tensor, L: int, h: int, out_pq, out_pk,
+                             out_pk_rev=None):
+    """pqk: bf16 [nb, 2S, 2H]; out_*: bf16 [nb, h, rel_rows, 64] (contiguous): the tables of nb layer passes in ONE
+    launch."""
+    nb, _, H2 = pqk.shape
+    rel_rows, rel_off = rel_table_geometry(L)
+    for t in (out_pq, out_pk, out_pk_rev):
+        assert t is None or (t.is_contiguous() and tuple(t.shape) == (nb, h, rel_rows, 64) and t.dtype == torch.bfloat16)
+    assert pqk.dtype == torch.bfloat16 and pqk.stride(2) == 1
+    check(load().fb_build_rel_tables_batched(_ptr(pqk), C.c_longlong(pqk.stride(1)), H2 // 2, h, _ptr(bucket_of_rel),
+                                             rel_rows, rel_off, L, _ptr(out_pq), _ptr(out_pk), _ptr(out_pk_rev), nb,
+                                             C.c_longlong(pqk.stride(0)), stream_ptr()), "fb_build_rel_tables_batched")
 
 
 def attn_fwd(Q, K, V, PKrel, PQrel, mask_u8, ctx, lse, *, B, L, h, scale, dropout_p=0.0, seed=0, offset=0,
@@ -605,6 +627,20 @@ def dropout_apply(x32, dropout, *, out32=None, accumulate=False, out16=None):
                                   stream_ptr()), "fb_dropout_apply")
 
 
+def dropout_batched(x32, dropout, offset_stride, *, out16=None, out32_accum=None):
+    """nb layer passes of fb_dropout_apply in one launch (pass b: site offset + b * offset_stride).
+    out16 [nb, M, N] bf16 = dropout_b(x32 [M, N])   |   out32_accum [M, N] fp32 += sum_b dropout_b(x32 [nb, M, N])."""
+    if out16 is not None:
+        nb, M, N = out16.shape
+        assert out16.is_contiguous() and tuple(x32.shape) == (M, N) and out32_accum is None
+    else:
+        nb, M, N = x32.shape
+        assert tuple(out32_accum.shape) == (M, N) and out32_accum.is_contiguous()
+    assert x32.is_contiguous() and x32.dtype == torch.float32
+    check(load().fb_dropout_batched(_ptr(x32), M, N, nb, _dp(dropout), int(offset_stride), _ptr(out32_accum),
+                                    _ptr(out16), stream_ptr()), "fb_dropout_batched")
+
+
 def sumsq(g, out):
     check(load().fb_sumsq(_ptr(g), g.numel(), _ptr(out), stream_ptr()), "fb_sumsq")
 
@@ -707,6 +743,16 @@ def rel_to_bucket(gpq, gpk, bucket_of_rel, L, h, out):
     H = h * 64
     check(load().fb_rel_to_bucket(_ptr(gpq), _ptr(gpk), H, h, _ptr(bucket_of_rel), rel_rows, rel_off, L, _ptr(out),
                                   out.stride(0), stream_ptr()), "fb_rel_to_bucket")
+
+
+def rel_to_bucket_batched(gpq, gpk, bucket_of_rel, L, h, out):
+    """gpq/gpk: fp32 [nb, h, rel_rows, 64]; out: fp32 [nb, 2S, 2H], ACCUMULATES."""
+    rel_rows, rel_off = rel_table_geometry(L)
+    nb = gpq.shape[0]
+    assert gpq.is_contiguous() and gpk.is_contiguous() and out.shape[0] == nb
+    check(load().fb_rel_to_bucket_batched(_ptr(gpq), _ptr(gpk), h * 64, h, _ptr(bucket_of_rel), rel_rows, rel_off, L,
+                                          _ptr(out), out.stride(1), nb, C.c_longlong(out.stride(0)), stream_ptr()),
+          "fb_rel_to_bucket_batched")
 
 
 def mlm_corrupt(ids: torch.Tensor, special_mask, pad_id, mask_id: int, vocab: int, mlm_probability: float, seed: int,

@@ -74,6 +74,7 @@ typedef struct fb_gemm_args {
   const unsigned char* rowmask;  /* optional uint8 [M]: v = 0 for rows with rowmask == 0 (after bias) */
   fb_dropout drop; int drop_pos; /* 0 none, 1 = after bias/rowmask (before D_pre and act),
                                     2 = after act/aux (before resid); element id = (row, col) */
+  long long stride_bias;         /* batched mode: outer batch o uses bias + o * stride_bias (0 = one shared bias) */
 } fb_gemm_args;
 
 int fb_gemm(const fb_gemm_args* args, void* stream);
@@ -132,6 +133,10 @@ typedef struct fb_attn_bwd_prep_args {
 int fb_attn_bwd_prep(const fb_attn_bwd_prep_args* args, void* stream);
 int fb_rel_to_bucket(const float* gpq, const float* gpk, int H, int h, const int* bucket_of_rel, int rel_rows,
                      int rel_off, int L, float* out, long long ldo, void* stream);
+/* The same for nb layer passes in one launch: gpq / gpk are [nb, h, rel_rows, 64], pass b accumulates into
+ * out + b * stride_out. */
+int fb_rel_to_bucket_batched(const float* gpq, const float* gpk, int H, int h, const int* bucket_of_rel, int rel_rows,
+                             int rel_off, int L, float* out, long long ldo, int nb, long long stride_out, void* stream);
 
 /* Fused attention backward (same autograd, deberta.py:769-808 / 820-947 / XSoftmax :134-138 / XDropout :188-194),
  * one tcgen05 kernel per layer pass instead of the staged schedule above: one CTA per (batch, head) recomputes
@@ -183,6 +188,12 @@ int fb_attn_bwd_rel(const fb_attn_bwd_rel_args* args, void* stream);
  * out_pk with its rows reversed (row r <-> rel_rows - 1 - r): the operand fb_attn_bwd wants. */
 int fb_build_rel_tables(const void* pqk, long long ld, int H, int h, const int* bucket_of_rel, int rel_rows,
                         int rel_off, int L, void* out_pq, void* out_pk, void* out_pk_rev, void* stream);
+/* The tables of nb layer passes in one launch (the positional projections do not depend on the activations, so the
+ * host side builds them for the whole forward up front): pass b reads pqk + b * stride_pqk (elements) and writes
+ * out_* + b * h * rel_rows * 64. */
+int fb_build_rel_tables_batched(const void* pqk, long long ld, int H, int h, const int* bucket_of_rel, int rel_rows,
+                                int rel_off, int L, void* out_pq, void* out_pk, void* out_pk_rev, int nb,
+                                long long stride_pqk, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * HBM-bound row kernels (fb_elementwise.cu).  All matrices are dense row-major [M, H].
@@ -229,6 +240,12 @@ int fb_softmax_topk(const float* logits, long long ld, int P, int V, int k, floa
 /* out = dropout(x) as fp32 (optionally accumulating) and/or bf16: relative-embedding dropout, deberta.py:779. */
 int fb_dropout_apply(const float* x, int M, int N, const fb_dropout* drop, float* out_f32, int accumulate,
                      void* out_bf16, void* stream);
+/* fb_dropout_apply for nb layer passes in one launch; pass b uses the site offset drop->offset + b * offset_stride and
+ * element ids (row, col) (bit-identical to nb separate calls).  Exactly one output:
+ *   out_bf16 [nb, M, N]     = dropout_b(x [M, N])                      (x shared by the passes)
+ *   out_f32_accum [M, N]   += sum_b dropout_b(x [nb, M, N])            (backward: dR accumulates over the passes) */
+int fb_dropout_batched(const float* x, int M, int N, int nb, const fb_dropout* drop, unsigned long long offset_stride,
+                       float* out_f32_accum, void* out_bf16, void* stream);
 /* clip_grad_norm_ + Adam over a flat fp32 bucket (main.py:82-84, args.py:246-275), refreshing the bf16 copy. */
 int fb_sumsq(const float* g, long long n, float* out, void* stream);
 /* Same sum of squares, OVERWRITING *out, with a fixed summation order (bit-identical on every data-parallel rank for

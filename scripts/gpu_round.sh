@@ -1,8 +1,8 @@
 #!/bin/bash
+# scratch: the command of the most recent gpurun call
 mkdir -p gpurun_out
-timeout 200 python scripts/gpu_probe_kernels.py 2>&1 | tail -5
-timeout 200 python scripts/gpu_sanitize.py 2>&1 | tail -3
-for tool in memcheck racecheck; do
-  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python scripts/gpu_sanitize.py > gpurun_out/sanitizer_$tool.log 2>&1
-  echo "sanitizer $tool exit $?"; tail -4 gpurun_out/sanitizer_$tool.log
-done
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/pytest_gpu.log; tail -6 gpurun_out/pytest_gpu.log
+timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench_relbatched.json 2> gpurun_out/bench_relbatched.err
+cut -c1-330 gpurun_out/bench_relbatched.json; tail -3 gpurun_out/bench_relbatched.err
+FB_REL_BATCHED=0 timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench_relbatched0.json 2> gpurun_out/bench_relbatched0.err
+cut -c1-330 gpurun_out/bench_relbatched0.json
