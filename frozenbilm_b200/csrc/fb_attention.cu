@@ -294,7 +294,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_xfree);
+      if constexpr (REL) {          // (plain attention has no X2 / X1 hand-over: nobody waits on this barrier)
+        if (lane == 0) mbar_arrive(bar_xfree);
+      }
       if (kb > 0) accumulate_o(kb - 1);
       mbar_wait(bar_mma2, ph);
       tc_fence_after();
@@ -790,7 +792,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_xfree);
+      if constexpr (REL) {          // (plain attention has no X2 / X1 hand-over: nobody waits on this barrier)
+        if (lane == 0) mbar_arrive(bar_xfree);
+      }
       if (kb > 0) accumulate_o(kb - 1);
       if constexpr (REL) {
         mbar_wait(bar_mma2, ph);

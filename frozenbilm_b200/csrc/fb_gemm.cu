@@ -30,7 +30,11 @@ namespace fb {
 static constexpr int BM = 128;
 static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 static constexpr int A_STAGE_BYTES = BM * BK * 2;
-static constexpr int NUM_THREADS = 384;  // warps 0-2: TMA / MMA / TMEM alloc, warp 3 idle, warps 4-11: epilogue
+// warps 0-2: TMA / MMA / TMEM alloc, warp 3 idle, then EG epilogue warpgroups (EG = 2: warps 4-11).  EG = 3 (BN = 192
+// only: 6 chunks of 32 columns, two per group) gives ALU-heavy epilogues (erf-GELU + second output, GELU' x aux, fp32
+// residual) three warps per scheduler instead of two: they are bound by the issue rate of the epilogue warps.
+static constexpr int NUM_THREADS = 384;
+__host__ __device__ constexpr int gemm_threads(int eg) { return 128 + 128 * eg; }
 
 template <int BN>
 struct GemmCfg {
@@ -41,6 +45,7 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int STORE_STAGE_BYTES = 16384;  // one 128 x 32 chunk (fp32) per epilogue warpgroup
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STORE_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int smem_bytes(int eg) { return STAGES * STAGE_BYTES + eg * STORE_STAGE_BYTES + 1024 + 256; }
 };
 
 struct GemmParams {
@@ -318,8 +323,8 @@ __device__ __forceinline__ void decode_tile_cl(const GemmParams& p, int t, uint3
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, bool COAL, int CL>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, bool A_MN, bool B_MN, bool COAL, int CL, int EG = 2>
+__global__ void __launch_bounds__(gemm_threads(EG), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_d, const __grid_constant__ CUtensorMap map_pre,
             const __grid_constant__ GemmParams p) {
@@ -331,7 +336,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::STAGES * A_STAGE_BYTES;
   uint8_t* smem_store = smem + Cfg::STAGES * Cfg::STAGE_BYTES;   // 2 x 16 KB epilogue staging (TMA stores)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_store + 2 * Cfg::STORE_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_store + EG * Cfg::STORE_STAGE_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + Cfg::STAGES;
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
@@ -357,7 +362,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);
+      mbar_init(&tempty_bar[s], 4 * EG);
     }
     fence_barrier_init();
   }
@@ -469,9 +474,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int wq = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;   // which half of the tile's 32-column chunks this warpgroup drains
-    constexpr int CHUNKS = BN / 32, HALF_CHUNKS = (CHUNKS + 1) / 2;
-    const int c_begin = half * HALF_CHUNKS, c_end = (half == 0) ? HALF_CHUNKS : CHUNKS;
+    const int grp = (warp - 4) >> 2;    // which share of the tile's 32-column chunks this warpgroup drains
+    constexpr int CHUNKS = BN / 32, GRP_CHUNKS = (CHUNKS + EG - 1) / EG;
+    const int c_begin = grp * GRP_CHUNKS, c_end = (c_begin + GRP_CHUNKS < CHUNKS) ? c_begin + GRP_CHUNKS : CHUNKS;
     uint32_t nstore = 0;
     int it = 0;
     for (int tile = tile_first; tile < tile_total; tile += tile_step, ++it) {
@@ -764,18 +769,21 @@ static int make_tmap_operand(CUtensorMap* out, const void* ptr, uint64_t inner, 
   return make_tmap_bf16_nd(out, ptr, 4, dims, strides, box);
 }
 
-template <int BN, bool A_MN, bool B_MN, bool COAL, int CL>
+template <int BN, bool A_MN, bool B_MN, bool COAL, int CL, int EG = 2>
 static int launch_gemm_impl(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const CUtensorMap& mpre,
                             const GemmParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   static int max_clusters = 0;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, COAL, CL>;
+  constexpr int NUM_THREADS = gemm_threads(EG);
+  constexpr int SMEM = Cfg::smem_bytes(EG);
+  static_assert(SMEM <= 232448, "shared memory budget");
+  auto kern = gemm_kernel<BN, A_MN, B_MN, COAL, CL, EG>;
   if (!configured) {
-    FB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    FB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     if (CL > 1) {
       cudaLaunchConfig_t qc = {};
-      qc.gridDim = dim3(CL * 64); qc.blockDim = dim3(NUM_THREADS); qc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      qc.gridDim = dim3(CL * 64); qc.blockDim = dim3(NUM_THREADS); qc.dynamicSmemBytes = SMEM;
       cudaLaunchAttribute qa[1];
       qa[0].id = cudaLaunchAttributeClusterDimension;
       qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
@@ -788,11 +796,11 @@ static int launch_gemm_impl(const CUtensorMap& ma, const CUtensorMap& mb, const 
   if (CL == 1) {
     int grid = std::min(p.total_tiles, num_sms());
     FB_REQUIRE(grid > 0, "no CUDA device / empty GEMM");
-    FB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES, st, ma, mb, md, mpre, p));
+    FB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), SMEM, st, ma, mb, md, mpre, p));
   } else {
     const int clusters = std::min(p.total_tiles / CL, max_clusters);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(clusters * CL); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.gridDim = dim3(clusters * CL); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -820,6 +828,16 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUten
       (!has_res || (((reinterpret_cast<uintptr_t>(p.resid) & 15) == 0) && (p.ld_resid & 3) == 0));
   if constexpr (!A_MN && (BN == 256 || BN == 192)) {
     if (cluster_ok) {
+      if constexpr (BN == 192) {
+        // ALU-heavy epilogues get a third epilogue warpgroup (see gemm_threads)
+        static const int eg_env = [] { const char* e = getenv("FB_GEMM_EG"); return e ? atoi(e) : 0; }();
+        // (the coalesced-operand instantiation spills at the 128-register budget of 512 threads: only on request)
+        const bool heavy = p.tma_store == 1 && !coal && (p.act == FB_ACT_GELU || p.aux_op == FB_AUX_MUL_GELU_GRAD);
+        if (eg_env == 3 || (eg_env == 0 && heavy)) {
+          if (coal) return launch_gemm_impl<BN, A_MN, B_MN, true, 2, 3>(ma, mb, md, mpre, p, st);
+          return launch_gemm_impl<BN, A_MN, B_MN, false, 2, 3>(ma, mb, md, mpre, p, st);
+        }
+      }
       if (coal) return launch_gemm_impl<BN, A_MN, B_MN, true, 2>(ma, mb, md, mpre, p, st);
       return launch_gemm_impl<BN, A_MN, B_MN, false, 2>(ma, mb, md, mpre, p, st);
     }
@@ -888,6 +906,15 @@ int gemm(const fb_gemm_args* a, cudaStream_t st) {
     FB_REQUIRE(!a->D_pre && !a->aux && !a->resid && !a->rowmask && !a->drop_pos,
                "fb_gemm: batched mode supports bias/act only");
   int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N, batch_total, split_k);
+  {
+    // GELU / GELU' epilogues are bound by the issue rate of the epilogue warps: 128 x 192 tiles run with three
+    // epilogue warpgroups (launch_gemm), which 128 x 256 tiles cannot (8 chunks do not split three ways and four
+    // groups do not fit the shared-memory budget).  FB_GEMM_EG=2 keeps the two-group kernels everywhere.
+    static const int eg_env = [] { const char* e = getenv("FB_GEMM_EG"); return e ? atoi(e) : 0; }();
+    if (!a->block_n && bn == 256 && eg_env != 2 && a->N % 192 == 0 && batch_total == 1 && split_k == 1 &&
+        !a->a_mn_major && (a->act == FB_ACT_GELU || (a->aux && a->aux_op == FB_AUX_MUL_GELU_GRAD)))
+      bn = 192;
+  }
   FB_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, "fb_gemm: block_n must be 64/128/192/256");
 
   // 2-CTA multicast kernel (see gemm_kernel): big unbatched GEMMs with an even number of M blocks and K-major A

@@ -138,7 +138,7 @@ def test_gemm_batched():
 
 
 @pytest.mark.parametrize("M,N,K,block_n", [(5632, 2048, 320, 256), (5632, 1536, 384, 192), (5600, 1500, 200, 256),
-                                           (11264, 1536, 192, 0)])
+                                           (11264, 1536, 192, 0), (5632, 3072, 256, 0)])
 @pytest.mark.parametrize("b_mn", [False, True])
 def test_gemm_cluster_multicast_path(M, N, K, block_n, b_mn):
     """Shapes with >= 2 x 148 tiles and an even number of 128-row blocks take the 2-CTA cluster kernel (each CTA
@@ -173,3 +173,7 @@ def test_gemm_cluster_multicast_path(M, N, K, block_n, b_mn):
     D2 = torch.empty_like(Db)
     lib.gemm(A, B, D2, b_mn_major=b_mn, bias=bias, act=lib.FB_ACT_GELU, D_pre=Dp, block_n=block_n)
     assert torch.equal(D2, Db)
+    # GELU' x aux epilogue (the dX of the FFN down-projection; 128 x 192 tiles run it with three epilogue warpgroups)
+    refg, _ = _ref(A, B, False, b_mn, aux=aux, aux_op=1)
+    lib.gemm(A, B, Db, b_mn_major=b_mn, aux=aux, aux_op=lib.FB_AUX_MUL_GELU_GRAD, block_n=block_n)
+    assert (Db.float() - refg).abs().max().item() < 3e-2 + tol
