@@ -907,12 +907,14 @@ int gemm(const fb_gemm_args* a, cudaStream_t st) {
                "fb_gemm: batched mode supports bias/act only");
   int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N, batch_total, split_k);
   {
-    // GELU / GELU' epilogues are bound by the issue rate of the epilogue warps: 128 x 192 tiles run with three
-    // epilogue warpgroups (launch_gemm), which 128 x 256 tiles cannot (8 chunks do not split three ways and four
-    // groups do not fit the shared-memory budget).  FB_GEMM_EG=2 keeps the two-group kernels everywhere.
+    // The GELU' x aux epilogue (dX of the FFN down-projection) runs on 128 x 192 tiles with three epilogue warpgroups
+    // (launch_gemm), which 128 x 256 tiles cannot have (8 chunks do not split three ways, four groups do not fit the
+    // shared-memory budget): 202.5 -> 197.6 us at config 2.  The erf-GELU + pre-activation epilogue of the
+    // up-projection measured no gain (194.3 -> 196.3 us: it is not bound by the epilogue warps' issue rate) and keeps
+    // 128 x 256 tiles; FB_GEMM_EG=3 forces the three-group kernels for both, FB_GEMM_EG=2 the two-group ones.
     static const int eg_env = [] { const char* e = getenv("FB_GEMM_EG"); return e ? atoi(e) : 0; }();
     if (!a->block_n && bn == 256 && eg_env != 2 && a->N % 192 == 0 && batch_total == 1 && split_k == 1 &&
-        !a->a_mn_major && (a->act == FB_ACT_GELU || (a->aux && a->aux_op == FB_AUX_MUL_GELU_GRAD)))
+        !a->a_mn_major && ((a->aux && a->aux_op == FB_AUX_MUL_GELU_GRAD) || (eg_env == 3 && a->act == FB_ACT_GELU)))
       bn = 192;
   }
   FB_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, "fb_gemm: block_n must be 64/128/192/256");

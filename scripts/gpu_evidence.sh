@@ -15,8 +15,8 @@ timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --cloc
     --log-file gpurun_out/launches.csv python bench.py --profile-step > gpurun_out/ncu_launch.log 2>&1; echo "ncu launches exit $?"
 python scripts/summarize_launches.py gpurun_out/launches.csv > gpurun_out/step_launches.md 2>/dev/null; head -12 gpurun_out/step_launches.md
 # roofline kernels, one unambiguous capture each (bench.py reads the DRAM bytes from the trimmed CSV)
-timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k regex:"gemm_kernel|attn_fwd|attn_bwd" --launch-skip 13 --launch-count 4 -o gpurun_out/prof_probes -f \
+PROBE_ONCE=1 timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
+    -k regex:"gemm_kernel|attn_fwd|attn_bwd" --launch-skip 1 --launch-count 4 -o gpurun_out/prof_probes -f \
     python scripts/gpu_probe_kernels.py > gpurun_out/ncu_probes.log 2>&1; echo "ncu probes exit $?"
 ncu -i gpurun_out/prof_probes.ncu-rep --page raw --csv > gpurun_out/probes_raw.csv 2>/dev/null
 python scripts/ncu_summary.py --trim gpurun_out/ncu_raw_probes.csv gpurun_out/probes_raw.csv > gpurun_out/ncu_probes.md; cat gpurun_out/ncu_probes.md | cut -c1-200
