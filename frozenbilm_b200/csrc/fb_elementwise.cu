@@ -96,83 +96,59 @@ ln_fwd_kernel(const float* __restrict__ x, int M, const float* __restrict__ gamm
 // flushed with one atomic per column per CTA.  dx is written as fp32 (residual stream) and/or as a bf16
 // copy with the UPSTREAM hidden dropout's backward applied (the operand of the next dX/dW GEMMs).
 // ---------------------------------------------------------------------------------------------
-template <int NV>
-__global__ void __launch_bounds__(256, 2)
+template <int NV, int WPR>
+__global__ void __launch_bounds__(256, WPR == 4 ? 2 : 1)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean_in,
               const float* __restrict__ rstd_in, const float* __restrict__ gamma, int M,
               const uint8_t* __restrict__ rowmask, DropSpec out_drop, DropSpec in_drop, float* __restrict__ dx32,
               __nv_bfloat16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta,
               float* __restrict__ dx16_colsum) {
   pdl_prologue();
-  // TWO warps per row (64 lanes x NV/2 float4 each): halves the per-thread dgamma/dbeta/column-sum accumulators so
-  // that two CTAs (16 warps) fit per SM; the row is streamed twice (second read hits L1/L2).
+  // WPR warps per row (32 WPR lanes x NV/WPR float4 each), persistent CTAs, the row read ONCE: x and dy of the
+  // current row live in registers (reused for xhat and g = dy_eff * gamma), the NEXT row of the group is already in
+  // flight in a second register set while this one is reduced and stored, so HBM keeps streaming across the row
+  // reduction.  WPR = 4 (H a multiple of 512): ~110 registers, two CTAs = 16 warps per SM -- the kernel is bound by
+  // instruction latency (dropout hash + ~25 FP32 operations per float4), not by the second read of the row that the
+  // two-pass version did (measured: 2 warps per row at 255 registers, 8 warps per SM, ran no faster than two-pass).
   constexpr int H = NV * 128;
-  constexpr int NK = NV / 2;
-  __shared__ float red[4][256];
-  __shared__ float rowsum[4][2][2];
+  constexpr int NK = NV / WPR;          // float4 per thread and operand
+  constexpr int LPR = 32 * WPR;         // lanes per row
+  constexpr int GROUPS = 8 / WPR;       // rows per CTA and step
+  static_assert(NV % WPR == 0 && (WPR == 2 || WPR == 4), "row split");
+  __shared__ float red[GROUPS][LPR * 4];
+  __shared__ float rowsum[2][GROUPS][WPR][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = warp >> 1, half = warp & 1;
-  const int l64 = half * 32 + lane;
+  const int grp = warp / WPR, part = warp % WPR;
+  const int lrow = part * 32 + lane;
   float4 ag[NK], ab[NK], ac[NK];
 #pragma unroll
   for (int k = 0; k < NK; ++k) {
     ag[k] = make_float4(0, 0, 0, 0); ab[k] = make_float4(0, 0, 0, 0); ac[k] = make_float4(0, 0, 0, 0);
   }
-  const int row_iters = (M + gridDim.x * 4 - 1) / (gridDim.x * 4);
-  for (int it = 0; it < row_iters; ++it) {
-    const int row = (it * gridDim.x + blockIdx.x) * 4 + pair;
-    const bool live = row < M;                       // both warps of a pair agree; barriers stay uniform
-    {
-      // the rows of the NEXT iteration are pulled into L2 now (one bulk prefetch per row and operand), so that
-      // HBM keeps streaming while this iteration reduces, re-reads and stores: the two-pass structure otherwise
-      // leaves the memory pipe idle about half of the time (measured 3.5 of 6.5 TB/s)
-      const int nrow = ((it + 1) * gridDim.x + blockIdx.x) * 4 + pair;
-      if (half == 0 && lane == 0 && nrow < M) {
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + (long long)nrow * H), "r"(H * 4) : "memory");
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(dy + (long long)nrow * H), "r"(H * 4) : "memory");
-      }
-    }
-    float mean = 0.f, rstd = 0.f, rm = 0.f;
-    const float4* xr = nullptr;
-    const float4* dr = nullptr;
-    float s1 = 0.0f, s2 = 0.0f;
-    if (live) {
-      mean = mean_in[row]; rstd = rstd_in[row];
-      rm = rowmask ? (rowmask[row] ? 1.0f : 0.0f) : 1.0f;
-      xr = reinterpret_cast<const float4*>(x + (long long)row * H);
-      dr = reinterpret_cast<const float4*>(dy + (long long)row * H);
+  const int stride = gridDim.x * GROUPS;
+  float4 xn[NK], dn[NK];
+  auto fetch = [&](int r) {
+    if (r < M) {
+      const float4* xr = reinterpret_cast<const float4*>(x + (long long)r * H);
+      const float4* dr = reinterpret_cast<const float4*>(dy + (long long)r * H);
 #pragma unroll
-      for (int k = 0; k < NK; ++k) {
-        const int c4 = l64 + 64 * k, col = c4 * 4;
-        const float4 xv = __ldg(xr + c4);
-        float4 d = __ldg(dr + c4);
-        if (out_drop.thresh16) {
-          float f[4];
-          drop_factors4(out_drop, (uint32_t)row, col, f);
-          d.x *= f[0]; d.y *= f[1]; d.z *= f[2]; d.w *= f[3];
-        }
-        d.x *= rm; d.y *= rm; d.z *= rm; d.w *= rm;
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + col));
-        const float4 xh = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
-        ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
-        ag[k].x += d.x * xh.x; ag[k].y += d.y * xh.y; ag[k].z += d.z * xh.z; ag[k].w += d.w * xh.w;
-        const float4 g = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
-        s1 += g.x + g.y + g.z + g.w;
-        s2 += g.x * xh.x + g.y * xh.y + g.z * xh.z + g.w * xh.w;
-      }
-      s1 = warp_sum(s1); s2 = warp_sum(s2);
-      if (lane == 0) { rowsum[pair][half][0] = s1; rowsum[pair][half][1] = s2; }
+      for (int k = 0; k < NK; ++k) { xn[k] = __ldg(xr + lrow + LPR * k); dn[k] = __ldg(dr + lrow + LPR * k); }
     }
-    __syncthreads();
-    const float m1 = (rowsum[pair][0][0] + rowsum[pair][1][0]) * (1.0f / H);
-    const float m2 = (rowsum[pair][0][1] + rowsum[pair][1][1]) * (1.0f / H);
-    __syncthreads();
-    if (!live || (!dx32 && !dx16)) continue;
+  };
+  int row = blockIdx.x * GROUPS + grp;
+  fetch(row);
+  for (int it = 0; row < M; row += stride, ++it) {     // the warps of a group share the row: the loop is group-uniform
+    float4 xv[NK], dv[NK];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) { xv[k] = xn[k]; dv[k] = dn[k]; }
+    fetch(row + stride);
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    const float rm = rowmask ? (rowmask[row] ? 1.0f : 0.0f) : 1.0f;
+    float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
     for (int k = 0; k < NK; ++k) {
-      const int c4 = l64 + 64 * k, col = c4 * 4;
-      const float4 xv = __ldg(xr + c4);
-      float4 d = __ldg(dr + c4);
+      const int col = (lrow + LPR * k) * 4;
+      float4 d = dv[k];
       if (out_drop.thresh16) {
         float f[4];
         drop_factors4(out_drop, (uint32_t)row, col, f);
@@ -180,9 +156,29 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
       }
       d.x *= rm; d.y *= rm; d.z *= rm; d.w *= rm;
       const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + col));
-      const float xh[4] = {(xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd};
-      float o[4] = {rstd * (d.x * gm.x - m1 - xh[0] * m2), rstd * (d.y * gm.y - m1 - xh[1] * m2),
-                    rstd * (d.z * gm.z - m1 - xh[2] * m2), rstd * (d.w * gm.w - m1 - xh[3] * m2)};
+      const float4 xh = make_float4((xv[k].x - mean) * rstd, (xv[k].y - mean) * rstd, (xv[k].z - mean) * rstd,
+                                    (xv[k].w - mean) * rstd);
+      ab[k].x += d.x; ab[k].y += d.y; ab[k].z += d.z; ab[k].w += d.w;
+      ag[k].x += d.x * xh.x; ag[k].y += d.y * xh.y; ag[k].z += d.z * xh.z; ag[k].w += d.w * xh.w;
+      const float4 g = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+      s1 += g.x + g.y + g.z + g.w;
+      s2 += g.x * xh.x + g.y * xh.y + g.z * xh.z + g.w * xh.w;
+      xv[k] = xh; dv[k] = g;          // keep xhat and g for the output pass
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    float (*rs)[2] = rowsum[it & 1][grp];              // double-buffered: one barrier per row
+    if (lane == 0) { rs[part][0] = s1; rs[part][1] = s2; }
+    named_bar_sync(1 + grp, LPR);
+    float m1 = 0.0f, m2 = 0.0f;
+#pragma unroll
+    for (int w = 0; w < WPR; ++w) { m1 += rs[w][0]; m2 += rs[w][1]; }
+    m1 *= (1.0f / H); m2 *= (1.0f / H);
+    if (!dx32 && !dx16) continue;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const int col = (lrow + LPR * k) * 4;
+      float o[4] = {rstd * (dv[k].x - m1 - xv[k].x * m2), rstd * (dv[k].y - m1 - xv[k].y * m2),
+                    rstd * (dv[k].z - m1 - xv[k].z * m2), rstd * (dv[k].w - m1 - xv[k].w * m2)};
       if (dx32) *reinterpret_cast<float4*>(dx32 + (long long)row * H + col) = make_float4(o[0], o[1], o[2], o[3]);
       if (dx16) {
         if (in_drop.thresh16) {
@@ -200,7 +196,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
       }
     }
   }
-  // cross-pair reduction of the per-lane column partials: 256 columns (one k of the 64-lane pair) at a time
+  // cross-group reduction of the per-lane column partials: 4 LPR columns (one k of the row group) at a time
 #pragma unroll 1
   for (int pass = 0; pass < 3; ++pass) {
     float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dx16_colsum);
@@ -209,11 +205,16 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const f
     for (int k = 0; k < NK; ++k) {
       const float4 a = pass == 0 ? ag[k] : (pass == 1 ? ab[k] : ac[k]);
       __syncthreads();
-      red[pair][l64 * 4 + 0] = a.x; red[pair][l64 * 4 + 1] = a.y;
-      red[pair][l64 * 4 + 2] = a.z; red[pair][l64 * 4 + 3] = a.w;
+      red[grp][lrow * 4 + 0] = a.x; red[grp][lrow * 4 + 1] = a.y;
+      red[grp][lrow * 4 + 2] = a.z; red[grp][lrow * 4 + 3] = a.w;
       __syncthreads();
-      atomicAdd(dst + k * 256 + threadIdx.x,
-                red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x]);
+#pragma unroll
+      for (int j = 0; j < LPR * 4 / 256; ++j) {
+        float v = 0.0f;
+#pragma unroll
+        for (int gi = 0; gi < GROUPS; ++gi) v += red[gi][j * 256 + threadIdx.x];
+        atomicAdd(dst + k * LPR * 4 + j * 256 + threadIdx.x, v);
+      }
     }
   }
 }
@@ -250,10 +251,18 @@ int layernorm_bwd(const float* dy, const float* x, const float* mean, const floa
                   void* dx16, float* dgamma, float* dbeta, float* dx16_colsum, cudaStream_t st) {
   FB_REQUIRE(dy && x && mean && rstd && gamma && M > 0 && H % 128 == 0, "fb_layernorm_bwd: bad args");
   const DropSpec od = drop_from(out_drop), id = drop_from(in_drop);
-  const int grid = std::max(1, std::min((M + 3) / 4, 2 * num_sms()));
   cudaError_t le = cudaSuccess;
-  FB_DISPATCH_NV(H, (le = launch_pdl(ln_bwd_kernel<NV>, dim3(grid), dim3(256), 0, st, dy, x, mean, rstd, gamma, M, rowmask, od,
-                                     id, dx32, reinterpret_cast<__nv_bfloat16*>(dx16), dgamma, dbeta, dx16_colsum)));
+  if (H % 512 == 0) {
+    // four warps per row, two rows per CTA and step, two persistent CTAs per SM
+    const int grid = std::max(1, std::min((M + 1) / 2, 2 * num_sms()));
+    FB_DISPATCH_NV(H, (le = launch_pdl(ln_bwd_kernel<(NV % 4 == 0 ? NV : 4), 4>, dim3(grid), dim3(256), 0, st, dy, x, mean, rstd,
+                                       gamma, M, rowmask, od, id, dx32, reinterpret_cast<__nv_bfloat16*>(dx16), dgamma,
+                                       dbeta, dx16_colsum)));
+  } else {
+    const int grid = std::max(1, std::min((M + 3) / 4, num_sms()));
+    FB_DISPATCH_NV(H, (le = launch_pdl(ln_bwd_kernel<NV, 2>, dim3(grid), dim3(256), 0, st, dy, x, mean, rstd, gamma, M, rowmask,
+                                       od, id, dx32, reinterpret_cast<__nv_bfloat16*>(dx16), dgamma, dbeta, dx16_colsum)));
+  }
   FB_CHECK_CUDA(le);
   count_launch();
   FB_CHECK_CUDA(cudaGetLastError());

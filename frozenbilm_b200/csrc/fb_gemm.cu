@@ -64,14 +64,25 @@ struct GemmParams {
   const float* resid; long long ld_resid;
   int accumulate;
   int tma_store;   // epilogue stages 128x32 chunks in smem and writes them with cp.async.bulk.tensor stores
+  int m_fast;      // tile order: M block fastest (see decode_tile)
 };
 
 __device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int& split, int& b,
                                             int& mb, int& nb) {
-  nb = tile % p.nblocks;
-  int t = tile / p.nblocks;
-  mb = t % p.mblocks;
-  t /= p.mblocks;
+  int t;
+  if (p.m_fast) {
+    // consecutive tiles (= the CTAs of one wave) share the N block: a B operand that is much larger than L2 (the
+    // 128100-row vocabulary table of the MLM head) is then streamed from HBM once instead of once per M block
+    mb = tile % p.mblocks;
+    t = tile / p.mblocks;
+    nb = t % p.nblocks;
+    t /= p.nblocks;
+  } else {
+    nb = tile % p.nblocks;
+    t = tile / p.nblocks;
+    mb = t % p.mblocks;
+    t /= p.mblocks;
+  }
   b = t % p.batch;   // combined batch index: outer * batch_inner + inner
   split = t / p.batch;
 }
@@ -970,6 +981,13 @@ int gemm(const fb_gemm_args* a, cudaStream_t st) {
   p.aux_op = a->aux ? a->aux_op : FB_AUX_NONE;
   p.resid = a->resid; p.ld_resid = a->ld_resid;
   p.accumulate = (a->accumulate || split_k > 1) ? 1 : 0;
+  {
+    // B far larger than L2 and A small enough to stay there: walk the M blocks of an N block first
+    static const int mf_env = [] { const char* e = getenv("FB_GEMM_MFAST"); return e ? atoi(e) : -1; }();
+    const double a_bytes = 2.0 * a->M * a->K, b_bytes = 2.0 * a->N * a->K;
+    const bool want = batch_total == 1 && !cluster_ok && p.mblocks > 1 && b_bytes > 96e6 && a_bytes < 48e6;
+    p.m_fast = (mf_env >= 0) ? (mf_env && batch_total == 1 && !cluster_ok) : want;
+  }
 
   // coalesced TMA-store epilogue whenever the output is a plain (unbatched, non-accumulating) matrix with
   // 16-byte aligned rows; otherwise the per-thread direct-store path

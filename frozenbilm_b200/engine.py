@@ -694,6 +694,11 @@ class DebertaEngine:
         # ---- head: logits -> t -> LN -> gelu -> dense
         dt32 = ws.rows("bw.dt32", n, H, F32)
         if dlogits is None:
+            # (K = V = 128100 with only 13 x 8 output tiles at config 2: 30 % of the SMs idle.  Splitting K seven ways
+            # measured 731 -> 590 us, but its fp32 atomics sit at the HEAD of the backward chain: the 1e-7 summation-order
+            # noise is amplified by every bf16 operand rounding downstream and the step stops being reproducible run to
+            # run at the 1e-3 level -- not worth 0.2 % of the step.  All other split-K / atomic reductions of the
+            # backward end in terminal gradient buffers.)
             lib.gemm(hs["dlog16"], hs["E"], dt32, b_mn_major=True, K=hs["V"], N=H)
             if torch.is_tensor(scale):
                 dt32.mul_(scale.to(dt32.dtype))         # d(loss) from autograd: a device scalar, never read on the host
