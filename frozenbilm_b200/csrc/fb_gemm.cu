@@ -353,6 +353,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
   uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
   uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+  volatile int* pf_started = reinterpret_cast<volatile int*>(bars + 2 * Cfg::STAGES + 5);   // epilogues started (COAL)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -375,6 +376,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 4 * EG);
     }
+    *pf_started = 0;
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -482,6 +484,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       }
     }
     __syncwarp();
+  } else if (warp == 3) {
+    // ===================== epilogue-operand prefetcher (coalesced-operand instantiation) =====================
+    // The aux / residual rows of a tile are pulled into L2 ahead of the epilogue warps, whose loads are the critical
+    // path of the K = 192 adapter GEMMs (one dependent HBM round trip per 32-column chunk and warp).  Tile `it` is
+    // requested once the epilogue of tile it - 1 has started (a monotonic counter in shared memory written by the
+    // first epilogue warp: no barrier phase can be missed).  Plain per-line L2 prefetches: per-row bulk prefetches
+    // (256 per tile through the TMA unit) could not keep up with 10 us tiles.  A hint only: correctness does not
+    // depend on it and the wait is bounded.
+    if constexpr (COAL) {
+      const bool has_aux = p.aux_op != FB_AUX_NONE, has_res = p.resid != nullptr;
+      int it = 0;
+      for (int tile = tile_first; tile < tile_total; tile += tile_step, ++it) {
+        int split, b, mb, nb;
+        decode_tile_cl<CL>(p, tile, crank, split, b, mb, nb);
+        for (uint32_t spins = 0; spins < (1u << 18) && *pf_started < it; ++spins) __nanosleep(64);
+        if (split != 0) continue;
+        const int n0 = nb * BN;
+        const int ncols = min(BN, p.N - n0);
+        const int rows = min(BM, p.M - mb * BM);
+        if (has_res) {
+          const int lpr = (ncols * 4 + 127) >> 7;                    // 128-byte lines per row segment
+          const char* base = reinterpret_cast<const char*>(p.resid + (long long)mb * BM * p.ld_resid + n0);
+          for (int i = lane; i < rows * lpr; i += 32) {
+            const int r = i / lpr, l = i - r * lpr;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (long long)r * p.ld_resid * 4 + l * 128));
+          }
+        }
+        if (has_aux) {
+          const int lpr = (ncols * 2 + 127) >> 7;
+          const char* base = reinterpret_cast<const char*>(p.aux + (long long)mb * BM * p.ld_aux + n0);
+          for (int i = lane; i < rows * lpr; i += 32) {
+            const int r = i / lpr, l = i - r * lpr;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (long long)r * p.ld_aux * 2 + l * 128));
+          }
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int wq = warp & 3;            // TMEM lane quarter this warp may access
@@ -497,6 +536,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
+      if constexpr (COAL) {
+        if (warp == 4 && lane == 0) *pf_started = it + 1;   // lets the prefetcher warp move on to the next tile
+      }
       const int row = mb * BM + wq * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * Cfg::ACC_STRIDE;
       if (!p.tma_store) {
