@@ -71,12 +71,18 @@ class FeatureShard:
     def save(self, path):
         """One file for the whole feature set (what a dataset preparation step writes once): packed fp16 rows +
         per-video offsets / frame counts, readable with ``FeatureShard.load``."""
-        np.savez(path, shard=self.shard.cpu().numpy(), offsets=self.offsets.cpu().numpy(),
+        np.savez(self._npz_path(path), shard=self.shard.cpu().numpy(), offsets=self.offsets.cpu().numpy(),
                  nframes=self.nframes.cpu().numpy())
+
+    @staticmethod
+    def _npz_path(path):
+        """np.savez appends ".npz" to a suffix-less path; save and load agree on the final name."""
+        path = str(path)
+        return path if path.endswith(".npz") else path + ".npz"
 
     @classmethod
     def load(cls, path, device="cuda"):
-        z = np.load(path)
+        z = np.load(cls._npz_path(path))
         return cls(torch.from_numpy(z["shard"]).to(device), torch.from_numpy(z["offsets"]).to(device),
                    torch.from_numpy(z["nframes"]).to(device))
 

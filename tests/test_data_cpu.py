@@ -74,6 +74,9 @@ def test_feature_shard_packing_and_roundtrip(tmp_path):
     fs.save(p)
     fs2 = FeatureShard.load(p, device="cpu")
     assert torch.equal(fs2.shard, fs.shard) and torch.equal(fs2.offsets, fs.offsets) and torch.equal(fs2.nframes, fs.nframes)
+    # a suffix-less path round-trips too (np.savez appends ".npz")
+    fs.save(tmp_path / "shard2")
+    assert torch.equal(FeatureShard.load(tmp_path / "shard2", device="cpu").shard, fs.shard)
     # the oracle on the packed representation reproduces the per-video rule
     v, l = dor.gather_frames(fs2.shard.numpy(), fs2.offsets.numpy(), fs2.nframes.numpy(), 4)
     assert l.tolist() == [3, 0, 4, 0] and np.array_equal(v[2], arrays[2][[0, 1, 2, 3]].astype(np.float32))
