@@ -510,10 +510,10 @@ def main():
     # projections (8S) in fb_attn_bwd_rel
     kern = {
         "ffn1": ("fb::gemm_kernel<256> FFN up-projection %dx%dx%d (+bias+GELU)" % (T, I, H), 2.0 * T * I * H,
-                 2.0 * (T * H + I * H + (2 if train else 1) * T * I), "gemm_kernel<256, 0, 0, 0, 2>"),
+                 2.0 * (T * H + I * H + (2 if train else 1) * T * I), "gemm_kernel<256, 0, 0, 0, 2"),
         "attn_fwd": ("fb::attn_fwd_kernel (QK^T + c2p + p2c + softmax + PV)", rows * L * H * (4 * L + (8 * S if rel else 0)),
                      2.0 * (4 * T * H) + (2.0 * rows * cfg.num_attention_heads * L * ((L + 127) // 128 * 128) if train else 0),
-                     "attn_fwd_kernel"),
+                     "attn_fwd"),
         "attn_bwd": ("fb::attn_bwd_kernel (dP, dS, dV, dQ, dK incl. positional terms)",
                      rows * L * H * (8 * L + (8 * S if rel else 0)),
                      2.0 * (8 * T * H) + 2.0 * rows * cfg.num_attention_heads * L * ((L + 127) // 128 * 128) * (2 if rel else 1),

@@ -27,8 +27,11 @@ ncu -i gpurun_out/prof_all.ncu-rep --page raw --csv > gpurun_out/all_raw.csv 2>/
 python scripts/ncu_summary.py --distinct --rows --trim gpurun_out/ncu_raw_all_kernels.csv gpurun_out/all_raw.csv > gpurun_out/ncu_all_kernels.md; wc -l gpurun_out/ncu_all_kernels.md
 rm -f gpurun_out/*.ncu-rep gpurun_out/all_raw.csv gpurun_out/probes_raw.csv
 # compute-sanitizer on the hand-rolled synchronisation protocols
-for tool in memcheck racecheck synccheck; do
+# (racecheck takes ~8 GPU-minutes; its findings are analysed in profiles/r2_sanitizer.md -- RACECHECK=1 re-runs it)
+for tool in memcheck synccheck ${RACECHECK:+racecheck}; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 20 python scripts/gpu_sanitize.py > gpurun_out/sanitizer_$tool.log 2>&1
   echo "sanitizer $tool exit $?"; tail -3 gpurun_out/sanitizer_$tool.log
 done
+timeout 100 python scripts/gpu_ln_time.py > gpurun_out/row_kernel_times.log 2>&1; timeout 100 python scripts/gpu_adapter_gemm_time.py >> gpurun_out/row_kernel_times.log 2>&1
+timeout 200 python scripts/gpu_gemm_shapes.py >> gpurun_out/row_kernel_times.log 2>&1; tail -22 gpurun_out/row_kernel_times.log
 du -sh gpurun_out
