@@ -20,7 +20,8 @@ quick = "--quick" in sys.argv
 variants = [("bias+gelu+pre", lambda: lib.gemm(A, W, D, bias=bias, act=lib.FB_ACT_GELU, D_pre=Dp))]
 if not quick:
     variants = [("plain", lambda: lib.gemm(A, W, D)), ("bias", lambda: lib.gemm(A, W, D, bias=bias)),
-                ("bias+gelu", lambda: lib.gemm(A, W, D, bias=bias, act=lib.FB_ACT_GELU))] + variants + \
+                ("bias+gelu", lambda: lib.gemm(A, W, D, bias=bias, act=lib.FB_ACT_GELU)),
+                ("bias+pre (two outputs, no GELU)", lambda: lib.gemm(A, W, D, bias=bias, D_pre=Dp))] + variants + \
                [("ffn2 f32+resid", lambda: lib.gemm(D, W2, D32, bias=resid[0].contiguous(), resid=resid))]
 for name, fn in variants:
     us = t(fn, 3 if quick else 10)
