@@ -185,6 +185,9 @@ def _load(path, exports) -> C.CDLL:
     lib.fb_last_error.restype = C.c_char_p
     lib.fb_abi_version.restype = C.c_int
     lib.fb_launch_count.restype = C.c_longlong
+    if lib.fb_abi_version() != ABI_VERSION:
+        raise FbError(f"{path} has ABI version {lib.fb_abi_version()}, this binding expects {ABI_VERSION}: rebuild it "
+                      "(python -c 'import __graft_entry__ as g; g.build()')")
     for name in exports:
         if name in ("fb_last_error", "fb_abi_version", "fb_launch_count"):
             continue
@@ -220,6 +223,8 @@ def _load(path, exports) -> C.CDLL:
     lib.fb_cross_entropy_f32.argtypes = [vp, ll, i, i, vp, vp, f, vp, ll, f, vp]
     return lib
 
+
+ABI_VERSION = 3   # FB_ABI_VERSION of include/frozenbilm_b200.h this binding (struct layouts, argtypes) was written for
 
 # every symbol include/frozenbilm_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [

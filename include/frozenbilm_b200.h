@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define FB_ABI_VERSION 2
+#define FB_ABI_VERSION 3   /* 3: fb_gemm_args.stride_bias, the *_batched entry points */
 
 const char* fb_last_error(void);
 int fb_abi_version(void);

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(dll, name), f"{name} declared in include/frozenbilm_b200.h but not exported"
     assert sorted(lib.EXPORTS) == declared
     dll.fb_abi_version.restype = ctypes.c_int
-    assert dll.fb_abi_version() == 2
+    assert dll.fb_abi_version() == 3
     # the hardware probe / phase-stamp hooks live only in the test-only debug library
     for name in lib.DEBUG_EXPORTS:
         assert not hasattr(dll, name), f"{name} must not be exported by the product library"
