@@ -190,6 +190,37 @@ def test_edge_cases_masks_and_modes():
         model(video=b["video"].to(DEV))
 
 
+def test_label_count_paths_agree_and_no_labelled_rows():
+    """The head's row count comes from the host when the labels are a host tensor and from a pinned-memory read-back
+    (after the encoder has been queued) when they live on the device: same loss and gradients either way, for the
+    train and the eval path; a batch without any labelled position gives the reference's NaN loss
+    (CrossEntropyLoss over an empty selection, deberta.py:1481-1488) without launching the head."""
+    cfg = CONFIG_TINY
+    P = synth_params(cfg, 5)
+    b = synth_batch(cfg, 3, 40, 6)
+    res = []
+    for on_host in (True, False):
+        model = build(cfg, P).train()
+        lab = b["labels"] if on_host else b["labels"].to(DEV)
+        out = model(labels=lab, **to_dev(b))
+        out["loss"].backward()
+        res.append((out["loss"].item(), torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])))
+        model.eval()
+        with torch.no_grad():
+            le = model(labels=lab, **to_dev(b))["loss"].item()
+        res[-1] += (le,)
+    assert abs(res[0][0] - res[1][0]) <= 1e-6 * abs(res[0][0]) and abs(res[0][2] - res[1][2]) <= 1e-6 * abs(res[0][2])
+    torch.testing.assert_close(res[0][1], res[1][1], rtol=1e-4, atol=1e-7)
+    model = build(cfg, P).train()
+    for lab in (torch.full_like(b["labels"], -100), torch.full_like(b["labels"], -100).to(DEV)):
+        out = model(labels=lab, **to_dev(b))
+        assert torch.isnan(out["loss"]) and not out["loss"].requires_grad
+    # the model is still usable afterwards (no pending forward state was leaked)
+    out = model(labels=b["labels"].to(DEV), **to_dev(b))
+    out["loss"].backward()
+    assert torch.isfinite(out["loss"])
+
+
 def test_train_mode_dropout_is_sane_and_reproducible_in_backward():
     """Train-mode dropout (Philox masks regenerated in the backward): loss stays close to the dropout-free
     loss, gradients are finite, and a second identical step after resetting the seed reproduces them."""
