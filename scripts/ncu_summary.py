@@ -1,7 +1,7 @@
 """Key metrics of `ncu --set full` captures (exported with `ncu -i X.ncu-rep --page raw --csv`) -> markdown.
 
 usage: python scripts/ncu_summary.py [--distinct] [--rows] [--trim out.csv] raw1.csv [raw2.csv ...]
-  --distinct   only the first capture of every kernel name
+  --distinct   one capture per kernel name: its longest launch
   --rows       one kernel per ROW (readable with many kernels); default: one kernel per column
   --trim F     also write the columns bench.py / this script read to F (small enough to commit under profiles/)
 """
@@ -65,14 +65,26 @@ def main():
         keep = [i for i, h in enumerate(hdr) if h in needed]
         if trim and trimmed is None:
             trimmed = [[hdr[i] for i in keep], [units[i] for i in keep]]
-        for r in rows[2:]:
-            if len(r) < len(hdr):
-                continue
+        body = [r for r in rows[2:] if len(r) >= len(hdr)]
+        if distinct:
+            # one capture per kernel name: the LONGEST launch (the step's main instance of that instantiation, not the
+            # small head / embedding calls that happen to come first), in order of first appearance
+            def dur(r):
+                try:
+                    return float(dict(zip(hdr, r))["gpu__time_duration.sum"].replace(",", ""))
+                except (KeyError, ValueError):
+                    return 0.0
+            best, order = {}, []
+            for r in body:
+                name = dict(zip(hdr, r))["Kernel Name"].split("(")[0].replace("void ", "")
+                if name not in best:
+                    order.append(name)
+                if name not in best or dur(r) > dur(best[name]):
+                    best[name] = r
+            body = sorted((best[n] for n in order), key=dur, reverse=True)
+        for r in body:
             d = dict(zip(hdr, r))
             name = d["Kernel Name"].split("(")[0].replace("void ", "")
-            if distinct and name in seen:
-                continue
-            seen.add(name)
             cols.append((name, d, dict(zip(hdr, units))))
             if trimmed is not None:
                 trimmed.append([r[i] for i in keep])
