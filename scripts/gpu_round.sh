@@ -1,7 +1,7 @@
 #!/bin/bash
 # scratch: the command of the most recent gpurun call
 mkdir -p gpurun_out
-timeout 100 python scripts/gpu_probe_kernels.py
-timeout 300 python -m pytest tests/test_attention_bwd_gpu.py -x -q 2>&1 | tail -2
-timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_relpf.json 2> gpurun_out/bench_relpf.err
-cut -c100-330 gpurun_out/bench_relpf.json; tail -2 gpurun_out/bench_relpf.err
+timeout 200 python __graft_entry__.py --smoke 2>&1 | tail -1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
+cut -c100-330 gpurun_out/bench_final.json; tail -2 gpurun_out/bench_final.err
